@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — plane-residual evaluation throughput on the 12-room apartment (BASELINE.json configs[2]).
+
+One "step" = one evaluation of the cuboid objective + gradient sums of all 12 rooms over every point of the
+apartment (nearest-plane assignment, Float residuals, Double reductions; hs_rooms_cuboid_sums), followed at N>1 by
+the all-reduce of the 12 x 24-double records (NCCL, the path's only exchange).  Points are sharded by contiguous
+point range across ranks; total work is fixed => "strong" scaling (use --scaling weak for a fixed
+100 M points per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job points/s with inputs resident
+in HBM; e2e = same metric through the public host-buffer API with the H2D copy of every point and the D2H of the
+record inside the timed region; roofline = 12 B/pt algorithmic bytes / kernel time against the measured HBM peak;
+cpu_baseline = the oracle (C port of the Haskell reference, OpenMP) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROOMS = 12
+PTS_PER_ROOM = 8_333_334  # 12 rooms ~ 100 M points (BASELINE.json configs[2])
+METRIC = "plane_residual_eval_points_per_sec"
+UNIT = "points/s"
+BYTES_PER_POINT = 12.0  # residual+gradient evaluation reads 12 B/pt, writes ~0
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def room_params(n_rooms=N_ROOMS, seed=3):
+    from housescan_b200 import synth
+
+    rng = np.random.default_rng(seed)
+    params = np.zeros((n_rooms, 10))
+    for r, (gx, gz) in enumerate(synth.diagonal_pairs(n_rooms)):
+        params[r, :3] = np.array([6.0 * gx, 0.0, 6.0 * gz]) + rng.uniform(-0.2, 0.2, size=3)
+        params[r, 3:6] = np.array([5.0, 2.6, 4.0]) + rng.uniform(-0.3, 0.3, size=3)
+        params[r, 6:] = synth.quat_from_axis_angle([0, 1, 0], rng.uniform(-3, 3))
+    return params
+
+
+def eval_params(params, seed=33):
+    """the parameters the optimiser would be evaluating: a few mm / mrad away from the generating ones"""
+    rng = np.random.default_rng(seed)
+    p = params.copy()
+    p[:, :6] += rng.normal(0, 0.004, size=(p.shape[0], 6))
+    p[:, 6:] += rng.normal(0, 0.002, size=(p.shape[0], 4))
+    return p
+
+
+def gen_points_torch(torch, dev, params, counts, seed, sigma=0.005):
+    """uniform points on the faces of each room's cuboid + normal noise, generated on the device (float32 AoS)."""
+    from housescan_b200 import synth
+
+    total = int(sum(counts))
+    pad = ((total * 12 + 47) // 48) * 48 // 4 + 16
+    buf = torch.empty(pad, dtype=torch.float32, device=dev)
+    out = buf[: total * 3].view(total, 3)
+    g = torch.Generator(device=dev)
+    o = 0
+    for r, n in enumerate(counts):
+        if n == 0:
+            continue
+        g.manual_seed(seed * 1000 + r)
+        p = params[r]
+        dims = torch.tensor(p[3:6], dtype=torch.float32, device=dev)
+        R = torch.tensor(synth.rot_rows_from_quat(p[6:]), dtype=torch.float32, device=dev)
+        c = torch.tensor(p[:3], dtype=torch.float32, device=dev)
+        a, b, cc = [float(v) for v in p[3:6]]
+        areas = torch.tensor([b * cc, b * cc, a * cc, a * cc, a * b, a * b], dtype=torch.float32, device=dev)
+        CH = 4_000_000
+        for s in range(0, n, CH):
+            m = min(CH, n - s)
+            face = torch.multinomial(areas / areas.sum(), m, replacement=True, generator=g)
+            u = (torch.rand(m, 3, device=dev, generator=g) - 0.5) * dims
+            axis = face // 2
+            sign = 1.0 - 2.0 * (face % 2).float()
+            wall = sign * dims[axis] * 0.5 + torch.randn(m, device=dev, generator=g) * sigma
+            u.scatter_(1, axis[:, None], wall[:, None])
+            out[o + s : o + s + m] = u @ R + c
+        o += n
+    return buf, out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in self.f:
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                util = float(t[8])
+                if util <= 0:
+                    continue
+                sm.append(float(t[1])); mx.append(float(t[2])); pw.append(float(t[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples under load"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle C port; no GHC in this image) on the host cores."""
+    if rank != 0:
+        return
+    import oracle as O
+    from housescan_b200 import synth
+
+    O.build()
+    per_room = args.ref_pts_per_room
+    params = room_params()
+    pe = eval_params(params)
+    rng = np.random.default_rng(3)
+    clouds = [synth.cuboid_room_cloud(per_room, params[r], sigma=0.005, rng=rng)[0] for r in range(N_ROOMS)]
+    n = per_room * N_ROOMS
+
+    def step():
+        for r in range(N_ROOMS):
+            O.cuboid_sums(clouds[r], pe[r])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    cores = O.num_threads()
+    sample = f"{N_ROOMS} rooms x {per_room} pts per step ({n} pts), all 12 records per step, OpenMP {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 geometry / f64 accumulation",
+        "data": "synthetic", "config": {"workload": "12-room grid apartment, cuboid residual+gradient sums per room (BASELINE configs[2]); bounded CPU sample", "rooms": N_ROOMS, "points_per_step": n},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--pts-per-room", type=int, default=PTS_PER_ROOM)
+    ap.add_argument("--ref-pts-per-room", type=int, default=2_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    ap.add_argument("--mode", type=int, default=-1, help="evaluation kernel variant (hs_ctx_set_mode key 0)")
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import housescan_b200 as hb
+    from housescan_b200.rooms import local_room_offsets, shard_range
+
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = hb.Context(local)  # raises HS_ECUDA without an sm_100 device: no fallback
+    if args.mode >= 0:
+        ctx.set_mode(0, args.mode)
+    if args.blocks_per_sm > 0:
+        ctx.set_mode(1, args.blocks_per_sm)
+    # a dedicated non-default stream shared by torch (events, NCCL ordering) and the library (kernels, copies)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- workload: this rank's point range of the concatenated apartment cloud
+    params = room_params()
+    pe = np.ascontiguousarray(eval_params(params))
+    per_room = args.pts_per_room
+    if args.scaling == "weak":
+        n_total = per_room * N_ROOMS * world
+        offs_global = np.arange(N_ROOMS + 1, dtype=np.int64) * per_room * world
+    else:
+        n_total = per_room * N_ROOMS
+        offs_global = np.arange(N_ROOMS + 1, dtype=np.int64) * per_room
+    lo, hi = shard_range(n_total, rank, world)
+    offs = local_room_offsets(offs_global, lo, hi)
+    counts = np.diff(offs).tolist()
+    buf, pts = gen_points_torch(torch, dev, params, counts, seed=3 + rank)
+    n_local = hi - lo
+    cloud = ctx.wrap(buf.data_ptr(), n_local, keepalive=buf)
+    rec = torch.zeros(N_ROOMS * hb.HS_REC, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
+        if world > 1:
+            dist.all_reduce(rec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    # ---- warm-up (>= W steps and >= 0.3 s so clocks settle and the sampler sees load)
+    t_w = time.perf_counter()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    while time.perf_counter() - t_w < 0.3:
+        step()
+        torch.cuda.synchronize()
+
+    # ---- value: K steps, device-timed, max over ranks
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = ctx.launch_count
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = ctx.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_total * args.steps / (ms * 1e-3)
+    rec_host = rec.cpu().numpy().reshape(N_ROOMS, hb.HS_REC).copy()
+
+    # ---- roofline of the dominant kernel: kernel-only launches, same stream, events around the loop
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
+    ev1.record()
+    torch.cuda.synchronize()
+    k_ms = ev0.elapsed_time(ev1) / args.steps
+    peak, peak_src = measured_peak_gbs()
+    achieved = BYTES_PER_POINT * n_local / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+            if int(tj.get("points_per_launch", -1)) == int(n_local):
+                traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- e2e: host buffers in, host record out, every step (public C-ABI path with pinned host memory)
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    host_pts = torch.empty((n_local, 3), dtype=torch.float32, pin_memory=True)
+    host_pts.copy_(pts)
+    host_rec = torch.empty(N_ROOMS * hb.HS_REC, dtype=torch.float64, pin_memory=True)
+    dcloud = ctx.alloc(n_local)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        ctx.write(dcloud, host_pts.data_ptr(), n_local)  # H2D of every point of the step
+        ctx.rooms_cuboid_sums_async(dcloud, offs, pe, rec.data_ptr())
+        if world > 1:
+            dist.all_reduce(rec)
+        host_rec.copy_(rec, non_blocking=True)  # D2H of the result
+        stream.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+    e2e_value = n_total * e2e_steps / (e_ms * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle as O
+
+        O.build()
+        hp = host_pts.numpy()
+        reps, t_cpu, n_cpu = 0, 0.0, 0
+        O.cuboid_sums(hp[: min(n_local, 1_000_000)], pe[0])
+        check = None
+        while t_cpu < 10.0 and reps < 8:
+            t0 = time.perf_counter()
+            for r in range(N_ROOMS):
+                rr = O.cuboid_sums(hp[offs[r] : offs[r + 1]], pe[r])
+                if reps == 0 and r == 0:
+                    check = rr
+            t_cpu += time.perf_counter() - t0
+            n_cpu += n_local
+            reps += 1
+        cpu = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+               "sample": f"{reps} x the full {n_local}-pt workload (12 rooms), OpenMP over all host threads",
+               "parity_room0_counts_equal": bool(np.array_equal(check[16:22], rec_host[0, 16:22])),
+               "parity_room0_f_rel": float(abs(check[0] - rec_host[0, 0]) / check[0])}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32 geometry / f64 accumulation", "data": "synthetic",
+            "config": {"workload": "12-room grid apartment (BASELINE configs[2]): per-room cuboid residual + gradient sums, nearest-plane assignment",
+                       "rooms": N_ROOMS, "points_total": int(n_total), "points_per_gpu": int(n_local), "sharding": f"point-range x{world}",
+                       "l2": "inputs larger than L2 (%.0f MB per GPU per step, L2 126 MB)" % (n_local * 12 / 1e6),
+                       "collective": "nccl all_reduce of 12x24 f64 per step" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 12), "d2h_bytes_per_step": int(N_ROOMS * hb.HS_REC * 8),
+                    "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "k_rooms_cuboid_sums", "kernel_ms": k_ms, "bytes_per_point": BYTES_PER_POINT,
+                         "points_per_launch": int(n_local), "frac_of_nominal_8TBs": achieved / 8000.0},
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+            "gpts_per_s": value / 1e9,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,593 @@
+// C ABI of libhousescan_b200.so (include/housescan_b200.h): context/cloud management and the glue from the
+// reference-shaped entry points to the CUDA launchers.  No CPU fallback: every compute entry needs a live ctx.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../host/hs_host.hpp"
+#include "hs_internal.cuh"
+
+static thread_local std::string g_create_err;
+
+#define HS_LOCK(ctx)                                     \
+  if (!(ctx)) return HS_EINVAL;                          \
+  std::lock_guard<std::mutex> lock__((ctx)->mu);         \
+  if (cudaSetDevice((ctx)->device) != cudaSuccess) { (ctx)->err = "cudaSetDevice failed"; return HS_ECUDA; }
+
+#define HS_FAIL(ctx, code, msg) \
+  do { (ctx)->err = (msg); return (code); } while (0)
+
+int32_t hs_ensure_scratch(hs_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return HS_OK;
+  size_t want = std::max(bytes, static_cast<size_t>(1) << 22);
+  if (ctx->d_scratch) { HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); HS_CUDA_TRY(ctx, cudaFree(ctx->d_scratch)); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0; }
+  HS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_scratch, want));
+  ctx->scratch_bytes = want;
+  return HS_OK;
+}
+int32_t hs_ensure_pinned(hs_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_bytes) return HS_OK;
+  size_t want = std::max(bytes, static_cast<size_t>(1) << 20);
+  if (ctx->h_pinned) { HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); HS_CUDA_TRY(ctx, cudaFreeHost(ctx->h_pinned)); ctx->h_pinned = nullptr; ctx->pinned_bytes = 0; }
+  HS_CUDA_TRY(ctx, cudaMallocHost(&ctx->h_pinned, want));
+  ctx->pinned_bytes = want;
+  return HS_OK;
+}
+
+// Host buffers handed to us by the caller are pageable (Haskell Storable vectors, numpy arrays): stage large copies
+// through the pinned buffer in chunks so the DMA engine runs at PCIe speed; small ones go directly.
+static int32_t copy_h2d(hs_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  HS_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return HS_OK;
+}
+static int32_t copy_d2h_sync(hs_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  HS_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+
+extern "C" {
+
+const char* hs_version(void) { return "housescan_b200 0.1 (sm_100a)"; }
+
+int32_t hs_ctx_create(int32_t device, hs_ctx** out) {
+  if (!out) return HS_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                   " (housescan_b200 has no CPU fallback)";
+    return HS_ECUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return HS_EINVAL; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return HS_ECUDA; }
+  if (prop.major != 10) {
+    g_create_err = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ", this library carries sm_100a code only";
+    return HS_ECUDA;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return HS_ECUDA; }
+  hs_ctx* ctx = new hs_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  auto fail = [&](cudaError_t err) { g_create_err = cudaGetErrorString(err); delete ctx; return HS_ECUDA; };
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+  ctx->stream = ctx->own_stream;
+  if ((e = cudaMalloc(&ctx->d_ticket, 256)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(ctx->d_ticket, 0, 256)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&ctx->d_small, sizeof(double) * (HS_MAX_ROOMS * HS_REC + 64))) != cudaSuccess) return fail(e);
+  if (hs_ensure_scratch(ctx, 1 << 22) != HS_OK || hs_ensure_pinned(ctx, 1 << 20) != HS_OK) { g_create_err = ctx->err; delete ctx; return HS_ECUDA; }
+  *out = ctx;
+  return HS_OK;
+}
+
+int32_t hs_ctx_destroy(hs_ctx* ctx) {
+  if (!ctx) return HS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->d_small) cudaFree(ctx->d_small);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return HS_OK;
+}
+
+const char* hs_last_error(const hs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int32_t hs_ctx_set_stream(hs_ctx* ctx, void* s) {
+  HS_LOCK(ctx);
+  ctx->stream = s ? static_cast<cudaStream_t>(s) : ctx->own_stream;
+  return HS_OK;
+}
+int32_t hs_ctx_sync(hs_ctx* ctx) {
+  HS_LOCK(ctx);
+  HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+int32_t hs_ctx_device(const hs_ctx* ctx) { return ctx ? ctx->device : -1; }
+int32_t hs_ctx_sm_count(const hs_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+int64_t hs_ctx_launch_count(const hs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int32_t hs_ctx_set_mode(hs_ctx* ctx, int32_t key, int32_t value) {
+  if (!ctx || key < 0 || key >= 16) return HS_EINVAL;
+  ctx->modes[key] = value;
+  return HS_OK;
+}
+
+// ---- clouds ----------------------------------------------------------------------------------------------------
+static int32_t cloud_alloc_impl(hs_ctx* ctx, int64_t n, hs_cloud** out) {
+  if (!out || n < 0) HS_FAIL(ctx, HS_EINVAL, "hs_cloud_alloc: bad arguments");
+  hs_cloud* c = new hs_cloud();
+  const size_t bytes = ((static_cast<size_t>(n) * 12 + 47) / 48) * 48 + 64;  // whole 4-point groups + slack
+  cudaError_t e = cudaMalloc(&c->d, bytes);
+  if (e != cudaSuccess) { delete c; ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? HS_ENOMEM : HS_ECUDA; }
+  c->n = n; c->cap = static_cast<int64_t>((bytes - 64) / 12); c->owned = true;
+  *out = c;
+  return HS_OK;
+}
+int32_t hs_cloud_alloc(hs_ctx* ctx, int64_t n, hs_cloud** out) {
+  HS_LOCK(ctx);
+  return cloud_alloc_impl(ctx, n, out);
+}
+int32_t hs_cloud_upload(hs_ctx* ctx, const float* xyz, int64_t n, hs_cloud** out) {
+  HS_LOCK(ctx);
+  if (!xyz && n > 0) HS_FAIL(ctx, HS_EINVAL, "hs_cloud_upload: null points");
+  if (int32_t rc = cloud_alloc_impl(ctx, n, out)) return rc;
+  if (n > 0) {
+    if (int32_t rc = copy_h2d(ctx, (*out)->d, xyz, static_cast<size_t>(n) * 12)) return rc;
+    HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return HS_OK;
+}
+int32_t hs_cloud_wrap_device(hs_ctx* ctx, void* dptr, int64_t n, hs_cloud** out) {
+  HS_LOCK(ctx);
+  if (!out || n < 0 || (!dptr && n > 0)) HS_FAIL(ctx, HS_EINVAL, "hs_cloud_wrap_device: bad arguments");
+  if (reinterpret_cast<uintptr_t>(dptr) & 15) HS_FAIL(ctx, HS_EINVAL, "hs_cloud_wrap_device: pointer must be 16-byte aligned");
+  hs_cloud* c = new hs_cloud();
+  c->d = static_cast<float*>(dptr); c->n = n; c->cap = n; c->owned = false;
+  *out = c;
+  return HS_OK;
+}
+int32_t hs_cloud_write(hs_ctx* ctx, hs_cloud* cloud, const float* xyz, int64_t n) {
+  HS_LOCK(ctx);
+  if (!cloud || n < 0 || n > cloud->cap) HS_FAIL(ctx, HS_EINVAL, "hs_cloud_write: size exceeds capacity");
+  cloud->n = n;
+  if (n > 0) return copy_h2d(ctx, cloud->d, xyz, static_cast<size_t>(n) * 12);
+  return HS_OK;
+}
+int32_t hs_cloud_download(hs_ctx* ctx, const hs_cloud* cloud, float* xyz_out) {
+  HS_LOCK(ctx);
+  if (!cloud || (!xyz_out && cloud->n > 0)) HS_FAIL(ctx, HS_EINVAL, "hs_cloud_download: bad arguments");
+  if (cloud->n == 0) return HS_OK;
+  return copy_d2h_sync(ctx, xyz_out, cloud->d, static_cast<size_t>(cloud->n) * 12);
+}
+int64_t hs_cloud_size(const hs_cloud* c) { return c ? c->n : -1; }
+void* hs_cloud_device_ptr(const hs_cloud* c) { return c ? c->d : nullptr; }
+int32_t hs_cloud_free(hs_ctx* ctx, hs_cloud* cloud) {
+  HS_LOCK(ctx);
+  if (!cloud) return HS_OK;
+  if (cloud->owned && cloud->d) { HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); HS_CUDA_TRY(ctx, cudaFree(cloud->d)); }
+  delete cloud;
+  return HS_OK;
+}
+
+// ---- (1) depth frames ----------------------------------------------------------------------------------------------
+int32_t hs_backproject_ref_dev(hs_ctx* ctx, const void* d_depth, int32_t w, int32_t h, hs_cloud* cloud_out, void* d_mask, int64_t* n_valid) {
+  HS_LOCK(ctx);
+  if (w <= 0 || h <= 0 || !d_depth) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_ref: bad frame");
+  const int64_t npx = static_cast<int64_t>(w) * h;
+  if (cloud_out && cloud_out->cap < npx) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_ref: output cloud smaller than w*h");
+  int64_t* d_n = reinterpret_cast<int64_t*>(ctx->d_small);
+  if (int32_t rc = launch_backproject(ctx, static_cast<const uint16_t*>(d_depth), w, h, cloud_out ? cloud_out->d : nullptr,
+                                      static_cast<uint8_t*>(d_mask), d_n)) return rc;
+  int64_t nv = 0;
+  if (int32_t rc = copy_d2h_sync(ctx, &nv, d_n, sizeof nv)) return rc;
+  if (cloud_out) cloud_out->n = nv;
+  if (n_valid) *n_valid = nv;
+  return HS_OK;
+}
+
+int32_t hs_backproject_ref(hs_ctx* ctx, const uint16_t* depth, int32_t w, int32_t h, float* xyz_out, uint8_t* mask_out, int64_t* n_valid) {
+  if (!ctx) return HS_EINVAL;
+  if (w <= 0 || h <= 0 || !depth) { ctx->err = "hs_backproject_ref: bad frame"; return HS_EINVAL; }
+  const int64_t npx = static_cast<int64_t>(w) * h;
+  hs_cloud* cl = nullptr;
+  uint16_t* d_depth = nullptr;
+  uint8_t* d_mask = nullptr;
+  int32_t rc = HS_OK;
+  {
+    HS_LOCK(ctx);
+    HS_CUDA_TRY(ctx, cudaMalloc(&d_depth, npx * 2 + 16));
+    if (mask_out) HS_CUDA_TRY(ctx, cudaMalloc(&d_mask, npx + 16));
+    rc = copy_h2d(ctx, d_depth, depth, npx * 2);
+  }
+  if (rc == HS_OK && xyz_out) rc = hs_cloud_alloc(ctx, npx, &cl);
+  int64_t nv = 0;
+  if (rc == HS_OK) rc = hs_backproject_ref_dev(ctx, d_depth, w, h, cl, d_mask, &nv);
+  if (rc == HS_OK && xyz_out && nv > 0) { HS_LOCK(ctx); rc = copy_d2h_sync(ctx, xyz_out, cl->d, nv * 12); }
+  if (rc == HS_OK && mask_out) { HS_LOCK(ctx); rc = copy_d2h_sync(ctx, mask_out, d_mask, npx); }
+  if (n_valid) *n_valid = nv;
+  if (cl) hs_cloud_free(ctx, cl);
+  { HS_LOCK(ctx); cudaStreamSynchronize(ctx->stream); cudaFree(d_depth); if (d_mask) cudaFree(d_mask); }
+  return rc;
+}
+
+static int32_t fill_plane_table(hs_ctx* ctx, const float* planes, int32_t K, int32_t maxK, PlaneTable& t, const char* who) {
+  if (!planes || K < 1 || K > maxK) { ctx->err = std::string(who) + ": K out of range"; return HS_EINVAL; }
+  t.K = K;
+  std::memset(t.pl, 0, sizeof t.pl);
+  std::memcpy(t.pl, planes, sizeof(float) * 4 * K);
+  return HS_OK;
+}
+
+int32_t hs_backproject_reduce6x6_dev(hs_ctx* ctx, const void* d_frames, int64_t nframes, int32_t w, int32_t h, const float* intr,
+                                     const float* poses, const float* planes, int32_t K, void* d_out) {
+  HS_LOCK(ctx);
+  if (!d_frames || nframes < 0 || w <= 0 || h <= 0 || !d_out) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_reduce6x6: bad arguments");
+  PlaneTable t;
+  if (int32_t rc = fill_plane_table(ctx, planes, K, 16, t, "hs_backproject_reduce6x6")) return rc;
+  float* d_poses = nullptr;
+  if (poses) {
+    if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(nframes) * 64)) return rc;
+    d_poses = reinterpret_cast<float*>(ctx->d_scratch);
+    if (int32_t rc = copy_h2d(ctx, d_poses, poses, static_cast<size_t>(nframes) * 64)) return rc;
+    HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // caller's pose buffer is not retained
+  }
+  if (nframes == 0) return HS_OK;
+  return launch_reduce6x6(ctx, static_cast<const uint16_t*>(d_frames), nframes, w, h, intr, d_poses, t, static_cast<double*>(d_out));
+}
+
+int32_t hs_backproject_reduce6x6(hs_ctx* ctx, const uint16_t* frames, int64_t nframes, int32_t w, int32_t h, const float* intr,
+                                 const float* poses, const float* planes, int32_t K, double* out) {
+  if (!ctx) return HS_EINVAL;
+  if (!frames || nframes < 0 || w <= 0 || h <= 0 || !out) { ctx->err = "hs_backproject_reduce6x6: bad arguments"; return HS_EINVAL; }
+  if (nframes == 0) return HS_OK;
+  const size_t fbytes = static_cast<size_t>(nframes) * w * h * 2;
+  uint16_t* d_frames = nullptr;
+  double* d_out = nullptr;
+  {
+    HS_LOCK(ctx);
+    HS_CUDA_TRY(ctx, cudaMalloc(&d_frames, fbytes + 16));
+    HS_CUDA_TRY(ctx, cudaMalloc(&d_out, static_cast<size_t>(nframes) * HS_NE * sizeof(double)));
+    if (int32_t rc = copy_h2d(ctx, d_frames, frames, fbytes)) return rc;
+  }
+  int32_t rc = hs_backproject_reduce6x6_dev(ctx, d_frames, nframes, w, h, intr, poses, planes, K, d_out);
+  { HS_LOCK(ctx);
+    if (rc == HS_OK) rc = copy_d2h_sync(ctx, out, d_out, static_cast<size_t>(nframes) * HS_NE * sizeof(double));
+    cudaStreamSynchronize(ctx->stream); cudaFree(d_frames); cudaFree(d_out); }
+  return rc;
+}
+
+// ---- (2) planes --------------------------------------------------------------------------------------------------------
+int32_t hs_plane_assign_dev(hs_ctx* ctx, const hs_cloud* cloud, const float* planes, int32_t K, void* d_assign, void* d_resid) {
+  HS_LOCK(ctx);
+  if (!cloud) HS_FAIL(ctx, HS_EINVAL, "hs_plane_assign: null cloud");
+  PlaneTable t;
+  if (int32_t rc = fill_plane_table(ctx, planes, K, 16, t, "hs_plane_assign")) return rc;
+  if (cloud->n == 0) return HS_OK;
+  return launch_plane_assign(ctx, cloud->d, cloud->n, t, static_cast<uint8_t*>(d_assign), static_cast<float*>(d_resid));
+}
+
+int32_t hs_plane_assign(hs_ctx* ctx, const hs_cloud* cloud, const float* planes, int32_t K, uint8_t* assign_out, float* resid_out) {
+  if (!ctx) return HS_EINVAL;
+  if (!cloud) { ctx->err = "hs_plane_assign: null cloud"; return HS_EINVAL; }
+  const int64_t n = cloud->n;
+  uint8_t* d_a = nullptr;
+  float* d_r = nullptr;
+  {
+    HS_LOCK(ctx);
+    if (assign_out) HS_CUDA_TRY(ctx, cudaMalloc(&d_a, n + 16));
+    if (resid_out) HS_CUDA_TRY(ctx, cudaMalloc(&d_r, n * 4 + 16));
+  }
+  int32_t rc = hs_plane_assign_dev(ctx, cloud, planes, K, d_a, d_r);
+  { HS_LOCK(ctx);
+    if (rc == HS_OK && assign_out && n) rc = copy_d2h_sync(ctx, assign_out, d_a, n);
+    if (rc == HS_OK && resid_out && n) rc = copy_d2h_sync(ctx, resid_out, d_r, n * 4);
+    cudaStreamSynchronize(ctx->stream); if (d_a) cudaFree(d_a); if (d_r) cudaFree(d_r); }
+  return rc;
+}
+
+int32_t hs_planes_from_cuboid(const double params[10], float planes_out[24]) {
+  if (!params || !planes_out) return HS_EINVAL;
+  hs::planes_from_cuboid(params, planes_out);
+  return HS_OK;
+}
+
+static int32_t rooms_sums_enqueue(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, const double* params, double* d_out) {
+  if (!cloud || !room_offsets || !params || nrooms < 1) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: bad arguments");
+  for (int r = 0; r < nrooms; ++r)
+    if (room_offsets[r] > room_offsets[r + 1]) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: room offsets must be non-decreasing");
+  if (room_offsets[0] < 0 || room_offsets[nrooms] > cloud->n) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: room offsets outside the cloud");
+  for (int r0 = 0; r0 < nrooms; r0 += HS_MAX_ROOMS) {
+    RoomTable t;
+    std::memset(&t, 0, sizeof t);
+    t.nrooms = std::min(HS_MAX_ROOMS, nrooms - r0);
+    t.paired = 1;
+    for (int r = 0; r < t.nrooms; ++r) {
+      t.off[r] = room_offsets[r0 + r];
+      float pl[24];
+      hs::planes_from_cuboid(params + 10 * (r0 + r), pl);
+      std::memcpy(t.pl[r], pl, sizeof pl);
+      for (int j = 0; j < 3; ++j)
+        for (int c = 0; c < 3; ++c)
+          if (pl[8 * j + c] != -pl[8 * j + 4 + c]) t.paired = 0;
+    }
+    t.off[t.nrooms] = room_offsets[r0 + t.nrooms];
+    if (int32_t rc = launch_rooms_cuboid_sums(ctx, cloud->d, cloud->n, t, d_out + static_cast<size_t>(r0) * HS_REC)) return rc;
+  }
+  return HS_OK;
+}
+
+int32_t hs_rooms_cuboid_sums_async(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, const double* params, void* d_rec_out) {
+  HS_LOCK(ctx);
+  if (!d_rec_out) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums_async: null output");
+  return rooms_sums_enqueue(ctx, cloud, room_offsets, nrooms, params, static_cast<double*>(d_rec_out));
+}
+
+int32_t hs_rooms_cuboid_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, const double* params, double* rec_out) {
+  HS_LOCK(ctx);
+  if (!rec_out || nrooms < 1) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: bad arguments");
+  double* d_out = ctx->d_small;
+  double* big = nullptr;
+  if (nrooms > HS_MAX_ROOMS) { HS_CUDA_TRY(ctx, cudaMalloc(&big, sizeof(double) * HS_REC * nrooms)); d_out = big; }
+  int32_t rc = rooms_sums_enqueue(ctx, cloud, room_offsets, nrooms, params, d_out);
+  if (rc == HS_OK) rc = copy_d2h_sync(ctx, rec_out, d_out, sizeof(double) * HS_REC * nrooms);
+  if (big) { cudaStreamSynchronize(ctx->stream); cudaFree(big); }
+  return rc;
+}
+
+int32_t hs_cuboid_grad_from_sums(const double params[10], const double rec[HS_REC], double* f, double grad[10], int64_t counts[6]) {
+  if (!params || !rec) return HS_EINVAL;
+  hs::cuboid_grad_from_sums(params, rec, f, grad, counts);
+  return HS_OK;
+}
+
+int32_t hs_cuboid_residual_grad(hs_ctx* ctx, const hs_cloud* cloud, const double params[10], double* f, double grad[10], int64_t counts[6]) {
+  if (!ctx) return HS_EINVAL;
+  if (!cloud || !params) { ctx->err = "hs_cuboid_residual_grad: bad arguments"; return HS_EINVAL; }
+  double rec[HS_REC];
+  const int64_t off[2] = {0, cloud->n};
+  if (int32_t rc = hs_rooms_cuboid_sums(ctx, cloud, off, 1, params, rec)) return rc;
+  hs::cuboid_grad_from_sums(params, rec, f, grad, counts);
+  return HS_OK;
+}
+
+int32_t hs_plane_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, const float* planes, int32_t K, double* out) {
+  HS_LOCK(ctx);
+  if (!cloud || !room_offsets || !planes || !out || nrooms < 1) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: bad arguments");
+  if (room_offsets[0] < 0 || room_offsets[nrooms] > cloud->n) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: room offsets outside the cloud");
+  for (int r = 0; r < nrooms; ++r) {
+    if (room_offsets[r] > room_offsets[r + 1]) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: room offsets must be non-decreasing");
+    PlaneTable t;
+    if (int32_t rc = fill_plane_table(ctx, planes + static_cast<size_t>(r) * K * 4, K, HS_MAX_PLANES, t, "hs_plane_sums")) return rc;
+    double* o = out + static_cast<size_t>(r) * K * HS_PS;
+    if (room_offsets[r] == room_offsets[r + 1]) { std::fill(o, o + K * HS_PS, 0.0); continue; }
+    if (int32_t rc = launch_plane_sums(ctx, cloud->d, room_offsets[r], room_offsets[r + 1], t, ctx->d_small)) return rc;
+    if (int32_t rc = copy_d2h_sync(ctx, o, ctx->d_small, sizeof(double) * K * HS_PS)) return rc;
+  }
+  return HS_OK;
+}
+
+static int32_t mean_impl(hs_ctx* ctx, const hs_cloud* cloud, double mean[3]) {
+  if (cloud->n == 0) HS_FAIL(ctx, HS_EINVAL, "pointMean: empty");  // Main.hs:1597
+  if (int32_t rc = launch_mean(ctx, cloud->d, cloud->n, ctx->d_small)) return rc;
+  double s[3];
+  if (int32_t rc = copy_d2h_sync(ctx, s, ctx->d_small, sizeof s)) return rc;
+  for (int i = 0; i < 3; ++i) mean[i] = s[i] / static_cast<double>(cloud->n);
+  return HS_OK;
+}
+
+int32_t hs_scatter3x3(hs_ctx* ctx, const hs_cloud* cloud, double mean[3], double scatter[6]) {
+  HS_LOCK(ctx);
+  if (!cloud || !mean || !scatter) HS_FAIL(ctx, HS_EINVAL, "hs_scatter3x3: bad arguments");
+  if (int32_t rc = mean_impl(ctx, cloud, mean)) return rc;
+  const float m[3] = {static_cast<float>(mean[0]), static_cast<float>(mean[1]), static_cast<float>(mean[2])};
+  if (int32_t rc = launch_scatter(ctx, cloud->d, cloud->n, m, ctx->d_small)) return rc;
+  return copy_d2h_sync(ctx, scatter, ctx->d_small, 6 * sizeof(double));
+}
+
+int32_t hs_fit_plane(hs_ctx* ctx, const hs_cloud* cloud, float plane_out[4]) {
+  if (!ctx) return HS_EINVAL;
+  if (!cloud || !plane_out) { ctx->err = "hs_fit_plane: bad arguments"; return HS_EINVAL; }
+  if (cloud->n < 3) { ctx->err = "fitPlane: " + std::to_string(cloud->n) + " points given, need at least 3"; return HS_EINVAL; }  // Main.hs:1438
+  double mean[3], sc[6], ev[3], evec[3][3];
+  if (int32_t rc = hs_scatter3x3(ctx, cloud, mean, sc)) return rc;
+  hs::eig_sym3(sc, ev, evec);
+  const hs::V3<float> nrm = hs::unit(hs::V3<float>{static_cast<float>(evec[0][0]), static_cast<float>(evec[1][0]), static_cast<float>(evec[2][0])});
+  const hs::V3<float> m{static_cast<float>(mean[0]), static_cast<float>(mean[1]), static_cast<float>(mean[2])};
+  plane_out[0] = nrm.x; plane_out[1] = nrm.y; plane_out[2] = nrm.z;
+  plane_out[3] = hs::dot(nrm, m) - 0.0f;  // signedDistanceToPlaneEq (PlaneEq n 0) m
+  return HS_OK;
+}
+
+// ---- (3) transforms --------------------------------------------------------------------------------------------------------
+static int32_t check_out(hs_ctx* ctx, const hs_cloud* in, hs_cloud* out, const char* who) {
+  if (!in || !out) { ctx->err = std::string(who) + ": null cloud"; return HS_EINVAL; }
+  if (out->cap < in->n) { ctx->err = std::string(who) + ": output cloud too small"; return HS_EINVAL; }
+  out->n = in->n;
+  return HS_OK;
+}
+int32_t hs_transform(hs_ctx* ctx, const hs_cloud* in, const float m[16], hs_cloud* out) {
+  HS_LOCK(ctx);
+  if (!m) HS_FAIL(ctx, HS_EINVAL, "hs_transform: null matrix");
+  if (int32_t rc = check_out(ctx, in, out, "hs_transform")) return rc;
+  if (m[3] != 0.0f || m[7] != 0.0f || m[11] != 0.0f || m[15] != 1.0f)
+    HS_FAIL(ctx, HS_EINVAL, "projectRoom: last column of the projection is not (0,0,0,1)");  // Main.hs:1725-1728
+  const float R[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]};
+  const float off[3] = {m[12], m[13], m[14]};
+  if (in->n == 0) return HS_OK;
+  return launch_affine(ctx, in->d, out->d, in->n, R, nullptr, off, 1);
+}
+int32_t hs_rotate_around(hs_ctx* ctx, const hs_cloud* in, const float c[3], const float R[9], hs_cloud* out) {
+  HS_LOCK(ctx);
+  if (!c || !R) HS_FAIL(ctx, HS_EINVAL, "hs_rotate_around: null arguments");
+  if (int32_t rc = check_out(ctx, in, out, "hs_rotate_around")) return rc;
+  if (in->n == 0) return HS_OK;
+  return launch_affine(ctx, in->d, out->d, in->n, R, c, c, 0);
+}
+int32_t hs_translate(hs_ctx* ctx, const hs_cloud* in, const float off[3], hs_cloud* out) {
+  HS_LOCK(ctx);
+  if (!off) HS_FAIL(ctx, HS_EINVAL, "hs_translate: null offset");
+  if (int32_t rc = check_out(ctx, in, out, "hs_translate")) return rc;
+  if (in->n == 0) return HS_OK;
+  return launch_affine(ctx, in->d, out->d, in->n, nullptr, nullptr, off, 2);
+}
+int32_t hs_mean_extent(hs_ctx* ctx, const hs_cloud* cloud, double mean[3], float* maxdist) {
+  HS_LOCK(ctx);
+  if (!cloud || !mean) HS_FAIL(ctx, HS_EINVAL, "hs_mean_extent: bad arguments");
+  if (int32_t rc = mean_impl(ctx, cloud, mean)) return rc;
+  if (maxdist) {
+    const float m[3] = {static_cast<float>(mean[0]), static_cast<float>(mean[1]), static_cast<float>(mean[2])};
+    unsigned int* d_bits = reinterpret_cast<unsigned int*>(ctx->d_small);
+    if (int32_t rc = launch_max_nsq(ctx, cloud->d, cloud->n, m, d_bits)) return rc;
+    unsigned int bits = 0;
+    if (int32_t rc = copy_d2h_sync(ctx, &bits, d_bits, sizeof bits)) return rc;
+    float q;
+    std::memcpy(&q, &bits, 4);
+    *maxdist = std::sqrt(q);
+  }
+  return HS_OK;
+}
+int32_t hs_write_ply(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb, const char* path) {
+  if (!ctx) return HS_EINVAL;
+  if (!cloud || !path) { ctx->err = "hs_write_ply: bad arguments"; return HS_EINVAL; }
+  std::vector<float> host(static_cast<size_t>(cloud->n) * 3);
+  if (int32_t rc = hs_cloud_download(ctx, cloud, host.data())) return rc;
+  std::string err;
+  if (!hs::write_ply(path, host.data(), rgb, cloud->n, &err)) { ctx->err = err; return HS_EIO; }
+  return HS_OK;
+}
+static int32_t put_string(const std::string& s, char* buf, int32_t buflen) {
+  if (!buf || buflen <= static_cast<int32_t>(s.size())) return HS_EINVAL;
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return HS_OK;
+}
+int32_t hs_proj_to_string(const float m[16], char* buf, int32_t buflen) { return m ? put_string(hs::proj_to_string(m), buf, buflen) : HS_EINVAL; }
+int32_t hs_proj_to_xf(const float m[16], char* buf, int32_t buflen) { return m ? put_string(hs::proj_to_xf(m), buf, buflen) : HS_EINVAL; }
+
+// ---- (4) connected components ------------------------------------------------------------------------------------------------
+int32_t hs_cc_label_dev(hs_ctx* ctx, const void* d_src, const void* d_dst, int64_t E, uint32_t N, void* d_label) {
+  HS_LOCK(ctx);
+  if (E < 0 || (E > 0 && (!d_src || !d_dst)) || (N > 0 && !d_label)) HS_FAIL(ctx, HS_EINVAL, "hs_cc_label: bad arguments");
+  return launch_cc(ctx, static_cast<const uint32_t*>(d_src), static_cast<const uint32_t*>(d_dst), E, N, static_cast<uint32_t*>(d_label));
+}
+int32_t hs_cc_label(hs_ctx* ctx, const uint32_t* src, const uint32_t* dst, int64_t E, uint32_t N, uint32_t* label_out) {
+  if (!ctx) return HS_EINVAL;
+  if (E < 0 || (E > 0 && (!src || !dst)) || (N > 0 && !label_out)) { ctx->err = "hs_cc_label: bad arguments"; return HS_EINVAL; }
+  for (int64_t e = 0; e < E; ++e)
+    if (src[e] >= N || dst[e] >= N) { ctx->err = "hs_cc_label: vertex id out of range (vertices must be contiguous, GroupConnectedComponents.hs:38)"; return HS_EINVAL; }
+  if (N == 0) return HS_OK;
+  uint32_t *d_s = nullptr, *d_d = nullptr, *d_l = nullptr;
+  {
+    HS_LOCK(ctx);
+    HS_CUDA_TRY(ctx, cudaMalloc(&d_l, static_cast<size_t>(N) * 4));
+    if (E > 0) {
+      HS_CUDA_TRY(ctx, cudaMalloc(&d_s, static_cast<size_t>(E) * 4));
+      HS_CUDA_TRY(ctx, cudaMalloc(&d_d, static_cast<size_t>(E) * 4));
+      if (int32_t rc = copy_h2d(ctx, d_s, src, static_cast<size_t>(E) * 4)) return rc;
+      if (int32_t rc = copy_h2d(ctx, d_d, dst, static_cast<size_t>(E) * 4)) return rc;
+    }
+  }
+  int32_t rc = hs_cc_label_dev(ctx, d_s, d_d, E, N, d_l);
+  { HS_LOCK(ctx);
+    if (rc == HS_OK) rc = copy_d2h_sync(ctx, label_out, d_l, static_cast<size_t>(N) * 4);
+    cudaStreamSynchronize(ctx->stream); cudaFree(d_l); if (d_s) cudaFree(d_s); if (d_d) cudaFree(d_d); }
+  return rc;
+}
+int32_t hs_group_cc(hs_ctx* ctx, const uint32_t* src, const uint32_t* dst, int64_t E, uint32_t N, int32_t* comp_out, int64_t* order_out, int32_t* ncomp_out) {
+  if (!ctx) return HS_EINVAL;
+  if (E == 0) { if (ncomp_out) *ncomp_out = 0; return HS_OK; }  // groupCCContiguous [] = []
+  if (!comp_out || !order_out || !ncomp_out) { ctx->err = "hs_group_cc: null outputs"; return HS_EINVAL; }
+  std::vector<uint32_t> label(N);
+  if (int32_t rc = hs_cc_label(ctx, src, dst, E, N, label.data())) return rc;
+  hs::group_edges_by_label(src, label.data(), E, comp_out, order_out, ncomp_out);
+  return HS_OK;
+}
+
+// ---- VectorUtil ------------------------------------------------------------------------------------------------------------------
+static int32_t kth_impl(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_t k, bool largest, float* out) {
+  if (!cloud || !out || axis < 0 || axis > 2) HS_FAIL(ctx, HS_EINVAL, "hs_kth: bad arguments");
+  if (k < 1) HS_FAIL(ctx, HS_EINVAL, "kLargestBy: k must be >= 1 if the vector is not empty");   // VectorUtil.hs:13
+  if (k > cloud->n) HS_FAIL(ctx, HS_EINVAL, "kLargestBy: k must bet be > length of the vector");  // VectorUtil.hs:14 (sic)
+  float* d_out = reinterpret_cast<float*>(ctx->d_small);
+  if (int32_t rc = launch_kth(ctx, cloud->d, cloud->n, axis, k, largest, d_out)) return rc;
+  return copy_d2h_sync(ctx, out, d_out, sizeof(float));
+}
+int32_t hs_kth_largest(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_t k, float* out) { HS_LOCK(ctx); return kth_impl(ctx, cloud, axis, k, true, out); }
+int32_t hs_kth_smallest(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_t k, float* out) { HS_LOCK(ctx); return kth_impl(ctx, cloud, axis, k, false, out); }
+
+static int32_t filter_impl(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, float limit, const hs_cloud* colors, hs_cloud* out, hs_cloud* colors_out, int64_t* n_out) {
+  if (!cloud || !out || axis < 0 || axis > 2) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: bad arguments");
+  if (out->cap < cloud->n || out->d == cloud->d) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: output cloud too small or aliases the input");
+  if ((colors != nullptr) != (colors_out != nullptr)) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: colors in/out must both be given");
+  if (colors && (colors->n != cloud->n || colors_out->cap < cloud->n)) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: colors must be same size as the cloud");  // Main.hs:114
+  int64_t* d_n = reinterpret_cast<int64_t*>(ctx->d_small);
+  if (int32_t rc = launch_filter_le(ctx, cloud->d, cloud->n, axis, limit, colors ? colors->d : nullptr, out->d, colors_out ? colors_out->d : nullptr, d_n)) return rc;
+  int64_t m = 0;
+  if (int32_t rc = copy_d2h_sync(ctx, &m, d_n, sizeof m)) return rc;
+  out->n = m;
+  if (colors_out) colors_out->n = m;
+  if (n_out) *n_out = m;
+  return HS_OK;
+}
+int32_t hs_filter_le(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, float limit, const hs_cloud* colors, hs_cloud* out, hs_cloud* colors_out, int64_t* n_out) {
+  HS_LOCK(ctx);
+  return filter_impl(ctx, cloud, axis, limit, colors, out, colors_out, n_out);
+}
+int32_t hs_remove_ceiling(hs_ctx* ctx, const hs_cloud* cloud, const hs_cloud* colors, hs_cloud* out, hs_cloud* colors_out, int64_t* n_out, float* y_limit) {
+  HS_LOCK(ctx);
+  if (!cloud || !out) HS_FAIL(ctx, HS_EINVAL, "hs_remove_ceiling: bad arguments");
+  if (cloud->n == 0) { out->n = 0; if (colors_out) colors_out->n = 0; if (n_out) *n_out = 0; return HS_OK; }  // V.null guard, Main.hs:2657
+  float ylim = 0.f;
+  if (int32_t rc = kth_impl(ctx, cloud, 1, cloud->n / 5, true, &ylim)) return rc;  // n < 5 => k = 0 => the reference errors too
+  if (y_limit) *y_limit = ylim;
+  return filter_impl(ctx, cloud, 1, ylim, colors, out, colors_out, n_out);
+}
+
+// ---- host-side module mirrors ------------------------------------------------------------------------------------------------------
+int32_t hs_cuboid_from_params(const double params[10], double out[24]) { if (!params || !out) return HS_EINVAL; hs::cuboid_from_params(params, out); return HS_OK; }
+double hs_errfun(const double corners[24], const double params[10]) { return hs::errfun(corners, params); }
+double hs_errfun_closest(const double* pts, int32_t npts, const double params[10]) { return hs::errfun_closest(pts, npts, params); }
+int32_t hs_guess_dims(const double corners[24], double out[3]) { if (!corners || !out) return HS_EINVAL; hs::guess_dims(corners, out); return HS_OK; }
+
+int32_t hs_fit_cuboid(const double corners[24], int32_t variant, double params_out[10], int32_t* steps, double* err, double* path_out, int32_t path_cap) {
+  if (!corners || !params_out || variant < 0 || variant > 2) return HS_EINVAL;
+  hs::FitResult r = hs::fit_cuboid(corners, variant, path_out != nullptr);
+  for (int i = 0; i < 10; ++i) params_out[i] = r.params[i];
+  if (steps) *steps = r.steps;
+  if (err) *err = r.err;
+  if (path_out && r.path_cols > 0) {
+    const size_t rows = std::min<size_t>(r.path.size() / r.path_cols, static_cast<size_t>(std::max(path_cap, 0)));
+    std::memcpy(path_out, r.path.data(), rows * r.path_cols * sizeof(double));
+  }
+  return HS_OK;
+}
+
+int32_t hs_fit_cuboid_cloud_bfgs(hs_ctx* ctx, const hs_cloud* cloud, const double init[10], int32_t max_iter, double gtol,
+                                 double params_out[10], double* f_out, int32_t* iters, int32_t* evals) {
+  if (!ctx) return HS_EINVAL;
+  if (!cloud || !init || !params_out) { ctx->err = "hs_fit_cuboid_cloud_bfgs: bad arguments"; return HS_EINVAL; }
+  int32_t last_rc = HS_OK;
+  auto eval = [&](const double* x, double* f, double* g) {
+    last_rc = hs_cuboid_residual_grad(ctx, cloud, x, f, g, nullptr);
+    return last_rc == HS_OK;
+  };
+  hs::BFGSResult r = hs::bfgs(eval, init, 10, max_iter > 0 ? max_iter : 200, gtol > 0 ? gtol : 1e-6);
+  if (!r.ok) return last_rc != HS_OK ? last_rc : HS_ECUDA;
+  for (int i = 0; i < 10; ++i) params_out[i] = r.x[i];
+  if (f_out) *f_out = r.f;
+  if (iters) *iters = r.iters;
+  if (evals) *evals = r.evals;
+  return HS_OK;
+}
+
+int32_t hs_lstsq_distances(const int32_t* i_idx, const int32_t* j_idx, const double* d, int32_t m, int32_t n_nodes, double* pos_out, double* rmse_out) {
+  if (!i_idx || !j_idx || !d || !pos_out || !rmse_out || m < 1 || n_nodes < 1) return HS_EINVAL;
+  for (int r = 0; r < m; ++r)
+    if (i_idx[r] < 0 || j_idx[r] < 0 || i_idx[r] >= n_nodes || j_idx[r] >= n_nodes) return HS_EINVAL;
+  return hs::lstsq_distances(i_idx, j_idx, d, m, n_nodes, pos_out, rmse_out) ? HS_OK : HS_ESINGULAR;
+}
+
+}  // extern "C"

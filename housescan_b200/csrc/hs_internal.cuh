@@ -1,0 +1,87 @@
+// Internal declarations shared by the CUDA translation units of libhousescan_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+
+#include "../../include/housescan_b200.h"
+
+#define HS_MAX_ROOMS 32   // rooms per launch (kernel-parameter table); larger calls are chunked
+#define HS_MAX_PLANES 8   // generic planes per room
+#define HS_TPB 256        // threads per block of the streaming kernels
+#define HS_NACC 22        // accumulators of a cuboid-sums record actually reduced (f, Sr[6], B[9], cnt[6])
+
+struct hs_cloud {
+  float* d = nullptr;
+  int64_t n = 0;
+  int64_t cap = 0;  // points the allocation can hold
+  bool owned = true;
+};
+
+struct hs_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // scratch (device) for partial reductions, tickets, small results
+  char* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  unsigned int* d_ticket = nullptr;  // zero between launches
+  double* d_small = nullptr;         // HS_MAX_ROOMS*HS_REC doubles + misc
+  // pinned host staging
+  char* h_pinned = nullptr;
+  size_t pinned_bytes = 0;
+  int modes[16] = {0};
+  std::mutex mu;
+};
+
+enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1 };
+
+// table of rooms passed by value to the evaluation kernels
+struct RoomTable {
+  int32_t nrooms;
+  int32_t paired;                       // 1: planes 2j+1 have exactly the negated normal of 2j (cuboid rooms)
+  int64_t off[HS_MAX_ROOMS + 1];        // point offsets (local to the cloud)
+  float pl[HS_MAX_ROOMS][6][4];         // 6 PlaneEq per room
+};
+
+struct PlaneTable {
+  int32_t K;
+  float pl[16][4];
+};
+
+#define HS_CUDA_TRY(ctx, call)                                                                                  \
+  do {                                                                                                          \
+    cudaError_t e__ = (call);                                                                                   \
+    if (e__ != cudaSuccess) {                                                                                   \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                         \
+      return HS_ECUDA;                                                                                          \
+    }                                                                                                           \
+  } while (0)
+
+// ---- launchers (each enqueues on ctx->stream and bumps ctx->launches) -------------------------------------
+int32_t hs_ensure_scratch(hs_ctx* ctx, size_t bytes);
+int32_t hs_ensure_pinned(hs_ctx* ctx, size_t bytes);
+
+int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);
+int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const PlaneTable& tbl, uint8_t* d_assign, float* d_resid);
+int32_t launch_plane_sums(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out /*K*HS_PS*/);
+
+int32_t launch_affine(hs_ctx* ctx, const float* in, float* out, int64_t n, const float R[9], const float pre[3], const float post[3], int kind);
+int32_t launch_mean(hs_ctx* ctx, const float* xyz, int64_t n, double* d_sum3);
+int32_t launch_max_nsq(hs_ctx* ctx, const float* xyz, int64_t n, const float m[3], unsigned int* d_maxbits);
+int32_t launch_scatter(hs_ctx* ctx, const float* xyz, int64_t n, const float m[3], double* d_sc6);
+
+int32_t launch_backproject(hs_ctx* ctx, const uint16_t* d_depth, int32_t w, int32_t h, float* d_xyz, uint8_t* d_mask, int64_t* d_nvalid);
+int32_t launch_reduce6x6(hs_ctx* ctx, const uint16_t* d_frames, int64_t nframes, int32_t w, int32_t h, const float* intr,
+                         const float* d_poses, const PlaneTable& tbl, double* d_out);
+
+int32_t launch_cc(hs_ctx* ctx, const uint32_t* d_src, const uint32_t* d_dst, int64_t E, uint32_t N, uint32_t* d_label);
+
+int32_t launch_kth(hs_ctx* ctx, const float* xyz, int64_t n, int axis, int64_t k, bool largest, float* d_out);
+int32_t launch_filter_le(hs_ctx* ctx, const float* xyz, int64_t n, int axis, float limit, const float* extra_in, float* out,
+                         float* extra_out, int64_t* d_nout);

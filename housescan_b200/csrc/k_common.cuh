@@ -1,0 +1,118 @@
+// Device helpers shared by the streaming kernels.
+#pragma once
+#include "hs_internal.cuh"
+
+namespace hsk {
+
+// signedDistanceToPlaneEq (Main.hs:1371-1372) in Float with GHC's evaluation order and no FMA contraction:
+//   ((nx*px + ny*py) + nz*pz) - d
+__device__ __forceinline__ float plane_dist(float nx, float ny, float nz, float d, float x, float y, float z) {
+  return __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, x), __fmul_rn(ny, y)), __fmul_rn(nz, z)), d);
+}
+
+// one thread's 4 consecutive AoS points = 3 x float4 (48 B, 16 B aligned)
+struct Pts4 {
+  float x[4], y[4], z[4];
+};
+__device__ __forceinline__ Pts4 load_group(const float* __restrict__ xyz, int64_t g) {
+  const float4* q = reinterpret_cast<const float4*>(xyz) + 3 * g;
+  const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  Pts4 p;
+  p.x[0] = a.x; p.y[0] = a.y; p.z[0] = a.z;
+  p.x[1] = a.w; p.y[1] = b.x; p.z[1] = b.y;
+  p.x[2] = b.z; p.y[2] = b.w; p.z[2] = c.x;
+  p.x[3] = c.y; p.y[3] = c.z; p.z[3] = c.w;
+  return p;
+}
+__device__ __forceinline__ void store_group(float* __restrict__ xyz, int64_t g, const Pts4& p) {
+  float4* q = reinterpret_cast<float4*>(xyz) + 3 * g;
+  q[0] = make_float4(p.x[0], p.y[0], p.z[0], p.x[1]);
+  q[1] = make_float4(p.y[1], p.z[1], p.x[2], p.y[2]);
+  q[2] = make_float4(p.z[2], p.x[3], p.y[3], p.z[3]);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block reduction of N per-thread doubles; thread c < N writes the block total of component c to dst[c].
+template <int N>
+__device__ __forceinline__ void block_sum_store(double (&v)[N], double* dst, double* smem /* [HS_TPB/32][N] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    const double s = warp_sum(v[c]);
+    if (lane == 0) smem[warp * N + c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < HS_TPB / 32; ++w) s += smem[w * N + threadIdx.x];
+    dst[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// "last block done" ticket: returns true in every thread of the block that arrives last.
+__device__ __forceinline__ bool last_block_arrives(unsigned int* ticket, unsigned int nblocks) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == nblocks - 1);
+    if (is_last) *ticket = 0u;  // re-arm for the next launch on this stream
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// Exclusive scan of ntiles unsigned counts in place by ONE block (chunks of HS_TPB with a running carry);
+// returns the grand total in every thread.  Used by the order-preserving compactions (V.filter semantics).
+__device__ __forceinline__ unsigned int block_scan_tiles_exclusive(unsigned int* tile_off, int64_t ntiles) {
+  __shared__ unsigned int wsum[HS_TPB / 32];
+  __shared__ unsigned int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < ntiles; base += HS_TPB) {
+    const int64_t t = base + threadIdx.x;
+    const unsigned int v = t < ntiles ? __ldcg(tile_off + t) : 0u;
+    unsigned int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += u;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned int woff = 0;
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += wsum[w];
+    const unsigned int c0 = carry;
+    if (t < ntiles) tile_off[t] = c0 + woff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == HS_TPB - 1) carry = c0 + woff + incl;
+    __syncthreads();
+  }
+  return carry;
+}
+
+// exclusive prefix of a per-thread count inside the block (raster order of threads); smem wsum[HS_TPB/32]
+__device__ __forceinline__ unsigned int block_exclusive_prefix(unsigned int c, unsigned int* wsum) {
+  unsigned int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += u;
+  }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  unsigned int pos = incl - c;
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) pos += wsum[w];
+  return pos;
+}
+
+}  // namespace hsk

@@ -1,0 +1,298 @@
+// Point-to-plane kernels: assignment (A5), cuboid objective/gradient sums per room (A6), generic per-plane sums (A13 inputs).
+// Reference semantics: signedDistanceToPlaneEq Main.hs:1371-1372; nearest plane = first minimum of |distance|
+// (minimumBy, FitCuboidBFGS.hs:74); cuboid planes from makePlanesFromCuboid Main.hs:1852-1874 (built on the host).
+// All per-point geometry is Float without FMA contraction (bit-exact assignment); all sums are Double.
+#include "k_common.cuh"
+
+namespace hsk {
+
+// ------------------------------------------------------------------------------------------------------------------
+// nearest of 6 planes held in registers; returns plane index, signed residual in r
+// ------------------------------------------------------------------------------------------------------------------
+struct Planes6 {
+  float nx[6], ny[6], nz[6], d[6];
+};
+__device__ __forceinline__ Planes6 load_planes6(const RoomTable& tbl, int r) {
+  Planes6 P;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { P.nx[k] = tbl.pl[r][k][0]; P.ny[k] = tbl.pl[r][k][1]; P.nz[k] = tbl.pl[r][k][2]; P.d[k] = tbl.pl[r][k][3]; }
+  return P;
+}
+__device__ __forceinline__ int nearest6(const Planes6& P, float x, float y, float z, float& r) {
+  float rb = plane_dist(P.nx[0], P.ny[0], P.nz[0], P.d[0], x, y, z);
+  float ab = fabsf(rb);
+  int kb = 0;
+#pragma unroll
+  for (int k = 1; k < 6; ++k) {
+    const float rk = plane_dist(P.nx[k], P.ny[k], P.nz[k], P.d[k], x, y, z);
+    const float ak = fabsf(rk);
+    const bool lt = ak < ab;  // strict: ties keep the lower index
+    ab = lt ? ak : ab;
+    rb = lt ? rk : rb;
+    kb = lt ? k : kb;
+  }
+  r = rb;
+  return kb;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Kernel EXACT (mode 0): every per-point product is formed in Double (exact for Float operands), sums in Double.
+//   acc[0] f = sum r^2; acc[1..6] Sr[k]; acc[7..15] B[j][c] = sum s p_c (s = r on the + wall, -r on the - wall); acc[16..21] counts
+// ------------------------------------------------------------------------------------------------------------------
+struct AccExact {
+  double v[HS_NACC];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < HS_NACC; ++i) v[i] = 0.0;
+  }
+  __device__ __forceinline__ void add(const Planes6& P, float x, float y, float z) {
+    float r;
+    const int k = nearest6(P, x, y, z, r);
+    const double rd = static_cast<double>(r);
+    v[0] = fma(rd, rd, v[0]);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const bool m = (k == q);
+      v[1 + q] += m ? rd : 0.0;
+      v[16 + q] += m ? 1.0 : 0.0;
+    }
+    const double s = (k & 1) ? -rd : rd;
+    const int j = k >> 1;
+    const double xd = x, yd = y, zd = z;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double w = (j == a) ? s : 0.0;
+      v[7 + 3 * a + 0] = fma(w, xd, v[7 + 3 * a + 0]);
+      v[7 + 3 * a + 1] = fma(w, yd, v[7 + 3 * a + 1]);
+      v[7 + 3 * a + 2] = fma(w, zd, v[7 + 3 * a + 2]);
+    }
+  }
+};
+
+// Work split: the cloud is cut into groups of 4 points (48 B); block b owns groups [b*gpb, (b+1)*gpb).  For every room
+// overlapping its range the block reduces one partial record; the block that finishes last sums the partials per room in
+// block order (deterministic for a fixed grid).
+template <class Acc>
+__global__ void __launch_bounds__(HS_TPB, 2)
+k_rooms_cuboid_sums(const float* __restrict__ xyz, int64_t n, const __grid_constant__ RoomTable tbl, int64_t gpb,
+                    double* __restrict__ partials, int* __restrict__ meta, unsigned int* ticket, double* __restrict__ out) {
+  __shared__ double smem[(HS_TPB / 32) * HS_NACC];
+  const int nrooms = tbl.nrooms;
+  const int64_t G = (n + 3) >> 2;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * gpb;
+  const int64_t g1 = min(g0 + gpb, G);
+  const int64_t p0 = g0 * 4, p1 = min(g1 * 4, n);
+  int rfirst = -1, rlast = -2;
+  for (int r = 0; r < nrooms; ++r)
+    if (tbl.off[r] < p1 && tbl.off[r + 1] > p0) { if (rfirst < 0) rfirst = r; rlast = r; }
+  if (threadIdx.x == 0) meta[blockIdx.x] = rfirst;
+
+  for (int r = rfirst; r <= rlast; ++r) {
+    const int64_t lo = max(tbl.off[r], p0), hi = min(tbl.off[r + 1], p1);
+    const Planes6 P = load_planes6(tbl, r);
+    Acc A;
+    A.clear();
+    const int64_t gl = (lo + 3) >> 2, gh = hi >> 2;  // whole groups inside [lo, hi)
+    if (gl <= gh) {
+      // ragged head / tail points (at most 3 each), one per thread
+      const int64_t head_end = gl * 4, tail_begin = gh * 4;
+      const int64_t nh = head_end - lo, nt = hi - tail_begin;
+      if (threadIdx.x < nh) { const int64_t i = lo + threadIdx.x; A.add(P, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+      else if (threadIdx.x >= 32 && threadIdx.x - 32 < nt) { const int64_t i = tail_begin + threadIdx.x - 32; A.add(P, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+      int64_t g = gl + threadIdx.x;
+      for (; g + HS_TPB < gh; g += 2 * HS_TPB) {  // two groups in flight per thread
+        const Pts4 a = load_group(xyz, g), b = load_group(xyz, g + HS_TPB);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) A.add(P, a.x[e], a.y[e], a.z[e]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) A.add(P, b.x[e], b.y[e], b.z[e]);
+      }
+      for (; g < gh; g += HS_TPB) {
+        const Pts4 a = load_group(xyz, g);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) A.add(P, a.x[e], a.y[e], a.z[e]);
+      }
+    } else {
+      // the whole overlap lies inside one group
+      const int64_t i = lo + threadIdx.x;
+      if (i < hi) A.add(P, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    }
+    block_sum_store<HS_NACC>(A.v, partials + (static_cast<int64_t>(blockIdx.x) * nrooms + (r - rfirst)) * HS_NACC, smem);
+  }
+
+  if (!last_block_arrives(ticket, gridDim.x)) return;
+  const int64_t ppb = gpb * 4;
+  for (int o = threadIdx.x; o < nrooms * HS_REC; o += HS_TPB) {
+    const int r = o / HS_REC, c = o % HS_REC;
+    double s = 0.0;
+    if (c < HS_NACC && tbl.off[r + 1] > tbl.off[r]) {
+      const int64_t b_lo = tbl.off[r] / ppb, b_hi = (tbl.off[r + 1] - 1) / ppb;
+      for (int64_t b = b_lo; b <= b_hi; ++b) {
+        const int slot = r - __ldcg(meta + b);
+        s += __ldcg(partials + (b * nrooms + slot) * HS_NACC + c);
+      }
+    }
+    out[o] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// plane assignment, generic K <= 16 planes (A5): writes uint8 index and optionally the Float residual
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearestK(const PlaneTable& t, float x, float y, float z, float& r) {
+  float rb = plane_dist(t.pl[0][0], t.pl[0][1], t.pl[0][2], t.pl[0][3], x, y, z);
+  float ab = fabsf(rb);
+  int kb = 0;
+  for (int k = 1; k < t.K; ++k) {
+    const float rk = plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z);
+    const float ak = fabsf(rk);
+    const bool lt = ak < ab;
+    ab = lt ? ak : ab; rb = lt ? rk : rb; kb = lt ? k : kb;
+  }
+  r = rb;
+  return kb;
+}
+
+__global__ void __launch_bounds__(HS_TPB)
+k_plane_assign(const float* __restrict__ xyz, int64_t n, const __grid_constant__ PlaneTable tbl, uint8_t* __restrict__ assign,
+               float* __restrict__ resid) {
+  const int64_t gfull = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x; g < gfull; g += stride) {
+    const Pts4 p = load_group(xyz, g);
+    float r[4];
+    uchar4 k;
+    k.x = nearestK(tbl, p.x[0], p.y[0], p.z[0], r[0]);
+    k.y = nearestK(tbl, p.x[1], p.y[1], p.z[1], r[1]);
+    k.z = nearestK(tbl, p.x[2], p.y[2], p.z[2], r[2]);
+    k.w = nearestK(tbl, p.x[3], p.y[3], p.z[3], r[3]);
+    if (assign) reinterpret_cast<uchar4*>(assign)[g] = k;
+    if (resid) reinterpret_cast<float4*>(resid)[g] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = gfull * 4 + threadIdx.x;
+    float r;
+    const int k = nearestK(tbl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], r);
+    if (assign) assign[i] = static_cast<uint8_t>(k);
+    if (resid) resid[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// generic per-plane sums over one point range [i0, i1): out[k] = count, sum r, sum r^2, sum p(3), sum r p(3), max|r|
+// (one launch per room; wall-alignment inputs, not the throughput path)
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(HS_TPB)
+k_plane_sums(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid_constant__ PlaneTable tbl,
+             double* __restrict__ partials, unsigned int* ticket, double* __restrict__ out) {
+  __shared__ double smem[(HS_TPB / 32) * 9];
+  __shared__ float smax[HS_TPB / 32];
+  double acc[K][9];
+  float mx[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { mx[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc[k][c] = 0.0; }
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
+  for (int64_t i = i0 + static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x; i < i1; i += stride) {
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    float r;
+    const int kk = nearestK(tbl, x, y, z, r);
+    const double rd = r, xd = x, yd = y, zd = z;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const bool m = (kk == k);
+      const double w = m ? 1.0 : 0.0, wr = m ? rd : 0.0;
+      acc[k][0] += w; acc[k][1] += wr; acc[k][2] = fma(wr, rd, acc[k][2]);
+      acc[k][3] = fma(w, xd, acc[k][3]); acc[k][4] = fma(w, yd, acc[k][4]); acc[k][5] = fma(w, zd, acc[k][5]);
+      acc[k][6] = fma(wr, xd, acc[k][6]); acc[k][7] = fma(wr, yd, acc[k][7]); acc[k][8] = fma(wr, zd, acc[k][8]);
+      mx[k] = m ? fmaxf(mx[k], fabsf(r)) : mx[k];
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    block_sum_store<9>(acc[k], partials + (static_cast<int64_t>(blockIdx.x) * K + k) * HS_PS, smem);
+    float m = mx[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) smax[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < HS_TPB / 32; ++w) t = fmaxf(t, smax[w]);
+      partials[(static_cast<int64_t>(blockIdx.x) * K + k) * HS_PS + 9] = t;
+    }
+    __syncthreads();
+  }
+  if (!last_block_arrives(ticket, gridDim.x)) return;
+  for (int o = threadIdx.x; o < K * HS_PS; o += HS_TPB) {
+    const int c = o % HS_PS;
+    double s = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) {
+      const double v = __ldcg(partials + static_cast<int64_t>(b) * K * HS_PS + o);
+      s = (c == 9) ? fmax(s, v) : s + v;
+    }
+    out[o] = s;
+  }
+}
+
+}  // namespace hsk
+
+// ======================================================== launchers ==================================================
+using namespace hsk;
+
+static int pick_blocks(const hs_ctx* ctx, int64_t work_items, int64_t min_items_per_block, int per_sm) {
+  int64_t nb = static_cast<int64_t>(ctx->sm_count) * per_sm;
+  const int64_t cap = (work_items + min_items_per_block - 1) / min_items_per_block;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  return static_cast<int>(nb);
+}
+
+int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out) {
+  const int64_t G = (n + 3) >> 2;
+  const int per_sm = ctx->modes[HS_MODE_BLOCKS_PER_SM] > 0 ? ctx->modes[HS_MODE_BLOCKS_PER_SM] : 2;
+  const int nb = pick_blocks(ctx, G, 2 * HS_TPB, per_sm);
+  const int64_t gpb = (G + nb - 1) / nb > 0 ? (G + nb - 1) / nb : 1;
+  const size_t need = static_cast<size_t>(nb) * tbl.nrooms * HS_NACC * sizeof(double) + static_cast<size_t>(nb) * sizeof(int) + 64;
+  if (int32_t rc = hs_ensure_scratch(ctx, need)) return rc;
+  double* partials = reinterpret_cast<double*>(ctx->d_scratch);
+  int* meta = reinterpret_cast<int*>(ctx->d_scratch + static_cast<size_t>(nb) * tbl.nrooms * HS_NACC * sizeof(double));
+  k_rooms_cuboid_sums<AccExact><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out);
+  ctx->launches++;
+  HS_CUDA_TRY(ctx, cudaGetLastError());
+  return HS_OK;
+}
+
+int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const PlaneTable& tbl, uint8_t* d_assign, float* d_resid) {
+  const int nb = pick_blocks(ctx, (n + 3) >> 2, HS_TPB, 8);
+  k_plane_assign<<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);
+  ctx->launches++;
+  HS_CUDA_TRY(ctx, cudaGetLastError());
+  return HS_OK;
+}
+
+template <int K>
+static int32_t launch_plane_sums_k(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out) {
+  const int nb = pick_blocks(ctx, i1 - i0, 4 * HS_TPB, 2);
+  if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(nb) * K * HS_PS * sizeof(double))) return rc;
+  k_plane_sums<K><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, i0, i1, tbl, reinterpret_cast<double*>(ctx->d_scratch), ctx->d_ticket, d_out);
+  ctx->launches++;
+  HS_CUDA_TRY(ctx, cudaGetLastError());
+  return HS_OK;
+}
+int32_t launch_plane_sums(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out) {
+  switch (tbl.K) {
+    case 1: return launch_plane_sums_k<1>(ctx, xyz, i0, i1, tbl, d_out);
+    case 2: return launch_plane_sums_k<2>(ctx, xyz, i0, i1, tbl, d_out);
+    case 3: return launch_plane_sums_k<3>(ctx, xyz, i0, i1, tbl, d_out);
+    case 4: return launch_plane_sums_k<4>(ctx, xyz, i0, i1, tbl, d_out);
+    case 5: return launch_plane_sums_k<5>(ctx, xyz, i0, i1, tbl, d_out);
+    case 6: return launch_plane_sums_k<6>(ctx, xyz, i0, i1, tbl, d_out);
+    case 7: return launch_plane_sums_k<7>(ctx, xyz, i0, i1, tbl, d_out);
+    case 8: return launch_plane_sums_k<8>(ctx, xyz, i0, i1, tbl, d_out);
+    default: ctx->err = "hs_plane_sums: K must be in 1..8"; return HS_EINVAL;
+  }
+}

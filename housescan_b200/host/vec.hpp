@@ -1,0 +1,84 @@
+// Host-side vector algebra with the semantics of the reference's `vect` dependency
+// (Data.Vect.Float in Main.hs:39-40, Data.Vect.Double in FitCuboidBFGS.hs:20-21).
+// Row vectors, right multiplication (Main.hs:10).  Every expression keeps Haskell's
+// left-to-right association and is compiled with -ffp-contract=off so that the Float
+// plane equations fed to the GPU are the ones the reference would compute.
+#pragma once
+#include <cmath>
+
+namespace hs {
+
+template <class T> struct V3 {
+  T x, y, z;
+  T operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+template <class T> struct V4 { T x, y, z, w; };
+template <class T> struct M3 {  // rows
+  V3<T> r[3];
+};
+
+template <class T> inline V3<T> operator+(V3<T> a, V3<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <class T> inline V3<T> operator-(V3<T> a, V3<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <class T> inline V3<T> operator*(T s, V3<T> a) { return {s * a.x, s * a.y, s * a.z}; }
+template <class T> inline T dot(V3<T> a, V3<T> b) {
+  T s = a.x * b.x;
+  s = s + a.y * b.y;
+  s = s + a.z * b.z;
+  return s;
+}
+template <class T> inline T dot(V4<T> a, V4<T> b) {
+  T s = a.x * b.x;
+  s = s + a.y * b.y;
+  s = s + a.z * b.z;
+  s = s + a.w * b.w;
+  return s;
+}
+template <class T> inline T norm(V3<T> a) { return std::sqrt(dot(a, a)); }
+template <class T> inline T distance(V3<T> a, V3<T> b) { return norm(a - b); }
+template <class T> inline V3<T> unit(V3<T> a) {  // normalize = (&* (1/norm))
+  T inv = T(1) / norm(a);
+  return {a.x * inv, a.y * inv, a.z * inv};
+}
+template <class T> inline V4<T> unit(V4<T> a) {
+  T inv = T(1) / std::sqrt(dot(a, a));
+  return {a.x * inv, a.y * inv, a.z * inv, a.w * inv};
+}
+template <class T> inline V3<T> cross(V3<T> a, V3<T> b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// v .* M
+template <class T> inline V3<T> rowmul(V3<T> v, const M3<T>& m) {
+  V3<T> c0{m.r[0].x, m.r[1].x, m.r[2].x}, c1{m.r[0].y, m.r[1].y, m.r[2].y}, c2{m.r[0].z, m.r[1].z, m.r[2].z};
+  return {dot(v, c0), dot(v, c1), dot(v, c2)};
+}
+// fromOrtho (rightOrthoU (mkU q)): transpose of the standard unit-quaternion matrix
+template <class T> inline M3<T> rot_from_quat(V4<T> q_raw) {
+  V4<T> q = unit(q_raw);
+  T a = q.x, b = q.y, c = q.z, d = q.w;
+  T two = T(2);
+  // left action matrix L, then R = L^T
+  T l00 = a * a + b * b - c * c - d * d, l01 = two * b * c - two * a * d, l02 = two * b * d + two * a * c;
+  T l10 = two * b * c + two * a * d, l11 = a * a - b * b + c * c - d * d, l12 = two * c * d - two * a * b;
+  T l20 = two * b * d - two * a * c, l21 = two * c * d + two * a * b, l22 = a * a - b * b - c * c + d * d;
+  return M3<T>{{{l00, l10, l20}, {l01, l11, l21}, {l02, l12, l22}}};
+}
+// rotateAround c R p
+template <class T> inline V3<T> rotate_around(V3<T> c, const M3<T>& R, V3<T> p) { return rowmul(p - c, R) + c; }
+
+// PlaneEq n d (Main.hs:1357) and its constructors / movers
+struct PlaneEq {
+  V3<float> n;
+  float d;
+};
+inline PlaneEq mk_plane_eq(V3<float> abc, float d) { return {unit(abc), d / norm(abc)}; }             // Main.hs:1360
+inline PlaneEq rotate_plane_eq_around(V3<float> c, const M3<float>& R, PlaneEq e) {                      // Main.hs:1571
+  V3<float> n2 = rowmul(e.n, R);
+  V3<float> o2 = rotate_around(c, R, e.d * e.n);
+  return mk_plane_eq(n2, dot(o2, n2));
+}
+inline PlaneEq translate_plane_eq(V3<float> off, PlaneEq e) {                                             // Main.hs:1681
+  V3<float> o2 = e.d * e.n + off;
+  return mk_plane_eq(e.n, dot(o2, e.n));
+}
+
+}  // namespace hs

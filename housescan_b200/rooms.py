@@ -1,0 +1,82 @@
+"""Room-level host logic around the GPU reductions: sharding of the concatenated room clouds over ranks and
+the wall-alignment driver of Main.optimizeRoomPositions (Main.hs:2089-2168).
+
+Sharding: contiguous POINT ranges, not rooms, so 12 rooms spread evenly over 8 GPUs; every rank
+reduces one HS_REC record per room over its range and the records are summed (they are plain sums).  The only
+exchange is that all-reduce of nrooms x 24 doubles."""
+from __future__ import annotations
+
+import numpy as np
+
+from .GroupConnectedComponents import groupConnectedComponents
+from .TranslationOptimizer import lstSqDistances
+
+
+def shard_range(n: int, rank: int, world: int, align: int = 4):
+    """Point range [lo, hi) of `rank`; boundaries are multiples of `align` points (48 B = 3 x float4) so every
+    shard starts 16-byte aligned inside the parent buffer."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    lo = min(rank * per, n)
+    hi = min(lo + per, n)
+    return lo, hi
+
+
+def local_room_offsets(room_offsets, lo: int, hi: int) -> np.ndarray:
+    """Room offsets of the global cloud clipped to [lo, hi) and rebased to the shard (rooms outside become empty)."""
+    ro = np.asarray(room_offsets, dtype=np.int64)
+    return (np.clip(ro, lo, hi) - lo).astype(np.int64)
+
+
+X, Y, Z = 0, 1, 2
+SAME = ("Same",)
+
+
+def Opposite(d: float):
+    return ("Opposite", float(d))
+
+
+def optimizeRoomPositions(room_ids, conns, plane_mean, corner_mean, ctx=None):
+    """Main.optimizeRoomPositions (Main.hs:2089-2168) as a pure function.
+
+    room_ids   : room ids in the order of `Map.elems sRooms` (ascending id)
+    conns      : sConnectedWalls, newest first: [(axis, relation, (room1, wall1), (room2, wall2))]
+    plane_mean : (room, wall) -> 3-vector  (reference: mean of the wall's 4 bound corners, Main.hs:1608; at scale:
+                 sum p / count of the wall's inlier points from hs_plane_sums / hs_rooms_cuboid_sums)
+    corner_mean: room -> 3-vector          (reference: mean of the 8 room corners, Main.hs:2183-2184)
+    Returns ({room: translation 3-vector (float32)}, log lines).  Quirks kept: offsets are `o + signum o * wallDistance`;
+    the shift uses the first room OF THE AXIS for every component (Main.hs:2121-2123, 2161); Float arithmetic for the
+    room-centre bookkeeping; lstSqDistances' "rmse" (TranslationOptimizer.hs:70)."""
+    f32 = np.float32
+    cm = {r: np.asarray(corner_mean(r), f32) for r in room_ids}
+    moved = {r: np.zeros(3, f32) for r in room_ids}
+    log = []
+    for axis in (X, Y, Z):
+        desired = []
+        axis_rooms = []
+        for (ax, relation, (r1, w1), (r2, w2)) in conns:
+            if ax != axis:
+                continue
+            pm1, pm2 = np.asarray(plane_mean(r1, w1), f32), np.asarray(plane_mean(r2, w2), f32)
+            o = f32(f32(pm1[axis] - cm[r1][axis]) - f32(pm2[axis] - cm[r2][axis]))  # rooms as captured before the loop (Main.hs:2091)
+            wall_d = f32(relation[1]) if relation[0] == "Opposite" else f32(0)
+            desired.append(((r1, r2), float(f32(o + f32(np.sign(o)) * wall_d))))
+            axis_rooms.append(r1)
+        if not axis_rooms:
+            log.append(f"Don't need to align along {'XYZ'[axis]} axis")
+            continue
+        first_room = axis_rooms[0]
+        comps = groupConnectedComponents(desired, ctx)
+        log.append(f"Aligning the {'XYZ'[axis]} ({len(comps)} components)")
+        for comp in comps:
+            res = lstSqDistances(dict(comp))  # Map.fromList: last duplicate wins
+            if res is None:
+                log.append("WARNING: optimizeRoomPositions singularity error")
+                continue
+            centers, rmse = res
+            log.append(f"Aligned component of {'XYZ'[axis]} axis with RMSE {rmse:.3f}")
+            first_c = cm[first_room][axis]  # the captured firstRoom, not the moved one (Main.hs:2161)
+            for rid in sorted(centers):
+                new_c = f32(f32(centers[rid]) + first_c)
+                moved[rid][axis] = f32(new_c - cm[rid][axis])  # a room is in one component per axis
+    return moved, log

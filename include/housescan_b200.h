@@ -1,0 +1,176 @@
+/* housescan_b200 — C ABI of the B200-native point-cloud path of nh2/housescan.
+ *
+ * This is the drop-in boundary.  The reference has no FFI for this path; the
+ * boundary it does have is the export list of its Haskell helper modules.  Every entry point
+ * below names the reference interface it replaces (file:line under /root/reference/housescan).
+ * A Haskell maintainer binds these with `foreign import ccall safe` (see INTEGRATION.md and
+ * haskell/*.hs); the tests and bench bind the identical symbols through Python ctypes.
+ *
+ * Conventions
+ *   - plain C types only; all functions return int32_t status (HS_OK == 0) unless noted.
+ *   - host buffers are caller-owned and never retained past return.
+ *   - device clouds are opaque handles owned by the ctx, freed with hs_cloud_free.
+ *   - one hs_ctx == one CUDA device + one stream; one in-flight call per ctx (not re-entrant);
+ *     several ctxs (one per GPU, or one per process under torchrun) may coexist.
+ *   - NO CPU FALLBACK: without an sm_100 device hs_ctx_create fails with HS_ECUDA.
+ *   - points are AoS float xyz, 12 B/point, exactly `Vector Vec3` (Main.hs:39-42,120,641).
+ *   - planes are 4 floats nx,ny,nz,d of `PlaneEq` n.x = d, |n| = 1 (Main.hs:1357).
+ *   - 4x4 transforms are row-major, right-multiplied (p' = p .* M), translation in row 3
+ *     (Main.hs:10, :1725-1730).
+ */
+#ifndef HOUSESCAN_B200_H
+#define HOUSESCAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_API __attribute__((visibility("default")))
+
+/* status codes; Haskell shim maps: HS_ECUDA/HS_EIO -> Left String (HoniHelper.hs:25-42),
+ * HS_ESINGULAR -> Nothing (TranslationOptimizer.hs:66, Main.hs:2151), HS_EINVAL -> error "..." */
+enum { HS_OK = 0, HS_EINVAL = 1, HS_ECUDA = 2, HS_ENCCL = 3, HS_ENOMEM = 4, HS_ESINGULAR = 5, HS_EIO = 6 };
+
+typedef struct hs_ctx hs_ctx;
+typedef struct hs_cloud hs_cloud;
+
+#define HS_REC 24 /* doubles per room in a cuboid-sums record (layout in DESIGN.md) */
+#define HS_PS 10  /* doubles per (room, plane) in hs_plane_sums */
+#define HS_NE 29  /* doubles per frame in hs_backproject_reduce6x6: 21 JtJ + 6 Jtr + sum r^2 + count */
+
+/* ---- context ------------------------------------------------------------------------------ */
+HS_API int32_t hs_ctx_create(int32_t device, hs_ctx** out);
+HS_API int32_t hs_ctx_destroy(hs_ctx* ctx);
+HS_API const char* hs_last_error(const hs_ctx* ctx); /* ctx may be NULL: last error of a failed create */
+HS_API int32_t hs_ctx_set_stream(hs_ctx* ctx, void* cuda_stream); /* borrow an external stream (NULL = own) */
+HS_API int32_t hs_ctx_sync(hs_ctx* ctx);
+HS_API int32_t hs_ctx_device(const hs_ctx* ctx);
+HS_API int32_t hs_ctx_sm_count(const hs_ctx* ctx);
+HS_API int64_t hs_ctx_launch_count(const hs_ctx* ctx); /* kernels this ctx has launched so far */
+HS_API int32_t hs_ctx_set_mode(hs_ctx* ctx, int32_t key, int32_t value); /* tuning knobs, see DESIGN.md */
+
+/* ---- clouds: `Cloud.cloudPoints :: Vector Vec3` (Main.hs:117-121) ------------------------- */
+HS_API int32_t hs_cloud_upload(hs_ctx* ctx, const float* xyz_aos, int64_t n, hs_cloud** out);
+HS_API int32_t hs_cloud_alloc(hs_ctx* ctx, int64_t n, hs_cloud** out);
+HS_API int32_t hs_cloud_wrap_device(hs_ctx* ctx, void* device_xyz_aos, int64_t n, hs_cloud** out); /* borrowed, 16 B aligned */
+HS_API int32_t hs_cloud_write(hs_ctx* ctx, hs_cloud* cloud, const float* xyz_aos, int64_t n);    /* async H2D into existing cloud */
+HS_API int32_t hs_cloud_download(hs_ctx* ctx, const hs_cloud* cloud, float* xyz_out);
+HS_API int64_t hs_cloud_size(const hs_cloud* cloud);
+HS_API void* hs_cloud_device_ptr(const hs_cloud* cloud);
+HS_API int32_t hs_cloud_free(hs_ctx* ctx, hs_cloud* cloud);
+
+/* ---- (1) depth frames -> points.  HoniHelper.takeDepthSnapshot frame format (HoniHelper.hs:20,34-36,45-46)
+ *      + Main.addDevicePointCloud (Main.hs:1296-1313): mask d != 0, order-preserving compaction,
+ *      x/10, y/10, d/20 - 30.  xyz_out holds up to w*h points; mask_out w*h bytes (either may be NULL). */
+HS_API int32_t hs_backproject_ref(hs_ctx* ctx, const uint16_t* depth, int32_t w, int32_t h, float* xyz_out,
+                                  uint8_t* mask_out, int64_t* n_valid);
+/* device-resident variant: frame already on the device, cloud_out preallocated with >= w*h points */
+HS_API int32_t hs_backproject_ref_dev(hs_ctx* ctx, const void* d_depth, int32_t w, int32_t h, hs_cloud* cloud_out,
+                                      void* d_mask_or_null, int64_t* n_valid);
+/* fused per-frame back-projection + point-to-plane assignment + 6x6 normal equations (north-star piece (1)+(2);
+ * no reference code).  intr = fx,fy,cx,cy or NULL (=> scalePoints of Main.hs:1311-1313); poses = nframes x 16 or NULL.
+ * out = nframes x HS_NE doubles (host).  frames are host pointers here, device pointers in the _dev variant. */
+HS_API int32_t hs_backproject_reduce6x6(hs_ctx* ctx, const uint16_t* frames, int64_t nframes, int32_t w, int32_t h,
+                                        const float* intr, const float* poses, const float* planes, int32_t K, double* out);
+HS_API int32_t hs_backproject_reduce6x6_dev(hs_ctx* ctx, const void* d_frames, int64_t nframes, int32_t w, int32_t h,
+                                            const float* intr, const float* poses, const float* planes, int32_t K,
+                                            void* d_out);
+
+/* ---- (2) planes: signedDistanceToPlaneEq (Main.hs:1371-1372), first-minimum assignment ------ */
+HS_API int32_t hs_plane_assign(hs_ctx* ctx, const hs_cloud* cloud, const float* planes, int32_t K, uint8_t* assign_out,
+                               float* resid_out_or_null);
+HS_API int32_t hs_plane_assign_dev(hs_ctx* ctx, const hs_cloud* cloud, const float* planes, int32_t K, void* d_assign,
+                                   void* d_resid_or_null);
+/* cuboid params [x,y,z,a,b,c,q1..q4] (FitCuboidBFGS.hs:99) -> 6 PlaneEq in Float, order +x -x +y -y +z -z
+ * (Main.hs:1831-1836 + makePlanesFromCuboid Main.hs:1852-1874).  Host arithmetic, no device needed. */
+HS_API int32_t hs_planes_from_cuboid(const double params[10], float planes_out[24]);
+/* objective + gradient of the cuboid over a whole cloud: f = sum r_i^2 over nearest-plane residuals,
+ * grad = d f / d params, counts = inliers per plane.  Generalises errfun/errfunClosestCenter
+ * (FitCuboidBFGS.hs:51-76) from 8 corners to the room cloud. */
+HS_API int32_t hs_cuboid_residual_grad(hs_ctx* ctx, const hs_cloud* cloud, const double params[10], double* f,
+                                       double grad[10], int64_t counts[6]);
+/* raw per-room reductions: rooms are contiguous point ranges [room_offsets[r], room_offsets[r+1]) of `cloud`,
+ * each with its own cuboid.  rec_out = nrooms x HS_REC doubles.  Additive across point shards / GPUs. */
+HS_API int32_t hs_rooms_cuboid_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms,
+                                    const double* params, double* rec_out);
+/* same, enqueued on the ctx stream with the result left in device memory (nrooms x HS_REC doubles). */
+HS_API int32_t hs_rooms_cuboid_sums_async(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets,
+                                          int32_t nrooms, const double* params, void* d_rec_out);
+/* host chain rule: (params, summed record) -> f, grad, counts */
+HS_API int32_t hs_cuboid_grad_from_sums(const double params[10], const double rec[HS_REC], double* f, double grad[10],
+                                        int64_t counts[6]);
+/* generic K planes per room: out[room][k] = count, sum r, sum r^2, sum p (3), sum r p (3), max|r|.
+ * Feeds the wall offsets of optimizeRoomPositions (Main.hs:2111-2118, 2188-2190) from points instead of 4+8 corners. */
+HS_API int32_t hs_plane_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms,
+                             const float* planes, int32_t K, double* out);
+/* fitPlane's per-point part (Main.hs:1436-1450): mean (Double accumulation, returned also rounded to Float),
+ * scatter of Float-centred points in Double: xx,xy,xz,yy,yz,zz. */
+HS_API int32_t hs_scatter3x3(hs_ctx* ctx, const hs_cloud* cloud, double mean[3], double scatter[6]);
+/* fitPlane complete: smallest eigenvector (host Jacobi) -> PlaneEq; sign as LAPACK leaves it is arbitrary. */
+HS_API int32_t hs_fit_plane(hs_ctx* ctx, const hs_cloud* cloud, float plane_out[4]);
+
+/* ---- (3) rigid transforms + export -------------------------------------------------------- */
+/* projectRoom's cloud part: translateCloud off . rotateCloudAround zero R (Main.hs:1716,1725-1730).
+ * HS_EINVAL if the last column of m is not exactly (0,0,0,1) (the reference pattern-fails).  in == out allowed. */
+HS_API int32_t hs_transform(hs_ctx* ctx, const hs_cloud* cloud_in, const float m_rowmajor[16], hs_cloud* cloud_out);
+/* rotateCloudAround c R (Main.hs:1657-1659, 1582-1583) and translateCloud (Main.hs:1697-1699) */
+HS_API int32_t hs_rotate_around(hs_ctx* ctx, const hs_cloud* cloud_in, const float center[3], const float R_rowmajor[9],
+                                hs_cloud* cloud_out);
+HS_API int32_t hs_translate(hs_ctx* ctx, const hs_cloud* cloud_in, const float off[3], hs_cloud* cloud_out);
+/* pointMean / cloudMean (Main.hs:1596-1605) with Double accumulation + max distance to the Float-rounded mean (Main.hs:1527) */
+HS_API int32_t hs_mean_extent(hs_ctx* ctx, const hs_cloud* cloud, double mean[3], float* maxdist);
+/* full-resolution export (README.md:16 step 4; replaces the external plyxform / pcl_transform_point_cloud of
+ * Main.hs:2311-2313): binary little-endian PLY, float x y z [+ uchar red green blue]. */
+HS_API int32_t hs_write_ply(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb_or_null, const char* path);
+/* roomProjectionToString / roomProjectionToXfFormat (Main.hs:2271-2302); buf receives a NUL-terminated string */
+HS_API int32_t hs_proj_to_string(const float m_rowmajor[16], char* buf, int32_t buflen);
+HS_API int32_t hs_proj_to_xf(const float m_rowmajor[16], char* buf, int32_t buflen);
+
+/* ---- (4) connected components: GroupConnectedComponents.groupCCContiguous on dense ids
+ *      (GroupConnectedComponents.hs:39-54); label = minimum vertex id of the component ------ */
+HS_API int32_t hs_cc_label(hs_ctx* ctx, const uint32_t* src, const uint32_t* dst, int64_t E, uint32_t N,
+                           uint32_t* label_out);
+HS_API int32_t hs_cc_label_dev(hs_ctx* ctx, const void* d_src, const void* d_dst, int64_t E, uint32_t N, void* d_label);
+
+/* ---- VectorUtil.kthLargestBy / kthSmallestBy on Float keys (VectorUtil.hs:11-19), removeCeiling (Main.hs:2643-2664) */
+/* keys read from the cloud at component `axis` (0,1,2).  k is 1-based; k<1 or k>n -> HS_EINVAL with the reference's message. */
+HS_API int32_t hs_kth_largest(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_t k, float* out);
+HS_API int32_t hs_kth_smallest(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_t k, float* out);
+/* order-preserving V.filter ((<= limit) . component axis).  `colors` (the ManyColors Vector Vec3 of Main.hs:112-115, same
+ * length as the cloud) is filtered by the same predicate on the POINTS (V.ifilter, Main.hs:2664) when given. */
+HS_API int32_t hs_filter_le(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, float limit, const hs_cloud* colors_or_null,
+                            hs_cloud* cloud_out, hs_cloud* colors_out_or_null, int64_t* n_out);
+HS_API int32_t hs_remove_ceiling(hs_ctx* ctx, const hs_cloud* cloud, const hs_cloud* colors_or_null, hs_cloud* cloud_out,
+                                 hs_cloud* colors_out_or_null, int64_t* n_out, float* y_limit);
+
+/* ---- host-side mirrors of the Haskell modules (C++ in housescan_b200/host, exported flat for FFI/tests) ---- */
+/* FitCuboidBFGS.cuboidFromParams / errfun (FitCuboidBFGS.hs:51-112), 8 corners x 3 doubles */
+HS_API int32_t hs_cuboid_from_params(const double params[10], double corners_out[24]);
+HS_API double hs_errfun(const double corners[24], const double params[10]);
+HS_API double hs_errfun_closest(const double* pts, int32_t npts, const double params[10]);
+HS_API int32_t hs_guess_dims(const double corners[24], double out[3]);
+/* fitCuboid / fitCuboidFromCenter / fitCuboidFromCenterFirst (FitCuboidBFGS.hs:172-233): Nelder-Mead simplex
+ * (GSL nmsimplex2 semantics), tol 1e-8, maxit 2000.  path_out may be NULL; else rows x (3 + nparams) doubles, up to path_cap rows. */
+HS_API int32_t hs_fit_cuboid(const double corners[24], int32_t variant /*0 fitCuboid,1 FromCenter,2 FromCenterFirst*/,
+                             double params_out[10], int32_t* steps, double* err, double* path_out, int32_t path_cap);
+/* north-star addition: BFGS over the whole cloud using hs_cuboid_residual_grad on the GPU */
+HS_API int32_t hs_fit_cuboid_cloud_bfgs(hs_ctx* ctx, const hs_cloud* cloud, const double init[10], int32_t max_iter,
+                                        double gtol, double params_out[10], double* f_out, int32_t* iters,
+                                        int32_t* evals);
+/* TranslationOptimizer.lstSqDistancesI (TranslationOptimizer.hs:48-72) on bijected indices; HS_ESINGULAR => Nothing */
+HS_API int32_t hs_lstsq_distances(const int32_t* i_idx, const int32_t* j_idx, const double* d, int32_t m, int32_t n_nodes,
+                                  double* pos_out, double* rmse_out);
+/* GroupConnectedComponents.groupConnectedComponents (GroupConnectedComponents.hs:16-32) on already-bijected edges:
+ * comp_out[e] = component index (ascending min vertex), order_out = edge indices grouped by component in the
+ * reference's output order (reverse input order inside a component).  Labels computed on the GPU. */
+HS_API int32_t hs_group_cc(hs_ctx* ctx, const uint32_t* src, const uint32_t* dst, int64_t E, uint32_t N,
+                           int32_t* comp_out, int64_t* order_out, int32_t* ncomp_out);
+
+HS_API const char* hs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,410 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for indices / masks / labels / Float geometry; Double sums within the tolerance written in each test
+(the north-star bar is 1e-6 relative; measured agreement is far tighter and asserted as such)."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle as O
+from housescan_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b, scale=None):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    s = np.maximum(np.abs(b), 1e-300) if scale is None else np.maximum(np.asarray(scale, float), 1e-300)
+    return float(np.max(np.abs(a - b) / s))
+
+
+@pytest.fixture(scope="module")
+def c1():
+    """config 1: one 640x480 frame of a cuboid room -> reference back-projection -> room cloud in its own frame."""
+    depth = synth.render_depth_frame()
+    return depth
+
+
+@pytest.fixture(scope="module")
+def room_small():
+    params = synth.C1_PARAMS.copy()
+    xyz, face = synth.cuboid_room_cloud(307_200, params, sigma=0.005, seed=11)
+    return xyz, params
+
+
+# ------------------------------------------------------------------ (1) back-projection
+@pytest.mark.parametrize("w,h", [(640, 480), (64, 48), (37, 5), (1, 1)])
+def test_backproject_mask_and_points_bit_exact(ctx, w, h):
+    rng = np.random.default_rng(w * 1000 + h)
+    depth = rng.integers(0, 65536, size=(h, w), dtype=np.uint16)
+    depth[rng.random((h, w)) < 0.3] = 0
+    xyz_o, mask_o = O.backproject_ref(depth, w, h)
+    xyz_g, mask_g = ctx.backproject_ref(depth, w, h)
+    assert np.array_equal(mask_g, mask_o)
+    assert xyz_g.shape == xyz_o.shape
+    assert np.array_equal(xyz_g.view(np.uint32), xyz_o.view(np.uint32))
+
+
+def test_backproject_all_invalid_and_all_valid(ctx):
+    z = np.zeros((48, 64), np.uint16)
+    xyz, mask = ctx.backproject_ref(z, 64, 48)
+    assert xyz.shape == (0, 3) and mask.sum() == 0
+    f = np.full((48, 64), 65535, np.uint16)
+    xyz, mask = ctx.backproject_ref(f, 64, 48)
+    xo, mo = O.backproject_ref(f, 64, 48)
+    assert np.array_equal(xyz.view(np.uint32), xo.view(np.uint32)) and mask.all()
+
+
+def test_backproject_every_depth_value_divides_exactly(ctx):
+    """d/20 - 30 for every uint16 and x/10 for every column index: IEEE division on the device == host."""
+    depth = np.arange(65536, dtype=np.uint16).reshape(16, 4096)
+    xg, mg = ctx.backproject_ref(depth, 4096, 16)
+    xo, mo = O.backproject_ref(depth, 4096, 16)
+    assert np.array_equal(mg, mo) and np.array_equal(xg.view(np.uint32), xo.view(np.uint32))
+
+
+def test_config1_frame(ctx, c1):
+    xyz_o, mask_o = O.backproject_ref(c1, 640, 480)
+    xyz_g, mask_g = ctx.backproject_ref(c1, 640, 480)
+    assert np.array_equal(mask_g, mask_o) and np.array_equal(xyz_g.view(np.uint32), xyz_o.view(np.uint32))
+    assert 0.97 < mask_g.mean() < 0.99  # 2 % invalid pixels
+
+
+# ------------------------------------------------------------------ (2) planes
+@pytest.mark.parametrize("n", [307_200, 1, 3, 4, 5, 1023, 4097])
+def test_plane_assign_bit_exact(ctx, room_small, n):
+    xyz, params = room_small
+    xyz = xyz[:n]
+    planes = O.planes_from_cuboid(params)
+    cl = ctx.upload(xyz)
+    a_g, r_g = ctx.plane_assign(cl, planes)
+    a_o, r_o = O.plane_assign(xyz, planes)
+    assert np.array_equal(a_g, a_o)
+    assert np.array_equal(r_g.view(np.uint32), r_o.view(np.uint32))
+
+
+def test_plane_assign_ties_pick_lowest_index(ctx):
+    """points on the bisector planes of an axis-aligned unit cube: exact Float ties -> first minimum"""
+    params = np.array([0, 0, 0, 2, 2, 2, 1, 0, 0, 0], float)
+    planes = O.planes_from_cuboid(params)
+    g = np.linspace(-1, 1, 9, dtype=np.float32)
+    xyz = np.array([[x, y, z] for x in g for y in g for z in g], np.float32)
+    a_g, _ = ctx.plane_assign(ctx.upload(xyz), planes)
+    a_o, _ = O.plane_assign(xyz, planes)
+    assert np.array_equal(a_g, a_o)
+    assert a_g[np.all(xyz == 0, axis=1)][0] == 0  # centre: six-way tie -> plane 0
+
+
+def test_plane_assign_generic_k(ctx):
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(size=(50_000, 3)).astype(np.float32) * 3
+    for K in (1, 2, 7, 16):
+        pl = np.stack([O.mk_plane_eq(rng.normal(size=3), rng.normal()) for _ in range(K)])
+        a_g, r_g = ctx.plane_assign(ctx.upload(xyz), pl)
+        a_o, r_o = O.plane_assign(xyz, pl)
+        assert np.array_equal(a_g, a_o) and np.array_equal(r_g.view(np.uint32), r_o.view(np.uint32))
+
+
+def test_cuboid_sums_config1(ctx, room_small):
+    xyz, params = room_small
+    cl = ctx.upload(xyz)
+    rec_g = ctx.rooms_cuboid_sums(cl, [0, len(xyz)], params[None])[0]
+    rec_o = O.cuboid_sums(xyz, params)
+    assert np.array_equal(rec_g[16:22], rec_o[16:22])  # counts exact
+    scale = np.abs(rec_o).copy()
+    scale[1:7] = np.maximum(scale[1:7], np.sqrt(rec_o[0] * rec_o[16:22]))  # sum r vs sqrt(N sum r^2)
+    scale[7:16] = np.maximum(scale[7:16], 1.0)
+    assert _rel(rec_g[:22], rec_o[:22], scale[:22]) < 1e-11
+
+
+@pytest.mark.parametrize("perturb", [0.0, 0.05])
+def test_cuboid_residual_grad_config1(ctx, room_small, perturb):
+    """f, gradient (10) and counts (6) vs the oracle's direct per-point Double accumulation.
+    Tolerance: 1e-9 of the gradient's magnitude sum (north-star bar: 1e-6)."""
+    xyz, params = room_small
+    rng = np.random.default_rng(3)
+    p = params + perturb * rng.normal(size=10)
+    cl = ctx.upload(xyz)
+    f_g, g_g, c_g = ctx.cuboid_residual_grad(cl, p)
+    f_o, g_o, c_o, gs = O.cuboid_residual_grad(xyz, p)
+    assert np.array_equal(c_g, c_o)
+    assert abs(f_g - f_o) <= 1e-12 * f_o
+    assert _rel(g_g, g_o, gs) < 1e-9
+
+
+def test_cuboid_gradient_matches_finite_differences(ctx, room_small):
+    """fixed-assignment finite differences of the oracle objective in Double (self-check of the chain rule)."""
+    xyz, params = room_small
+    p = params + 0.02 * np.random.default_rng(1).normal(size=10)
+    cl = ctx.upload(xyz[:50_000])
+    f0, g, _ = ctx.cuboid_residual_grad(cl, p)
+    pts = xyz[:50_000].astype(np.float64)
+    a0, _ = O.plane_assign(xyz[:50_000], O.planes_from_cuboid(p))
+
+    def fobj(q):
+        R = synth.rot_rows_from_quat(q[6:])
+        j, sg = a0 >> 1, np.where(a0 & 1, -1.0, 1.0)
+        r = sg * np.einsum("ij,ij->i", pts - q[:3], R[j]) - q[3:6][j] / 2
+        return float(np.sum(r * r))
+
+    for m in range(10):
+        h = 1e-6
+        e = np.zeros(10)
+        e[m] = h
+        fd = (fobj(p + e) - fobj(p - e)) / (2 * h)
+        assert abs(fd - g[m]) <= 1e-4 * abs(g[m]) + 5e-4 * abs(f0), (m, fd, g[m])  # Float residuals vs the Double model
+
+
+def test_rooms_sums_ragged_rooms(ctx):
+    """several rooms with offsets that are not multiples of 4, an empty room, points outside every room"""
+    rng = np.random.default_rng(9)
+    sizes = [1, 0, 5, 1023, 4096, 7, 20_001, 3]
+    params = np.stack([np.concatenate([rng.normal(size=3), rng.uniform(1, 5, 3), rng.normal(size=4)]) for _ in sizes])
+    clouds = [synth.cuboid_room_cloud(s, params[i], sigma=0.01, rng=rng)[0] for i, s in enumerate(sizes)]
+    lead, trail = rng.normal(size=(6, 3)).astype(np.float32), rng.normal(size=(9, 3)).astype(np.float32)
+    xyz = np.concatenate([lead] + clouds + [trail])
+    offs = np.concatenate([[0], np.cumsum(sizes)]) + 6
+    rec_g = ctx.rooms_cuboid_sums(ctx.upload(xyz), offs, params)
+    for r, s in enumerate(sizes):
+        rec_o = O.cuboid_sums(xyz[offs[r] : offs[r + 1]], params[r])
+        assert np.array_equal(rec_g[r, 16:22], rec_o[16:22]), r
+        assert np.allclose(rec_g[r, :16], rec_o[:16], rtol=1e-11, atol=1e-11 * max(1.0, np.abs(rec_o[:16]).max())), r
+        assert rec_g[r, 22] == 0 and rec_g[r, 23] == 0
+
+
+def test_rooms_sums_many_rooms_chunked(ctx):
+    """more rooms than one launch's table (HS_MAX_ROOMS = 32) + a multi-block cloud"""
+    rng = np.random.default_rng(10)
+    nrooms = 40
+    sizes = rng.integers(1000, 40_000, size=nrooms)
+    params = np.stack([np.concatenate([rng.normal(size=3), rng.uniform(1, 5, 3), rng.normal(size=4)]) for _ in sizes])
+    xyz = np.concatenate([synth.cuboid_room_cloud(int(s), params[i], sigma=0.01, rng=rng)[0] for i, s in enumerate(sizes)])
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    rec_g = ctx.rooms_cuboid_sums(ctx.upload(xyz), offs, params)
+    for r in (0, 13, 31, 32, 39):
+        rec_o = O.cuboid_sums(xyz[offs[r] : offs[r + 1]], params[r])
+        assert np.array_equal(rec_g[r, 16:22], rec_o[16:22])
+        assert np.allclose(rec_g[r, :16], rec_o[:16], rtol=1e-11, atol=1e-10)
+
+
+def test_rooms_sums_additive_over_point_shards(ctx, room_small):
+    """size-independent property used by the multi-GPU path: records of point shards add up to the whole"""
+    from housescan_b200.rooms import local_room_offsets, shard_range
+
+    xyz, params = room_small
+    n = len(xyz)
+    offs = np.array([0, 100_003, n])
+    pp = np.stack([params, params + 0.01])
+    whole = ctx.rooms_cuboid_sums(ctx.upload(xyz), offs, pp)
+    acc = np.zeros_like(whole)
+    for rank in range(3):
+        lo, hi = shard_range(n, rank, 3)
+        acc += ctx.rooms_cuboid_sums(ctx.upload(xyz[lo:hi]), local_room_offsets(offs, lo, hi), pp)
+    assert np.array_equal(acc[:, 16:22], whole[:, 16:22])
+    assert np.allclose(acc, whole, rtol=1e-12, atol=1e-9)
+
+
+def test_plane_sums_generic(ctx, room_small):
+    xyz, params = room_small
+    offs = np.array([0, 100_000, 100_000, len(xyz)])
+    planes = np.stack([O.planes_from_cuboid(params)] * 3)
+    out_g = ctx.plane_sums(ctx.upload(xyz), offs, planes, 6)
+    out_o = O.plane_sums(xyz, offs, planes, 6)
+    assert np.array_equal(out_g[..., 0], out_o[..., 0])
+    assert np.array_equal(out_g[..., 9], out_o[..., 9])  # max |r| exact
+    assert np.allclose(out_g, out_o, rtol=1e-11, atol=1e-9)
+
+
+def test_scatter_and_fit_plane(ctx):
+    rng = np.random.default_rng(2)
+    n_true = np.array([0.3, -0.5, 0.81])
+    n_true /= np.linalg.norm(n_true)
+    basis = np.linalg.svd(n_true[None])[2][1:]
+    pts = (rng.uniform(-3, 3, size=(200_000, 2)) @ basis + 1.7 * n_true + rng.normal(0, 0.004, size=(200_000, 1)) * n_true).astype(np.float32)
+    cl = ctx.upload(pts)
+    mean_g, sc_g = ctx.scatter3x3(cl)
+    m_o, sc_o = O.scatter3x3(pts, mean_mode=1)
+    assert np.array_equal(mean_g.astype(np.float32), m_o)
+    assert np.allclose(sc_g, sc_o, rtol=1e-12, atol=1e-9)
+    eq = ctx.fit_plane(cl)
+    eq_o = O.fit_plane(pts, mean_mode=1)
+    s = 1.0 if np.dot(eq[:3], eq_o[:3]) > 0 else -1.0  # eigenvector sign is arbitrary (LAPACK)
+    assert np.allclose(s * eq, eq_o, atol=2e-6)
+    assert abs(abs(np.dot(eq[:3], n_true)) - 1) < 1e-5 and abs(abs(eq[3]) - 1.7) < 1e-3
+    with pytest.raises(Exception, match="need at least 3"):
+        ctx.fit_plane(ctx.upload(pts[:2]))
+
+
+# ------------------------------------------------------------------ (3) transforms
+@pytest.mark.parametrize("n", [100_003, 1, 4, 7])
+def test_rigid_transforms_bit_exact(ctx, n):
+    rng = np.random.default_rng(n)
+    xyz = (rng.normal(size=(n, 3)) * 4).astype(np.float32)
+    R = O.rot_matrix3([1, 2, 3], 0.7, np.float32)
+    c = np.array([0.5, -1.25, 2.0], np.float32)
+    cl = ctx.upload(xyz)
+    out = ctx.rotate_around(cl, c, R).download()
+    assert np.array_equal(out.view(np.uint32), O.rotate_cloud_around(xyz, c, R).view(np.uint32))
+    out = ctx.translate(cl, c).download()
+    assert np.array_equal(out.view(np.uint32), O.translate_cloud(xyz, c).view(np.uint32))
+    M = O.proj_translate4([6, 0, -3], O.proj_rotate_around(c, R, O.proj_identity()))
+    out = ctx.transform(cl, M).download()
+    assert np.array_equal(out.view(np.uint32), O.project_cloud(xyz, M).view(np.uint32))
+
+
+def test_transform_rejects_projective_last_column(ctx):
+    M = np.eye(4, dtype=np.float32)
+    M[0, 3] = 0.5
+    cl = ctx.upload(np.zeros((4, 3), np.float32))
+    with pytest.raises(Exception, match="last column"):
+        ctx.transform(cl, M)
+
+
+def test_proj_replay_equivalence_on_gpu(ctx):
+    """projTest..projTest5 (Main.hs:2543-2616): replaying the accumulated roomProj on the fresh cloud coincides with
+    the incrementally transformed cloud (Float tolerance: the two paths round differently)."""
+    rng = np.random.default_rng(4)
+    xyz = (rng.uniform(0, 5, size=(20_000, 3))).astype(np.float32)
+    cl = ctx.upload(xyz)
+    Rx90 = O.rot_matrix3([1, 0, 0], math.radians(90), np.float32)
+    mean, _ = ctx.mean_extent(ctx.translate(cl, [6, 0, 0]))
+    m = mean.astype(np.float32)
+    inc = ctx.rotate_around(ctx.translate(cl, [6, 0, 0]), m, Rx90).download()
+    proj = O.proj_rotate_around(m, Rx90, O.proj_translate4([6, 0, 0], O.proj_identity()))
+    rep = ctx.transform(cl, proj).download()
+    assert np.allclose(inc, rep, atol=5e-5)
+
+
+def test_mean_extent(ctx):
+    rng = np.random.default_rng(6)
+    xyz = (rng.uniform(1, 6, size=(300_001, 3))).astype(np.float32)
+    mean, md = ctx.mean_extent(ctx.upload(xyz))
+    mo = O.point_mean_f64(xyz)
+    assert np.allclose(mean, mo, rtol=1e-13)
+    assert md == np.float32(O.max_distance(xyz, mo.astype(np.float32)))
+    # the reference's sequential Float fold drifts from this by ~1e-5 at this size (SURVEY §7 hard part 2)
+    assert np.allclose(O.point_mean_f32seq(xyz), mean, rtol=1e-3)
+    with pytest.raises(Exception, match="pointMean: empty"):
+        ctx.mean_extent(ctx.upload(np.zeros((0, 3), np.float32)))
+
+
+def test_write_ply_roundtrip(ctx, tmp_path):
+    rng = np.random.default_rng(7)
+    xyz = rng.normal(size=(1001, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, size=(1001, 3), dtype=np.uint8)
+    for colors in (None, rgb):
+        path = str(tmp_path / "room.ply")
+        ctx.write_ply(ctx.upload(xyz), path, colors)
+        raw = open(path, "rb").read()
+        head, body = raw.split(b"end_header\n", 1)
+        assert b"format binary_little_endian 1.0" in head and b"element vertex 1001" in head
+        if colors is None:
+            assert np.array_equal(np.frombuffer(body, np.float32).reshape(-1, 3), xyz)
+        else:
+            rec = np.frombuffer(body, np.dtype([("p", "<f4", 3), ("c", "u1", 3)]))
+            assert np.array_equal(rec["p"], xyz) and np.array_equal(rec["c"], rgb)
+
+
+# ------------------------------------------------------------------ (4) connected components
+def test_cc_labels_voxel_building_bit_exact(ctx):
+    src, dst, n, _ = synth.voxel_building_graph()
+    lab_g = ctx.cc_label(src, dst, n)
+    lab_o = O.cc_label(src, dst, n)
+    assert np.array_equal(lab_g, lab_o)
+    assert np.all(lab_g <= np.arange(n)) and np.array_equal(lab_g[lab_g], lab_g)  # canonical min-index, idempotent
+
+
+def test_cc_labels_random_graphs_and_edge_cases(ctx):
+    rng = np.random.default_rng(8)
+    for n, e in [(1, 0), (10, 0), (2, 1), (1000, 300), (1000, 5000), (200_000, 150_000)]:
+        src = rng.integers(0, n, size=e).astype(np.uint32)
+        dst = rng.integers(0, n, size=e).astype(np.uint32)
+        assert np.array_equal(ctx.cc_label(src, dst, n), O.cc_label(src, dst, n))
+    # one long chain (worst case for pointer jumping), self loops, duplicate edges
+    n = 100_000
+    src = np.arange(n - 1, dtype=np.uint32)[::-1].copy()
+    dst = src + 1
+    assert np.all(ctx.cc_label(src, dst, n) == 0)
+    src = np.array([3, 3, 5, 5, 7], np.uint32)
+    dst = np.array([3, 4, 4, 4, 7], np.uint32)
+    assert np.array_equal(ctx.cc_label(src, dst, 9), O.cc_label(src, dst, 9))
+    with pytest.raises(Exception, match="out of range"):
+        ctx.cc_label(np.array([9], np.uint32), np.array([0], np.uint32), 9)
+
+
+def test_group_connected_components_matches_reference_order(ctx):
+    from housescan_b200.GroupConnectedComponents import groupConnectedComponents
+
+    rng = np.random.default_rng(12)
+    names = [f"room{i}" for i in range(14)]
+    for _ in range(20):
+        m = int(rng.integers(1, 25))
+        edges = [((names[int(rng.integers(14))], names[int(rng.integers(14))]), float(rng.normal())) for _ in range(m)]
+        assert groupConnectedComponents(edges, ctx) == O.group_connected_components(edges)
+    assert groupConnectedComponents([], ctx) == []
+
+
+# ------------------------------------------------------------------ VectorUtil / removeCeiling
+def test_kth_and_remove_ceiling(ctx):
+    rng = np.random.default_rng(13)
+    n = 250_007
+    xyz = rng.normal(size=(n, 3)).astype(np.float32) * 2
+    xyz[rng.integers(0, n, 5000), 1] = np.float32(1.5)  # heavy ties around the cut
+    xyz[:10, 1] = [0.0, -0.0, 1e-30, -1e-30, 3e38, -3e38, 1.5, 1.5, 1.5, 1.5]
+    cl = ctx.upload(xyz)
+    for k in (1, 2, n // 5, n // 2, n - 1, n):
+        assert ctx.kth_largest(cl, 1, k) == O.kth_largest(xyz[:, 1], k), k
+        assert ctx.kth_smallest(cl, 2, k) == np.sort(xyz[:, 2])[k - 1], k
+    with pytest.raises(Exception, match="k must be >= 1"):
+        ctx.kth_largest(cl, 1, 0)
+    with pytest.raises(Exception, match="length of the vector"):
+        ctx.kth_largest(cl, 1, n + 1)
+    colors = rng.random((n, 3)).astype(np.float32)
+    out, cout, ylim = ctx.remove_ceiling(cl, ctx.upload(colors))
+    keep_o, col_o = O.remove_ceiling(xyz, None)[0], colors[xyz[:, 1] <= O.kth_largest(xyz[:, 1], n // 5)]
+    assert ylim == O.kth_largest(xyz[:, 1], n // 5)
+    assert np.array_equal(out.download().view(np.uint32), keep_o.view(np.uint32))
+    assert np.array_equal(cout.download(), col_o)
+    assert len(out) >= n - (n // 5 - 1)  # ties at the limit are kept: removes at most k-1 points
+    o2, _, _ = ctx.remove_ceiling(ctx.upload(np.zeros((0, 3), np.float32)))
+    assert len(o2) == 0
+    with pytest.raises(Exception, match="k must be >= 1"):  # n < 5 => k = 0: the reference errors as well
+        ctx.remove_ceiling(ctx.upload(xyz[:4]))
+
+
+def test_filter_le_order_preserving(ctx):
+    rng = np.random.default_rng(14)
+    for n in (1, 5, 1024, 1025, 70_001):
+        xyz = rng.normal(size=(n, 3)).astype(np.float32)
+        for axis, lim in ((0, 0.0), (2, -5.0), (1, 5.0)):
+            out, _ = ctx.filter_le(ctx.upload(xyz), axis, lim)
+            assert np.array_equal(out.download(), O.filter_le(xyz, axis, lim)[0])
+
+
+# ------------------------------------------------------------------ A4 fused per-frame normal equations
+@pytest.mark.parametrize("use_intr,use_pose", [(False, False), (True, True), (True, False)])
+def test_backproject_reduce6x6(ctx, use_intr, use_pose):
+    frames, poses = synth.depth_stream(3, 160, 120)
+    intr = (synth.KINFU_INTR * 0.25).astype(np.float32) if use_intr else None
+    planes = O.planes_from_cuboid(synth.C1_PARAMS) if use_intr else np.stack(
+        [O.mk_plane_eq([0, 0, 1], 40.0), O.mk_plane_eq([1, 0, 0], 3.0), O.mk_plane_eq([0, 1, 0], 2.0), O.mk_plane_eq([0.6, 0, 0.8], 60.0)])
+    ps = poses if use_pose else None
+    out_g = ctx.backproject_reduce6x6(frames, 160, 120, planes, intr, ps)
+    out_o = O.backproject_reduce6x6(frames, 160, 120, planes, intr, ps)
+    assert np.array_equal(out_g[:, 28], out_o[:, 28])
+    scale = np.maximum(np.abs(out_o), 1e-9 * np.abs(out_o).max(axis=1, keepdims=True))
+    assert _rel(out_g, out_o, scale) < 1e-10
+
+
+# ------------------------------------------------------------------ optimiser on the GPU objective
+def test_bfgs_on_cloud_recovers_cuboid(ctx):
+    true = np.concatenate([[0.4, -0.3, 3.5], [4.0, 2.5, 3.0], synth.quat_from_axis_angle([0.2, 1, 0.1], 12.0)])
+    xyz, _ = synth.cuboid_room_cloud(200_000, true, sigma=0.003, seed=21)
+    init = true + np.concatenate([[0.05, -0.04, 0.03], [0.08, -0.06, 0.05], 0.02 * np.array([1, -1, 1, -1])])
+    cl = ctx.upload(xyz)
+    f0, _, _ = ctx.cuboid_residual_grad(cl, init)
+    p, f, iters, evals = ctx.fit_cuboid_cloud_bfgs(cl, init, 100, 1e-7)
+    assert f < 0.05 * f0 and f < 200_000 * (0.003 ** 2) * 1.3
+    assert np.allclose(p[:6], true[:6], atol=2e-3)
+    qa, qb = p[6:] / np.linalg.norm(p[6:]), true[6:] / np.linalg.norm(true[6:])
+    assert min(np.linalg.norm(qa - qb), np.linalg.norm(qa + qb)) < 2e-3
