@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libhousescan_b200.so")
-CU = ["hs_api.cu", "k_planes.cu", "k_transform.cu", "k_depth.cu", "k_graph.cu", "k_select.cu"]
+CU = ["hs_api.cu", "k_planes.cu", "k_eval_fast.cu", "k_transform.cu", "k_depth.cu", "k_graph.cu", "k_select.cu"]
 HOST = ["hs_host.cpp"]
 HEADERS = [
     os.path.join(ROOT, "include", "housescan_b200.h"),
@@ -27,6 +27,9 @@ HEADERS = [
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    # never contract mul+add into fma behind our back: the reference's Float arithmetic has no FMA, and ptxas does fuse
+    # mul.rn.f32x2 + add.rn.f32x2 into FFMA2 without this (seen in SASS); every FMA we want is written as fma().
+    "--fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden,-O2",
     "-Xptxas", "-v",
 ]

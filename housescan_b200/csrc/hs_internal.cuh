@@ -39,7 +39,8 @@ struct hs_ctx {
   std::mutex mu;
 };
 
-enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1 };
+enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1, HS_MODE_EVAL_CONSUMERS = 2, HS_MODE_EVAL_VARIANT = 3, HS_MODE_EVAL_TPI = 4 };
+enum { HS_EVAL_AUTO = 0, HS_EVAL_EXACT = 1, HS_EVAL_FAST = 2 };  // values of modes[HS_MODE_EVAL_KERNEL]
 
 // table of rooms passed by value to the evaluation kernels
 struct RoomTable {
@@ -67,7 +68,8 @@ struct PlaneTable {
 int32_t hs_ensure_scratch(hs_ctx* ctx, size_t bytes);
 int32_t hs_ensure_pinned(hs_ctx* ctx, size_t bytes);
 
-int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);
+int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);       // exact Double products
+int32_t launch_rooms_cuboid_sums_fast(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);  // packed f32x2 + TMA ring
 int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const PlaneTable& tbl, uint8_t* d_assign, float* d_resid);
 int32_t launch_plane_sums(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out /*K*HS_PS*/);
 

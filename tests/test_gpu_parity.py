@@ -105,22 +105,48 @@ def test_plane_assign_generic_k(ctx):
         assert np.array_equal(a_g, a_o) and np.array_equal(r_g.view(np.uint32), r_o.view(np.uint32))
 
 
-def test_cuboid_sums_config1(ctx, room_small):
+# evaluation kernels: "exact" = every product in Double (k_planes.cu); "fast" = the packed-f32x2 / TMA throughput kernel
+# (k_eval_fast.cu: Float products, 60-point Float chains, Double accumulation).  Assignment (counts) is bit-exact in both;
+# sums: exact 1e-11 of the magnitude sum, fast 1e-6 (the north-star bar; measured ~1e-7).
+EVAL_MODES = {"exact": (1, 1e-11), "fast": (2, 1e-6)}
+
+
+@pytest.fixture(params=["exact", "fast"])
+def eval_mode(request, ctx):
+    mode, tol = EVAL_MODES[request.param]
+    ctx.set_mode(0, mode)
+    yield tol
+    ctx.set_mode(0, 0)
+
+
+def _record_scale(xyz, params):
+    """magnitude sums the tolerances are relative to: sum |term| of every record entry"""
+    a, r = O.plane_assign(xyz, O.planes_from_cuboid(params))
+    r = r.astype(np.float64)
+    sc = np.zeros(22)
+    sc[0] = np.sum(r * r)
+    for k in range(6):
+        sc[1 + k] = np.sum(np.abs(r[a == k]))
+    for j in range(3):
+        m = (a >> 1) == j
+        sc[7 + 3 * j : 10 + 3 * j] = np.sum(np.abs(r[m, None] * xyz[m].astype(np.float64)), axis=0)
+    sc[16:22] = 1.0
+    return np.maximum(sc, 1e-300)
+
+
+def test_cuboid_sums_config1(ctx, room_small, eval_mode):
     xyz, params = room_small
     cl = ctx.upload(xyz)
     rec_g = ctx.rooms_cuboid_sums(cl, [0, len(xyz)], params[None])[0]
     rec_o = O.cuboid_sums(xyz, params)
     assert np.array_equal(rec_g[16:22], rec_o[16:22])  # counts exact
-    scale = np.abs(rec_o).copy()
-    scale[1:7] = np.maximum(scale[1:7], np.sqrt(rec_o[0] * rec_o[16:22]))  # sum r vs sqrt(N sum r^2)
-    scale[7:16] = np.maximum(scale[7:16], 1.0)
-    assert _rel(rec_g[:22], rec_o[:22], scale[:22]) < 1e-11
+    assert _rel(rec_g[:22], rec_o[:22], _record_scale(xyz, params)) < eval_mode
 
 
 @pytest.mark.parametrize("perturb", [0.0, 0.05])
-def test_cuboid_residual_grad_config1(ctx, room_small, perturb):
-    """f, gradient (10) and counts (6) vs the oracle's direct per-point Double accumulation.
-    Tolerance: 1e-9 of the gradient's magnitude sum (north-star bar: 1e-6)."""
+def test_cuboid_residual_grad_config1(ctx, room_small, perturb, eval_mode):
+    """f, gradient (10) and counts (6) vs the oracle's direct per-point Double accumulation, relative to the gradient's
+    magnitude sum (sum |2 r dr/dtheta|)."""
     xyz, params = room_small
     rng = np.random.default_rng(3)
     p = params + perturb * rng.normal(size=10)
@@ -128,8 +154,8 @@ def test_cuboid_residual_grad_config1(ctx, room_small, perturb):
     f_g, g_g, c_g = ctx.cuboid_residual_grad(cl, p)
     f_o, g_o, c_o, gs = O.cuboid_residual_grad(xyz, p)
     assert np.array_equal(c_g, c_o)
-    assert abs(f_g - f_o) <= 1e-12 * f_o
-    assert _rel(g_g, g_o, gs) < 1e-9
+    assert abs(f_g - f_o) <= eval_mode * f_o
+    assert _rel(g_g, g_o, gs) < max(eval_mode, 1e-9)
 
 
 def test_cuboid_gradient_matches_finite_differences(ctx, room_small):
@@ -155,7 +181,7 @@ def test_cuboid_gradient_matches_finite_differences(ctx, room_small):
         assert abs(fd - g[m]) <= 1e-4 * abs(g[m]) + 5e-4 * abs(f0), (m, fd, g[m])  # Float residuals vs the Double model
 
 
-def test_rooms_sums_ragged_rooms(ctx):
+def test_rooms_sums_ragged_rooms(ctx, eval_mode):
     """several rooms with offsets that are not multiples of 4, an empty room, points outside every room"""
     rng = np.random.default_rng(9)
     sizes = [1, 0, 5, 1023, 4096, 7, 20_001, 3]
@@ -168,11 +194,12 @@ def test_rooms_sums_ragged_rooms(ctx):
     for r, s in enumerate(sizes):
         rec_o = O.cuboid_sums(xyz[offs[r] : offs[r + 1]], params[r])
         assert np.array_equal(rec_g[r, 16:22], rec_o[16:22]), r
-        assert np.allclose(rec_g[r, :16], rec_o[:16], rtol=1e-11, atol=1e-11 * max(1.0, np.abs(rec_o[:16]).max())), r
+        if s:
+            assert _rel(rec_g[r, :16], rec_o[:16], _record_scale(xyz[offs[r] : offs[r + 1]], params[r])[:16]) < eval_mode, r
         assert rec_g[r, 22] == 0 and rec_g[r, 23] == 0
 
 
-def test_rooms_sums_many_rooms_chunked(ctx):
+def test_rooms_sums_many_rooms_chunked(ctx, eval_mode):
     """more rooms than one launch's table (HS_MAX_ROOMS = 32) + a multi-block cloud"""
     rng = np.random.default_rng(10)
     nrooms = 40
@@ -184,10 +211,10 @@ def test_rooms_sums_many_rooms_chunked(ctx):
     for r in (0, 13, 31, 32, 39):
         rec_o = O.cuboid_sums(xyz[offs[r] : offs[r + 1]], params[r])
         assert np.array_equal(rec_g[r, 16:22], rec_o[16:22])
-        assert np.allclose(rec_g[r, :16], rec_o[:16], rtol=1e-11, atol=1e-10)
+        assert _rel(rec_g[r, :16], rec_o[:16], _record_scale(xyz[offs[r] : offs[r + 1]], params[r])[:16]) < eval_mode
 
 
-def test_rooms_sums_additive_over_point_shards(ctx, room_small):
+def test_rooms_sums_additive_over_point_shards(ctx, room_small, eval_mode):
     """size-independent property used by the multi-GPU path: records of point shards add up to the whole"""
     from housescan_b200.rooms import local_room_offsets, shard_range
 
@@ -201,7 +228,8 @@ def test_rooms_sums_additive_over_point_shards(ctx, room_small):
         lo, hi = shard_range(n, rank, 3)
         acc += ctx.rooms_cuboid_sums(ctx.upload(xyz[lo:hi]), local_room_offsets(offs, lo, hi), pp)
     assert np.array_equal(acc[:, 16:22], whole[:, 16:22])
-    assert np.allclose(acc, whole, rtol=1e-12, atol=1e-9)
+    for r in range(2):
+        assert _rel(acc[r, :16], whole[r, :16], _record_scale(xyz[offs[r] : offs[r + 1]], pp[r])[:16]) < 2 * eval_mode
 
 
 def test_plane_sums_generic(ctx, room_small):

@@ -1,0 +1,56 @@
+"""Minimal driver for profiling the evaluation kernel under ncu (never a bench number).
+usage: python tools/prof_eval.py [--n POINTS] [--mode M] [--reps R] [--bps B]"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+import housescan_b200 as hb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=100_000_008)
+ap.add_argument("--mode", type=int, default=-1)
+ap.add_argument("--bps", type=int, default=0)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--cons", type=int, default=0)
+ap.add_argument("--var", type=int, default=0)
+ap.add_argument("--tpi", type=int, default=1)
+ap.add_argument("--time", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+ctx = hb.Context(0)
+if a.mode >= 0:
+    ctx.set_mode(0, a.mode)
+if a.bps > 0:
+    ctx.set_mode(1, a.bps)
+if a.cons > 0:
+    ctx.set_mode(2, a.cons)
+ctx.set_mode(3, a.var)
+ctx.set_mode(4, a.tpi)
+s = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(s)
+ctx.set_stream(s.cuda_stream)
+params = bench.room_params()
+pe = np.ascontiguousarray(bench.eval_params(params))
+per = a.n // 12
+offs = np.arange(13, dtype=np.int64) * per
+buf, pts = bench.gen_points_torch(torch, dev, params, [per] * 12, seed=3)
+cloud = ctx.wrap(buf.data_ptr(), per * 12, keepalive=buf)
+rec = torch.zeros(12 * hb.HS_REC, dtype=torch.float64, device=dev)
+torch.cuda.synchronize()
+for _ in range(3):
+    ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.reps):
+    ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.reps
+print(f"mode={a.mode} bps={a.bps} cons={a.cons} var={a.var} tpi={a.tpi} n={per*12} {ms*1e3:.1f} us/launch  {per*12/ms/1e6:.1f} Gpts/s  {per*12*12/ms/1e6:.0f} GB/s  frac_of_6553={per*12*12/ms/1e6/6553.3:.3f}")
