@@ -1,0 +1,139 @@
+"""Host-side logic of the product (C++ mirror of the Haskell modules, Python module shims) against the oracle.
+No GPU needed: plane construction, chain rule, Nelder-Mead, least squares, export formats, sharding helpers."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import housescan_b200 as hb
+import oracle as O
+from housescan_b200 import FitCuboidBFGS as F
+from housescan_b200 import TranslationOptimizer as T
+from housescan_b200 import synth
+from housescan_b200.Bijection import biject
+from housescan_b200.rooms import local_room_offsets, shard_range
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_planes_from_cuboid_bit_exact_vs_oracle():
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        p = np.concatenate([rng.normal(size=3) * 10, rng.uniform(0.5, 12, 3), rng.normal(size=4)])
+        a, b = hb.planes_from_cuboid(p), O.planes_from_cuboid(p)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_chain_rule_from_sums_matches_per_point_gradient():
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        true = np.concatenate([rng.normal(size=3), rng.uniform(2, 6, 3), rng.normal(size=4)])
+        xyz, _ = synth.cuboid_room_cloud(20_000, true, sigma=0.01, rng=rng)
+        p = true + 0.03 * rng.normal(size=10)
+        f, g, c = hb.cuboid_grad_from_sums(p, O.cuboid_sums(xyz, p))
+        f_o, g_o, c_o, gs = O.cuboid_residual_grad(xyz, p)
+        assert np.array_equal(c, c_o) and abs(f - f_o) <= 1e-13 * f_o
+        assert np.max(np.abs(g - g_o) / gs) < 1e-12
+        assert abs(np.dot(g, np.concatenate([np.zeros(6), p[6:]]))) < 1e-9 * gs[6:].max()  # scale of q is a gauge direction
+
+
+def test_eight_corner_functions_match_oracle():
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        p = np.concatenate([rng.normal(size=3) * 5, rng.uniform(0.5, 9, 3), rng.normal(size=4)])
+        pts = rng.normal(size=(8, 3)) * 3
+        assert np.array_equal(F.cuboidFromParams(p), O.cuboid_from_params(p))
+        assert F.errfun(pts, p) == O.errfun(pts, p)
+        assert F.errfunClosest(pts, p) == O.errfun_closest(pts, p)
+        assert np.array_equal(np.array(F.guessDims(pts)), O.guess_dims(pts), equal_nan=True)  # sqrt of a negative for non-cuboids: NaN in both
+    with pytest.raises(ValueError, match="bad arguments passed to cuboidFromParams"):
+        F.cuboidFromParams([1, 2, 3])
+
+
+def test_nelder_mead_fit_reaches_the_oracle_end_state():
+    pts = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [2, 0, 0], [2, 0, 1], [2, 1, 0], [2, 1, 1]], float) @ O.rot_matrix3([1, 2, 3], math.radians(20))
+    for fit_p, fit_o in ((F.fitCuboid, O.fit_cuboid), (F.fitCuboidFromCenter, O.fit_cuboid_from_center), (F.fitCuboidFromCenterFirst, O.fit_cuboid_from_center_first)):
+        p, steps, err, path = fit_p(pts)
+        po, so, eo, patho = fit_o(pts)
+        assert err < 1e-12 and eo < 1e-12
+        assert np.allclose(sorted(p[3:6]), [1, 1, 2], atol=1e-5) and np.allclose(p[:3], po[:3], atol=1e-6)
+        assert abs(steps - so) <= max(5, 0.05 * so)  # same algorithm; last-ulp summation order may shift a few iterations
+        assert path.shape[1] == patho.shape[1] and path[0, 0] == 1
+    err, steps = F.fitCuboidFromCenterFirstError(pts)
+    assert err < 1e-12 and steps > 0
+    rooms = json.load(open(os.path.join(GOLDEN, "room_corners.json")))
+    for name, corners in rooms.items():
+        p, steps, err, _ = F.fitCuboidFromCenterFirst(np.array(corners, float))
+        po, so, eo, _ = O.fit_cuboid_from_center_first(np.array(corners, float))
+        assert abs(err - eo) <= 1e-6 * max(1.0, eo), name
+
+
+def test_lstsq_distances_matches_oracle_incl_quirks():
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        n = int(rng.integers(2, 9))
+        names = [f"r{i}" for i in rng.permutation(12)[:n]]
+        edges = {}
+        for i in range(n - 1):  # a spanning chain keeps it solvable
+            edges[(names[i], names[i + 1])] = float(rng.normal())
+        for _ in range(int(rng.integers(0, 6))):
+            a, b = rng.choice(n, 2, replace=False)
+            edges[(names[a], names[b])] = float(rng.normal())
+        res_p, res_o = T.lstSqDistances(edges), O.lst_sq_distances(edges)
+        assert (res_p is None) == (res_o is None)
+        if res_p:
+            assert res_p[0].keys() == res_o[0].keys()
+            assert all(abs(res_p[0][k] - res_o[0][k]) < 1e-9 for k in res_o[0])
+            assert abs(res_p[1] ** 2 - res_o[1] ** 2) < 1e-12  # rmse = sqrt(||r||_2 / m): compare before the sqrt amplifies 1e-16
+    assert T.lstSqDistances({(1, 2): 1.0, (3, 4): 1.0}) is None  # Nothing
+
+
+def test_proj_export_formats_match_oracle():
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        M = O.proj_translate4(rng.normal(size=3) * 10 ** rng.uniform(-3, 3), O.proj_linear(O.rot_matrix3(rng.normal(size=3), float(rng.uniform(0, 6)), np.float32)))
+        M[rng.integers(0, 3), rng.integers(0, 3)] *= 10 ** rng.uniform(-9, 9)
+        assert hb.proj_to_string(M) == O.room_projection_to_string(M)
+        assert hb.proj_to_xf(M) == O.room_projection_to_xf(M)
+
+
+def test_biject_and_sharding_helpers():
+    idx, unb = biject(["c", "a", "c", "b"])
+    assert idx == O.biject(["c", "a", "c", "b"])[0] and unb == ["c", "a", "b"]
+    n = 100_000_008
+    cover = 0
+    for world in (1, 2, 3, 4, 8):
+        prev = 0
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            assert lo == prev and lo % 4 == 0 and hi <= n
+            prev = hi
+        assert prev == n
+    offs = np.arange(13) * 8_333_334
+    lo, hi = shard_range(n, 3, 8)
+    loc = local_room_offsets(offs, lo, hi)
+    assert loc[0] == 0 and loc[-1] == hi - lo and np.all(np.diff(loc) >= 0)
+    assert np.sum(np.diff(loc)) == hi - lo
+
+
+def test_optimize_room_positions_reference_semantics():
+    """Main.optimizeRoomPositions (Main.hs:2089-2168) with two rooms: an `Opposite 0.1` wall pair along X ends 0.1 m apart"""
+    from housescan_b200.rooms import X, Opposite, optimizeRoomPositions
+
+    corner_mean = {1: np.array([0.0, 0, 0]), 2: np.array([5.3, 0, 0])}
+    plane_mean = {(1, 0): np.array([2.0, 0, 0]), (2, 1): np.array([5.3 - 2.5, 0, 0])}  # +x wall of room 1, -x wall of room 2
+
+    class FakeCtx:  # groupConnectedComponents needs GPU labels; on CPU use the oracle's labels through the same interface
+        def group_cc(self, src, dst, n):
+            lab = O.cc_label(src, dst, n)
+            uniq = sorted(set(lab[src]))
+            comp = np.array([uniq.index(lab[s]) for s in src], np.int32)
+            order = np.concatenate([np.flatnonzero(comp == c)[::-1] for c in range(len(uniq))]).astype(np.int64)
+            return comp, order, len(uniq)
+
+    moved, log = optimizeRoomPositions([1, 2], [(X, Opposite(0.1), (1, 0), (2, 1))], lambda r, w: plane_mean[(r, w)], lambda r: corner_mean[r], ctx=FakeCtx())
+    # o = (2.0 - 0) - (2.8 - 5.3) = 4.5; desired centre offset = 4.5 + 0.1 => room 2 sits at x = 4.6
+    assert abs(moved[2][0] - (4.6 - 5.3)) < 1e-6 and moved[1][0] == 0 and not moved[2][1:].any()
+    assert any("Aligning the X (1 components)" in l for l in log)

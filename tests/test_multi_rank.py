@@ -1,0 +1,55 @@
+"""N > 1 path on CPU: two gloo ranks shard the apartment by point range, reduce one record per room each and all-reduce
+them; the summed records and the gradients must equal the unsharded evaluation.  On the CPU box the per-shard reduction is
+the oracle standing in for the kernel (tests may use it as the checker); the sharding helpers, the record algebra, the
+all-reduce and the host chain rule are the product's own code, i.e. exactly what runs around the kernel under torchrun."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import housescan_b200 as hb
+    import oracle as O
+    from housescan_b200 import synth
+    from housescan_b200.rooms import local_room_offsets, shard_range
+
+    xyz, offs, params = synth.apartment(n_rooms=3, pts_per_room=20_001, seed=3)
+    pe = params + 0.01
+    n = len(xyz)
+    lo, hi = shard_range(n, rank, world)
+    loc = local_room_offsets(offs, lo, hi)
+    shard = xyz[lo:hi]
+    rec = np.stack([O.cuboid_sums(shard[loc[r] : loc[r + 1]], pe[r]) for r in range(3)])
+    t = torch.from_numpy(rec.copy())
+    dist.all_reduce(t)  # the path's only exchange: nrooms x HS_REC doubles
+    total = t.numpy()
+    whole = np.stack([O.cuboid_sums(xyz[offs[r] : offs[r + 1]], pe[r]) for r in range(3)])
+    ok = np.array_equal(total[:, 16:22], whole[:, 16:22]) and np.allclose(total, whole, rtol=1e-12, atol=1e-9)
+    for r in range(3):
+        f, g, c = hb.cuboid_grad_from_sums(pe[r], total[r])
+        f_o, g_o, c_o, gs = O.cuboid_residual_grad(xyz[offs[r] : offs[r + 1]], pe[r])
+        ok = ok and np.array_equal(c, c_o) and abs(f - f_o) <= 1e-12 * f_o and np.max(np.abs(g - g_o) / gs) < 1e-11
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_point_range_sharding_equals_unsharded(tmp_path, built_lib, oracle_lib):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / f"ok{r}").read() for r in range(world)] == ["1", "1"]
