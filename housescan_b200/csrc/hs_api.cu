@@ -318,7 +318,8 @@ static int32_t rooms_sums_enqueue(hs_ctx* ctx, const hs_cloud* cloud, const int6
     const int mode = ctx->modes[HS_MODE_EVAL_KERNEL];
     if (mode == HS_EVAL_FAST && !t.paired) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: fast kernel needs antiparallel plane pairs");
     const bool fast = t.paired && mode != HS_EVAL_EXACT;
-    if (int32_t rc = (fast ? launch_rooms_cuboid_sums_fast : launch_rooms_cuboid_sums)(ctx, cloud->d, cloud->n, t, d_out + static_cast<size_t>(r0) * HS_REC)) return rc;
+    auto launch = !fast ? launch_rooms_cuboid_sums : (ctx->modes[HS_MODE_EVAL_VARIANT] == 2 ? launch_rooms_cuboid_sums_pred : launch_rooms_cuboid_sums_fast);
+    if (int32_t rc = launch(ctx, cloud->d, cloud->n, t, d_out + static_cast<size_t>(r0) * HS_REC)) return rc;
   }
   return HS_OK;
 }

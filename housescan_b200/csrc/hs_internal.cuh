@@ -70,6 +70,7 @@ int32_t hs_ensure_pinned(hs_ctx* ctx, size_t bytes);
 
 int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);       // exact Double products
 int32_t launch_rooms_cuboid_sums_fast(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);  // packed f32x2 + TMA ring
+int32_t launch_rooms_cuboid_sums_pred(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);  // scalar predicated + TMA ring
 int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const PlaneTable& tbl, uint8_t* d_assign, float* d_resid);
 int32_t launch_plane_sums(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out /*K*HS_PS*/);
 
