@@ -1,6 +1,7 @@
 // C ABI of libhousescan_b200.so (include/housescan_b200.h): context/cloud management and the glue from the
 // reference-shaped entry points to the CUDA launchers.  No CPU fallback: every compute entry needs a live ctx.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -78,8 +79,20 @@ int32_t hs_ctx_create(int32_t device, hs_ctx** out) {
   if ((e = cudaMemset(ctx->d_ticket, 0, 256)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&ctx->d_small, sizeof(double) * (HS_MAX_ROOMS * HS_REC + 64))) != cudaSuccess) return fail(e);
   if (hs_ensure_scratch(ctx, 1 << 22) != HS_OK || hs_ensure_pinned(ctx, 1 << 20) != HS_OK) { g_create_err = ctx->err; delete ctx; return HS_ECUDA; }
+  // tuning knobs can also come from the environment (HS_MODE_<key>=<value>, keys as in hs_ctx_set_mode)
+  for (int k = 0; k < 16; ++k) {
+    const std::string name = "HS_MODE_" + std::to_string(k);
+    if (const char* v = std::getenv(name.c_str())) ctx->modes[k] = std::atoi(v);
+  }
   *out = ctx;
   return HS_OK;
+}
+
+// tools only (not in the public header): per-block {start, main loop done, end, is_last} timestamps of the last evaluation launch
+extern "C" HS_API int32_t hs_dbg_block_times(hs_ctx* ctx, unsigned long long* out, int32_t nblocks) {
+  if (!ctx || !ctx->d_dbg || nblocks > 1024) return HS_EINVAL;
+  cudaStreamSynchronize(ctx->stream);
+  return cudaMemcpy(out, ctx->d_dbg, sizeof(unsigned long long) * 4 * nblocks, cudaMemcpyDeviceToHost) == cudaSuccess ? HS_OK : HS_ECUDA;
 }
 
 int32_t hs_ctx_destroy(hs_ctx* ctx) {
@@ -89,6 +102,7 @@ int32_t hs_ctx_destroy(hs_ctx* ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_small) cudaFree(ctx->d_small);
+  if (ctx->d_dbg) cudaFree(ctx->d_dbg);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -113,6 +127,10 @@ int64_t hs_ctx_launch_count(const hs_ctx* ctx) { return ctx ? ctx->launches : 0;
 int32_t hs_ctx_set_mode(hs_ctx* ctx, int32_t key, int32_t value) {
   if (!ctx || key < 0 || key >= 16) return HS_EINVAL;
   ctx->modes[key] = value;
+  if (key == HS_MODE_DEBUG_TIMES && value && !ctx->d_dbg) {
+    HS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * 4 * 1024));
+    HS_CUDA_TRY(ctx, cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 4 * 1024));
+  }
   return HS_OK;
 }
 

@@ -36,10 +36,11 @@ struct hs_ctx {
   char* h_pinned = nullptr;
   size_t pinned_bytes = 0;
   int modes[16] = {0};
+  unsigned long long* d_dbg = nullptr;  // per-block timestamps of the evaluation kernel (mode key 5; tools only)
   std::mutex mu;
 };
 
-enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1, HS_MODE_EVAL_CONSUMERS = 2, HS_MODE_EVAL_VARIANT = 3, HS_MODE_EVAL_TPI = 4 };
+enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1, HS_MODE_EVAL_CONSUMERS = 2, HS_MODE_EVAL_VARIANT = 3, HS_MODE_EVAL_TPI = 4, HS_MODE_DEBUG_TIMES = 5 };
 enum { HS_EVAL_AUTO = 0, HS_EVAL_EXACT = 1, HS_EVAL_FAST = 2 };  // values of modes[HS_MODE_EVAL_KERNEL]
 
 // table of rooms passed by value to the evaluation kernels

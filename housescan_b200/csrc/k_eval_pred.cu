@@ -16,10 +16,12 @@
 
 #include "k_common.cuh"
 #include "k_ring.cuh"
+#include "k_eval_point.cuh"
+#include "k_eval_group_gen.cuh"
 
 namespace hsk {
 
-constexpr int EP_FLUSH_TILES = 16;  // Float chain length: 16 tiles x 4 points per thread
+constexpr int EP_FLUSH_POINTS = 128;  // Float chain length (points per thread between flushes into the Double accumulators)
 
 struct PredTable {
   int32_t nrooms;
@@ -29,64 +31,6 @@ struct PredTable {
   float dp[HS_MAX_ROOMS][3];    // d of the + wall
   float dm[HS_MAX_ROOMS][3];    // d of the - wall (whose normal is -n)
 };
-
-struct RoomK {  // one room's constants in registers (uniform across the block)
-  float n[3][3], dp[3], dm[3];
-};
-
-// Float chains of one thread since the last flush
-struct ChainsP {
-  float f, T[3], M[3], B[3][3], C1, C2, Cm[3];
-  __device__ __forceinline__ void clear() {
-    f = C1 = C2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      T[j] = M[j] = Cm[j] = 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) B[j][c] = 0.f;
-    }
-  }
-};
-
-// One point.  Written as one PTX block so that every accumulation is a predicated FP instruction (the C++ front end is free
-// to turn `if (E) acc += v` into selects, which cost an ALU-pipe slot each).  ptxas schedules across consecutive blocks.
-__device__ __forceinline__ void add_point_pred(ChainsP& c, const RoomK& R, float x, float y, float z) {
-  asm("{\n"
-      ".reg .pred P, Q1, E0, E1, E2;\n"
-      ".reg .f32 a, b, t, sp, sm, asp, asm_, s0, s1, s2, p0, p1, p2, a0, a1, a2, a01;\n"
-      // axis 0
-      "mul.rn.f32 a, %24, %21;\n mul.rn.f32 b, %25, %22;\n add.rn.f32 a, a, b;\n mul.rn.f32 b, %26, %23;\n add.rn.f32 t, a, b;\n"
-      "sub.rn.f32 sp, t, %33;\n add.rn.f32 sm, t, %36;\n abs.f32 asp, sp;\n abs.f32 asm_, sm;\n"
-      "setp.lt.f32 P, asm_, asp;\n selp.f32 s0, sm, sp, P;\n selp.f32 p0, 0f3F800000, 0f00000000, P;\n"
-      // axis 1
-      "mul.rn.f32 a, %27, %21;\n mul.rn.f32 b, %28, %22;\n add.rn.f32 a, a, b;\n mul.rn.f32 b, %29, %23;\n add.rn.f32 t, a, b;\n"
-      "sub.rn.f32 sp, t, %34;\n add.rn.f32 sm, t, %37;\n abs.f32 asp, sp;\n abs.f32 asm_, sm;\n"
-      "setp.lt.f32 P, asm_, asp;\n selp.f32 s1, sm, sp, P;\n selp.f32 p1, 0f3F800000, 0f00000000, P;\n"
-      // axis 2
-      "mul.rn.f32 a, %30, %21;\n mul.rn.f32 b, %31, %22;\n add.rn.f32 a, a, b;\n mul.rn.f32 b, %32, %23;\n add.rn.f32 t, a, b;\n"
-      "sub.rn.f32 sp, t, %35;\n add.rn.f32 sm, t, %38;\n abs.f32 asp, sp;\n abs.f32 asm_, sm;\n"
-      "setp.lt.f32 P, asm_, asp;\n selp.f32 s2, sm, sp, P;\n selp.f32 p2, 0f3F800000, 0f00000000, P;\n"
-      // nearest axis, sequential first-minimum semantics (NaN compares false and keeps the earlier wall)
-      "abs.f32 a0, s0;\n abs.f32 a1, s1;\n abs.f32 a2, s2;\n"
-      "setp.lt.f32 Q1, a1, a0;\n selp.f32 a01, a1, a0, Q1;\n setp.lt.f32 E2, a2, a01;\n"
-      "setp.lt.and.f32 E1, a1, a0, !E2;\n setp.geu.and.f32 E0, a1, a0, !E2;\n"
-      // predicated accumulation
-      "@E0 fma.rn.f32 %0, s0, s0, %0;\n @E0 add.rn.f32 %1, %1, s0;\n @E0 fma.rn.f32 %4, s0, p0, %4;\n @E0 add.rn.f32 %18, %18, p0;\n"
-      "@E0 fma.rn.f32 %7, s0, %21, %7;\n @E0 fma.rn.f32 %8, s0, %22, %8;\n @E0 fma.rn.f32 %9, s0, %23, %9;\n"
-      "@E1 fma.rn.f32 %0, s1, s1, %0;\n @E1 add.rn.f32 %2, %2, s1;\n @E1 fma.rn.f32 %5, s1, p1, %5;\n @E1 add.rn.f32 %19, %19, p1;\n"
-      "@E1 fma.rn.f32 %10, s1, %21, %10;\n @E1 fma.rn.f32 %11, s1, %22, %11;\n @E1 fma.rn.f32 %12, s1, %23, %12;\n @E1 add.rn.f32 %16, %16, 0f3F800000;\n"
-      "@E2 fma.rn.f32 %0, s2, s2, %0;\n @E2 add.rn.f32 %3, %3, s2;\n @E2 fma.rn.f32 %6, s2, p2, %6;\n @E2 add.rn.f32 %20, %20, p2;\n"
-      "@E2 fma.rn.f32 %13, s2, %21, %13;\n @E2 fma.rn.f32 %14, s2, %22, %14;\n @E2 fma.rn.f32 %15, s2, %23, %15;\n @E2 add.rn.f32 %17, %17, 0f3F800000;\n"
-      "}\n"
-      : "+f"(c.f), "+f"(c.T[0]), "+f"(c.T[1]), "+f"(c.T[2]), "+f"(c.M[0]), "+f"(c.M[1]), "+f"(c.M[2]),              // 0..6
-        "+f"(c.B[0][0]), "+f"(c.B[0][1]), "+f"(c.B[0][2]), "+f"(c.B[1][0]), "+f"(c.B[1][1]), "+f"(c.B[1][2]),       // 7..12
-        "+f"(c.B[2][0]), "+f"(c.B[2][1]), "+f"(c.B[2][2]), "+f"(c.C1), "+f"(c.C2),                                  // 13..17
-        "+f"(c.Cm[0]), "+f"(c.Cm[1]), "+f"(c.Cm[2])                                                                 // 18..20
-      : "f"(x), "f"(y), "f"(z),                                                                                      // 21..23
-        "f"(R.n[0][0]), "f"(R.n[0][1]), "f"(R.n[0][2]), "f"(R.n[1][0]), "f"(R.n[1][1]), "f"(R.n[1][2]),             // 24..29
-        "f"(R.n[2][0]), "f"(R.n[2][1]), "f"(R.n[2][2]),                                                              // 30..32
-        "f"(R.dp[0]), "f"(R.dp[1]), "f"(R.dp[2]), "f"(R.dm[0]), "f"(R.dm[1]), "f"(R.dm[2]));                        // 33..38
-}
 
 // Per-thread Double accumulators live in shared memory (slot c of thread t at acc[c * NCONS + t]: conflict-free, private,
 // no synchronisation) so the register file is left to the Float chains; they are touched once per 64 points.
@@ -133,17 +77,24 @@ __device__ __noinline__ void add_point_exact_p(double* acc, const float* pl /* 6
   a[(7 + 3 * j + 2) * NCONS] = fma(s, static_cast<double>(z), a[(7 + 3 * j + 2) * NCONS]);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+#define DBG_EVT(k) do { if (dbg && threadIdx.x == 0 && (r - rfirst) < 2) dbg[4 * gridDim.x + 8 * blockIdx.x + 4 * (r - rfirst) + (k)] = globaltimer_ns(); } while (0)
+
 template <int NCONS>
 __device__ __forceinline__ void consumers_sync_p() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 
 // block b owns groups [b*gpb, (b+1)*gpb); per overlapping room: stream whole-group tiles through the ring.
-template <int NCONS, int STAGES, int BPS>
+// GPT = 48-byte groups per thread per tile (tile = GPT * NCONS groups); FORM 0 = scalar products, 1 = packed products
+template <int NCONS, int STAGES, int BPS, int GPT, int FORM>
 __global__ void __launch_bounds__(NCONS + 32, BPS)
 k_rooms_cuboid_sums_pred(const float* __restrict__ xyz, int64_t n, const __grid_constant__ PredTable tbl, int64_t gpb,
-                         double* __restrict__ partials, int* __restrict__ meta, unsigned int* ticket, double* __restrict__ out) {
+                         double* __restrict__ partials, int* __restrict__ meta, unsigned int* ticket, double* __restrict__ out,
+                         unsigned long long* __restrict__ dbg) {
+  constexpr int TILE_GROUPS = GPT * NCONS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(STAGES) * NCONS * 48);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(STAGES) * TILE_GROUPS * 48);
   uint64_t* empty = full + STAGES;
   double* acc = reinterpret_cast<double*>(empty + STAGES);           // [HS_NACC][NCONS] per-thread Double accumulators
   double* red = acc + static_cast<size_t>(HS_NACC) * NCONS;           // [NCONS/32][HS_NACC]
@@ -160,6 +111,7 @@ k_rooms_cuboid_sums_pred(const float* __restrict__ xyz, int64_t n, const __grid_
     if (tbl.off[r] < p1 && tbl.off[r + 1] > p0) { if (rfirst < 0) rfirst = r; rlast = r; }
 
   if (threadIdx.x == 0) {
+    if (dbg) dbg[4 * blockIdx.x] = globaltimer_ns();
     meta[blockIdx.x] = rfirst;
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCONS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,12 +125,12 @@ k_rooms_cuboid_sums_pred(const float* __restrict__ xyz, int64_t n, const __grid_
       for (int r = rfirst; r <= rlast; ++r) {
         const int64_t lo = max(tbl.off[r], p0), hi = min(tbl.off[r + 1], p1);
         const int64_t gl = (lo + 3) >> 2, gh = hi >> 2;
-        for (int64_t tg = gl; tg < gh; tg += NCONS, ++tt) {
+        for (int64_t tg = gl; tg < gh; tg += TILE_GROUPS, ++tt) {
           const int s = static_cast<int>(tt % STAGES);
           if (tt >= STAGES) mbar_wait(empty + s, static_cast<uint32_t>(((tt / STAGES) - 1) & 1));
-          const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(NCONS), gh - tg) * 48);
+          const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(TILE_GROUPS), gh - tg) * 48);
           mbar_expect_tx(full + s, bytes);
-          bulk_g2s(tiles + static_cast<size_t>(s) * NCONS * 3, reinterpret_cast<const float4*>(xyz) + 3 * tg, bytes, full + s);
+          bulk_g2s(tiles + static_cast<size_t>(s) * TILE_GROUPS * 3, reinterpret_cast<const float4*>(xyz) + 3 * tg, bytes, full + s);
         }
       }
     }
@@ -216,44 +168,73 @@ k_rooms_cuboid_sums_pred(const float* __restrict__ xyz, int64_t n, const __grid_
       else if (threadIdx.x >= 32 && threadIdx.x - 32 < ntail) { const int64_t i = tail_begin + threadIdx.x - 32; add_point_exact_p<NCONS>(acc, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
       // full tiles: the hot loop.  Ring position is carried as (stage, parity); `tt` only keeps producer and consumers on
       // the same global tile count across rooms.
+      DBG_EVT(0);
       const int64_t ngroups = gh - gl;
-      const int nfull = static_cast<int>(ngroups / NCONS);
-      const int rem_groups = static_cast<int>(ngroups - static_cast<int64_t>(nfull) * NCONS);
-      constexpr uint32_t TILE_BYTES = NCONS * 48;
+      const int nfull = static_cast<int>(ngroups / TILE_GROUPS);
+      const int rem_groups = static_cast<int>(ngroups - static_cast<int64_t>(nfull) * TILE_GROUPS);
+      constexpr uint32_t TILE_BYTES = TILE_GROUPS * 48;
+      constexpr int FLUSH_TILES = EP_FLUSH_POINTS / (4 * GPT);
       uint32_t stage = static_cast<uint32_t>(tt % STAGES);
       uint32_t parity = static_cast<uint32_t>((tt / STAGES) & 1);
       const uint32_t tiles_s = smem_u32(tiles) + threadIdx.x * 48, full_s = smem_u32(full), empty_s = smem_u32(empty);
+      const RoomK2 R2 = make_room_k2(R);
       int since_flush = 0;
       for (int t = 0; t < nfull; ++t) {
         mbar_wait_s(full_s + 8 * stage, parity);
-        // this thread's group of the tile: 4 consecutive points = 3 x LDS.128 (48 B lane stride: conflict-free quarter-warps)
+        // this thread's GPT groups of the tile (group g*NCONS + tid): 4 consecutive points = 3 x LDS.128 each
+        // (48 B lane stride: conflict-free quarter-warps)
         const uint32_t base = tiles_s + stage * TILE_BYTES;
-        const float4 q0 = lds_v4(base), q1 = lds_v4(base + 16), q2 = lds_v4(base + 32);
-        mbar_arrive_s(empty_s + 8 * stage);  // the values are in registers: hand the slot back before the math
+        if (FORM == 0) {
+          float4 q[GPT][3];
+#pragma unroll
+          for (int g = 0; g < GPT; ++g) {
+            q[g][0] = lds_v4(base + g * NCONS * 48); q[g][1] = lds_v4(base + g * NCONS * 48 + 16); q[g][2] = lds_v4(base + g * NCONS * 48 + 32);
+          }
+          mbar_arrive_s(empty_s + 8 * stage);  // the values are in registers: hand the slot back before the math
+#pragma unroll
+          for (int g = 0; g < GPT; ++g) {
+            add_point_pred(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
+            add_point_pred(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
+            add_point_pred(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
+            add_point_pred(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
+          }
+        } else {
+          unsigned long long w[GPT][6];
+#pragma unroll
+          for (int g = 0; g < GPT; ++g) {
+            lds_v2b64(base + g * NCONS * 48, w[g][0], w[g][1]); lds_v2b64(base + g * NCONS * 48 + 16, w[g][2], w[g][3]);
+            lds_v2b64(base + g * NCONS * 48 + 32, w[g][4], w[g][5]);
+          }
+          mbar_arrive_s(empty_s + 8 * stage);
+#pragma unroll
+          for (int g = 0; g < GPT; ++g) add_group_v1(ch, R2, w[g][0], w[g][1], w[g][2], w[g][3], w[g][4], w[g][5]);
+        }
         if (++stage == STAGES) { stage = 0; parity ^= 1u; }
-        add_point_pred(ch, R, q0.x, q0.y, q0.z);
-        add_point_pred(ch, R, q0.w, q1.x, q1.y);
-        add_point_pred(ch, R, q1.z, q1.w, q2.x);
-        add_point_pred(ch, R, q2.y, q2.z, q2.w);
-        if (++since_flush == EP_FLUSH_TILES) { flush_chains_p<NCONS>(ch, acc, 4 * EP_FLUSH_TILES); since_flush = 0; }
+        if (++since_flush == FLUSH_TILES) { flush_chains_p<NCONS>(ch, acc, 4 * GPT * FLUSH_TILES); since_flush = 0; }
       }
-      flush_chains_p<NCONS>(ch, acc, 4 * since_flush);
+      flush_chains_p<NCONS>(ch, acc, 4 * GPT * since_flush);
       tt += nfull;
+      DBG_EVT(1);
       if (rem_groups) {  // partial last tile of the room segment: exact scalar path for the in-range groups
         mbar_wait_s(full_s + 8 * stage, parity);
-        const float* tile = reinterpret_cast<const float*>(tiles) + static_cast<size_t>(stage) * NCONS * 12;
-        float v[12];
+        const float* tile = reinterpret_cast<const float*>(tiles) + static_cast<size_t>(stage) * TILE_GROUPS * 12;
+        float v[GPT][12];
 #pragma unroll
-        for (int e = 0; e < 12; ++e) v[e] = tile[12 * threadIdx.x + e];  // out-of-range slots read stale but valid shared memory
+        for (int g = 0; g < GPT; ++g)
+#pragma unroll
+          for (int e = 0; e < 12; ++e) v[g][e] = tile[12 * (g * NCONS + threadIdx.x) + e];  // out-of-range slots: stale but valid shared memory
         mbar_arrive_s(empty_s + 8 * stage);
-        if (static_cast<int>(threadIdx.x) < rem_groups)
-          for (int e = 0; e < 4; ++e) add_point_exact_p<NCONS>(acc, spl, v[3 * e], v[3 * e + 1], v[3 * e + 2]);
+#pragma unroll
+        for (int g = 0; g < GPT; ++g)
+          if (g * NCONS + static_cast<int>(threadIdx.x) < rem_groups)
+            for (int e = 0; e < 4; ++e) add_point_exact_p<NCONS>(acc, spl, v[g][3 * e], v[g][3 * e + 1], v[g][3 * e + 2]);
         ++tt;
       }
     } else {
       const int64_t i = lo + threadIdx.x;
       if (i < hi) add_point_exact_p<NCONS>(acc, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     }
+    DBG_EVT(2);
     // consumer-only deterministic block reduction
     {
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -271,9 +252,11 @@ k_rooms_cuboid_sums_pred(const float* __restrict__ xyz, int64_t n, const __grid_
       }
       consumers_sync_p<NCONS>();
     }
+    DBG_EVT(3);
   }
 
   // ---------------- last block sums the partials per room in block order
+  if (dbg && threadIdx.x == 0) dbg[4 * blockIdx.x + 1] = globaltimer_ns();
   __threadfence();
   consumers_sync_p<NCONS>();
   if (threadIdx.x == 0) {
@@ -282,20 +265,79 @@ k_rooms_cuboid_sums_pred(const float* __restrict__ xyz, int64_t n, const __grid_
     if (is_last) *ticket = 0u;
   }
   consumers_sync_p<NCONS>();
+  if (dbg && threadIdx.x == 0) { dbg[4 * blockIdx.x + 2] = globaltimer_ns(); dbg[4 * blockIdx.x + 3] = is_last; }
   if (!is_last) return;
   __threadfence();
+  // The other SMs are idle from here on, so this must be short: all partials are fetched with independent loads into shared
+  // memory first (one round trip instead of one per block), then every output is summed from shared memory in block order.
   const int64_t ppb = gpb * 4;
-  for (int o = threadIdx.x; o < nrooms * HS_REC; o += NCONS) {
+  int* smeta = reinterpret_cast<int*>(red);
+  const int nblocks = static_cast<int>(gridDim.x);
+  constexpr int SMETA_CAP = (NCONS / 32) * HS_NACC * 2, STAGE_CAP = HS_NACC * NCONS;
+  // per room: first overlapping block, number of overlapping blocks, prefix of those counts (one 64-bit division pair per room)
+  __shared__ int s_blo[HS_MAX_ROOMS], s_nbr[HS_MAX_ROOMS], s_base[HS_MAX_ROOMS + 1];
+  if (threadIdx.x < nrooms) {
+    const int r = threadIdx.x;
+    const bool nonempty = tbl.off[r + 1] > tbl.off[r];
+    const int64_t b_lo = nonempty ? tbl.off[r] / ppb : 0;
+    s_blo[r] = static_cast<int>(b_lo);
+    s_nbr[r] = nonempty ? static_cast<int>((tbl.off[r + 1] - 1) / ppb - b_lo) + 1 : 0;
+  }
+  consumers_sync_p<NCONS>();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int r = 0; r < nrooms; ++r) { s_base[r] = run; run += s_nbr[r]; }
+    s_base[nrooms] = run;
+  }
+  consumers_sync_p<NCONS>();
+  const int total_slots = s_base[nrooms];  // sum over rooms of the number of blocks overlapping the room
+  if (nblocks <= SMETA_CAP && total_slots * HS_NACC <= STAGE_CAP) {
+    for (int b = threadIdx.x; b < nblocks; b += NCONS) smeta[b] = __ldcg(meta + b);
+    consumers_sync_p<NCONS>();
+    const int total = total_slots * HS_NACC;
+    constexpr int U = 4;
+    for (int i0 = 0; i0 < total; i0 += NCONS * U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * NCONS + threadIdx.x;
+        v[u] = 0.0;
+        if (i < total) {
+          const int q = i / HS_NACC, c = i - q * HS_NACC;
+          int r = 0;
+          while (q >= s_base[r + 1]) ++r;  // room of slot q (empty rooms have equal prefixes and are skipped)
+          const int bb = s_blo[r] + (q - s_base[r]);
+          v[u] = __ldcg(partials + (static_cast<int64_t>(bb) * nrooms + (r - smeta[bb])) * HS_NACC + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * NCONS + threadIdx.x;
+        if (i < total) acc[i] = v[u];
+      }
+    }
+    consumers_sync_p<NCONS>();
+    for (int o = threadIdx.x; o < nrooms * HS_REC; o += NCONS) {
+      const int r = o / HS_REC, c = o % HS_REC;
+      double sum = 0.0;
+      if (c < HS_NACC)
+        for (int k = 0; k < s_nbr[r]; ++k) sum += acc[(s_base[r] + k) * HS_NACC + c];
+      out[o] = sum;
+    }
+    if (dbg && threadIdx.x == 0) dbg[4 * blockIdx.x + 2] = globaltimer_ns();
+    return;
+  }
+  for (int o = threadIdx.x; o < nrooms * HS_REC; o += NCONS) {  // general fallback: same sums, one dependent load per block
     const int r = o / HS_REC, c = o % HS_REC;
-    double s = 0.0;
+    double sum = 0.0;
     if (c < HS_NACC && tbl.off[r + 1] > tbl.off[r]) {
       const int64_t b_lo = tbl.off[r] / ppb, b_hi = (tbl.off[r + 1] - 1) / ppb;
       for (int64_t b = b_lo; b <= b_hi; ++b) {
         const int slot = r - __ldcg(meta + b);
-        s += __ldcg(partials + (b * nrooms + slot) * HS_NACC + c);
+        sum += __ldcg(partials + (b * nrooms + slot) * HS_NACC + c);
       }
     }
-    out[o] = s;
+    out[o] = sum;
   }
 }
 
@@ -303,7 +345,7 @@ k_rooms_cuboid_sums_pred(const float* __restrict__ xyz, int64_t n, const __grid_
 
 using namespace hsk;
 
-template <int NCONS, int STAGES, int BPS>
+template <int NCONS, int STAGES, int BPS, int GPT, int FORM>
 static int32_t launch_pred_t(hs_ctx* ctx, const float* xyz, int64_t n, const PredTable& tbl, double* d_rec_out) {
   const int64_t G = (n + 3) >> 2;
   int64_t nb = static_cast<int64_t>(ctx->sm_count) * BPS;
@@ -315,14 +357,14 @@ static int32_t launch_pred_t(hs_ctx* ctx, const float* xyz, int64_t n, const Pre
   if (int32_t rc = hs_ensure_scratch(ctx, need)) return rc;
   double* partials = reinterpret_cast<double*>(ctx->d_scratch);
   int* meta = reinterpret_cast<int*>(ctx->d_scratch + static_cast<size_t>(nb) * tbl.nrooms * HS_NACC * sizeof(double));
-  const size_t smem = static_cast<size_t>(STAGES) * NCONS * 48 + 2 * STAGES * 8 + static_cast<size_t>(HS_NACC) * NCONS * 8 +
+  const size_t smem = static_cast<size_t>(STAGES) * GPT * NCONS * 48 + 2 * STAGES * 8 + static_cast<size_t>(HS_NACC) * NCONS * 8 +
                       static_cast<size_t>(NCONS / 32) * HS_NACC * 8 + 6 * 4 * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_rooms_cuboid_sums_pred<NCONS, STAGES, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_rooms_cuboid_sums_pred<NCONS, STAGES, BPS, GPT, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_set = true;
   }
-  k_rooms_cuboid_sums_pred<NCONS, STAGES, BPS><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out);
+  k_rooms_cuboid_sums_pred<NCONS, STAGES, BPS, GPT, FORM><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out, ctx->d_dbg);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;
@@ -340,12 +382,15 @@ int32_t launch_rooms_cuboid_sums_pred(hs_ctx* ctx, const float* xyz, int64_t n, 
       t.dp[r][j] = rt.pl[r][2 * j][3];
       t.dm[r][j] = rt.pl[r][2 * j + 1][3];
     }
-  switch (ctx->modes[HS_MODE_EVAL_CONSUMERS]) {
-    case 1: return launch_pred_t<224, 4, 2>(ctx, xyz, n, t, d_rec_out);   // 2 CTAs/SM x (7 consumer warps + producer)
-    case 2: return launch_pred_t<320, 3, 2>(ctx, xyz, n, t, d_rec_out);   // 2 CTAs/SM x (10 + 1)
-    case 3: return launch_pred_t<608, 3, 1>(ctx, xyz, n, t, d_rec_out);   // 19 + 1 warps
-    case 4: return launch_pred_t<736, 2, 1>(ctx, xyz, n, t, d_rec_out);   // 23 + 1 warps
-    case 5: return launch_pred_t<352, 4, 1>(ctx, xyz, n, t, d_rec_out);   // 11 + 1 warps
-    default: return launch_pred_t<480, 4, 1>(ctx, xyz, n, t, d_rec_out);  // 15 consumer warps + producer
+  switch (ctx->modes[HS_MODE_EVAL_CONSUMERS]) {  // tuning variants (tools/prof_eval.py --cons N); 0 is the product default
+    case 1: return launch_pred_t<480, 4, 1, 1, 0>(ctx, xyz, n, t, d_rec_out);
+    case 2: return launch_pred_t<480, 4, 1, 1, 1>(ctx, xyz, n, t, d_rec_out);
+    case 3: return launch_pred_t<480, 3, 1, 2, 0>(ctx, xyz, n, t, d_rec_out);
+    case 4: return launch_pred_t<480, 3, 1, 2, 1>(ctx, xyz, n, t, d_rec_out);
+    case 5: return launch_pred_t<384, 4, 1, 2, 0>(ctx, xyz, n, t, d_rec_out);
+    case 6: return launch_pred_t<384, 4, 1, 2, 1>(ctx, xyz, n, t, d_rec_out);
+    case 7: return launch_pred_t<608, 2, 1, 2, 0>(ctx, xyz, n, t, d_rec_out);
+    case 8: return launch_pred_t<608, 2, 1, 2, 1>(ctx, xyz, n, t, d_rec_out);
+    default: return launch_pred_t<480, 3, 1, 2, 0>(ctx, xyz, n, t, d_rec_out);
   }
 }

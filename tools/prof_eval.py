@@ -21,6 +21,7 @@ ap.add_argument("--cons", type=int, default=0)
 ap.add_argument("--var", type=int, default=0)
 ap.add_argument("--tpi", type=int, default=1)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--blocks", action="store_true", help="print the per-block timeline of the last launch")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 ctx = hb.Context(0)
@@ -54,3 +55,27 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
 print(f"mode={a.mode} bps={a.bps} cons={a.cons} var={a.var} tpi={a.tpi} n={per*12} {ms*1e3:.1f} us/launch  {per*12/ms/1e6:.1f} Gpts/s  {per*12*12/ms/1e6:.0f} GB/s  frac_of_6553={per*12*12/ms/1e6/6553.3:.3f}")
+
+if a.blocks:
+    import ctypes as C
+    from housescan_b200 import _lib
+    lib = C.CDLL(_lib.SO_PATH)
+    ctx.set_mode(5, 1)
+    for _ in range(3):
+        ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
+    torch.cuda.synchronize()
+    nb = 148
+    buf = (C.c_uint64 * (12 * nb))()
+    lib.hs_dbg_block_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    rc = lib.hs_dbg_block_times(ctx.h, buf, 3 * nb)
+    t = np.array(buf[: 4 * nb], dtype=np.int64).reshape(nb, 4)
+    ev = np.array(buf[4 * nb :], dtype=np.int64).reshape(nb, 2, 4)
+    t0 = t[:, 0].min()
+    st, md, en = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, (t[:, 2] - t0) / 1e3
+    print(f"rc={rc} block start us: min {st.min():.1f} max {st.max():.1f} | main-loop end us: min {md.min():.1f} median {np.median(md):.1f} p90 {np.percentile(md,90):.1f} max {md.max():.1f} | end max {en.max():.1f}")
+    print("main-loop duration us: min %.1f median %.1f max %.1f" % ((md - st).min(), np.median(md - st), (md - st).max()))
+    order = np.argsort(md)
+    print("slowest blocks (id, main end us):", [(int(b), round(float(md[b]), 1)) for b in order[-8:]])
+    print("last block:", int(np.argmax(t[:, 3])), "its end %.1f" % en[np.argmax(t[:, 3])])
+    for b in [35, 36, 37, 72, 73, 110, 12, 90]:
+        print("block", b, "start %.1f" % st[b], "seg events (head done, main done, rem done, reduce done):", [[round((x - t0) / 1e3, 1) if x else None for x in ev[b, k]] for k in range(2)])
