@@ -284,6 +284,7 @@ def main():
     # ---- value: K steps, device-timed, max over ranks
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.profiler.start()  # `ncu --profile-from-start off` lists the timed regions only (no-op without a profiler)
     l0 = ctx.launch_count
     ev0.record()
     for _ in range(args.steps):
@@ -348,6 +349,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = float(t.item())
     e2e_value = n_total * e2e_steps / (e_ms * 1e-3)
+    torch.cuda.profiler.stop()
     clocks = sampler.stop() if sampler else None
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample of the same workload

@@ -175,10 +175,61 @@ __device__ __forceinline__ void add_pair_arith(Chains& c, const RoomRegs& R, f2 
   }
 }
 
-enum { VAR_PRED = 0, VAR_ARITH = 1 };
+// Selection by minimum instead of compare+select chains: FMNMX (|.| operand modifiers, full rate) produces the per-axis and
+// cross-axis minima of |distance|, five FSET turn them into exact 0/1 indicators (e0: axis 0 wins ties, e2: axis 2 only on a
+// strict minimum, pf_j: - wall only when strictly nearer), and everything else is packed FP32 arithmetic on those indicators.
+__device__ __forceinline__ void mnmx_lane(const float (&sp)[3], const float (&sm)[3], float& e0, float& e2, float (&pf)[3], float& m) {
+  float a[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    a[j] = fminf(fabsf(sp[j]), fabsf(sm[j]));
+    pf[j] = fabsf(sm[j]) < fabsf(sp[j]) ? 1.0f : 0.0f;
+  }
+  const float m12 = fminf(a[1], a[2]), m01 = fminf(a[0], a[1]);
+  e0 = a[0] <= m12 ? 1.0f : 0.0f;
+  e2 = a[2] < m01 ? 1.0f : 0.0f;
+  m = fminf(m01, a[2]);
+}
+__device__ __forceinline__ void add_pair_mnmx(Chains& c, const RoomRegs& R, f2 x, f2 y, f2 z) {
+  f2 sp[3], sm[3];
+  float spl[3], sph[3], sml[3], smh[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const f2 t = fma2(fma2(mul2(R.nx[j], x), R.one, mul2(R.ny[j], y)), R.one, mul2(R.nz[j], z));  // see add_pair_pred
+    sp[j] = add2(t, R.ndp[j]);
+    sm[j] = add2(t, R.dm[j]);
+    unpack2(sp[j], spl[j], sph[j]);
+    unpack2(sm[j], sml[j], smh[j]);
+  }
+  float e0l, e0h, e2l, e2h, pfl[3], pfh[3], ml, mh;
+  mnmx_lane(spl, sml, e0l, e2l, pfl, ml);
+  mnmx_lane(sph, smh, e0h, e2h, pfh, mh);
+  f2 e[3], pf[3];
+  e[0] = pack2(e0l, e0h);
+  e[2] = pack2(e2l, e2h);
+  e[1] = sub2(sub2(R.one, e[0]), e[2]);
+  const f2 m = pack2(ml, mh);
+  c.f = fma2(m, m, c.f);  // |r|^2 of the nearest wall
+  c.E[0] = add2(c.E[0], e[1]);
+  c.E[1] = add2(c.E[1], e[2]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    pf[j] = pack2(pfl[j], pfh[j]);
+    const f2 zj = mul2(e[j], sel2(pf[j], sm[j], sp[j]));
+    c.C[j] = fma2(e[j], pf[j], c.C[j]);
+    c.T[j] = add2(c.T[j], zj);
+    c.M[j] = fma2(zj, pf[j], c.M[j]);
+    c.B[j][0] = fma2(zj, x, c.B[j][0]);
+    c.B[j][1] = fma2(zj, y, c.B[j][1]);
+    c.B[j][2] = fma2(zj, z, c.B[j][2]);
+  }
+}
+
+enum { VAR_PRED = 0, VAR_ARITH = 1, VAR_MNMX = 2 };
 template <int VAR>
 __device__ __forceinline__ void add_pair(Chains& c, const RoomRegs& R, f2 x, f2 y, f2 z) {
   if (VAR == VAR_ARITH) add_pair_arith(c, R, x, y, z);
+  else if (VAR == VAR_MNMX) add_pair_mnmx(c, R, x, y, z);
   else add_pair_pred(c, R, x, y, z);
 }
 
@@ -278,15 +329,15 @@ template <int NCONS>
 __device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 
 // block b owns groups [b*gpb, (b+1)*gpb); per overlapping room: stream whole-group tiles through the ring.
-template <int NCONS, int VAR, int TPI>
-__global__ void __launch_bounds__(NCONS + 32, 1)
+template <int NCONS, int VAR, int TPI, int STG>
+__global__ void __launch_bounds__(NCONS + 32, (NCONS <= 160 ? 3 : NCONS <= 256 ? 2 : 1))
 k_rooms_cuboid_sums_fast(const float* __restrict__ xyz, int64_t n, const __grid_constant__ PairedTable tbl, int64_t gpb,
                          double* __restrict__ partials, int* __restrict__ meta, unsigned int* ticket, double* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(EV_STAGES) * NCONS * 48);
-  uint64_t* empty = full + EV_STAGES;
-  double* acc = reinterpret_cast<double*>(empty + EV_STAGES);     // [HS_NACC][NCONS] per-thread Double accumulators
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(STG) * NCONS * 48);
+  uint64_t* empty = full + STG;
+  double* acc = reinterpret_cast<double*>(empty + STG);     // [HS_NACC][NCONS] per-thread Double accumulators
   double* red = acc + static_cast<size_t>(HS_NACC) * NCONS;       // [NCONS/32][HS_NACC]
   float* spl = reinterpret_cast<float*>(red + (NCONS / 32) * HS_NACC);  // 6 x 4 planes of the current room (edge path)
   __shared__ bool is_last;
@@ -302,7 +353,7 @@ k_rooms_cuboid_sums_fast(const float* __restrict__ xyz, int64_t n, const __grid_
 
   if (threadIdx.x == 0) {
     meta[blockIdx.x] = rfirst;
-    for (int s = 0; s < EV_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCONS); }
+    for (int s = 0; s < STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCONS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -316,8 +367,8 @@ k_rooms_cuboid_sums_fast(const float* __restrict__ xyz, int64_t n, const __grid_
         const int64_t lo = max(tbl.off[r], p0), hi = min(tbl.off[r + 1], p1);
         const int64_t gl = (lo + 3) >> 2, gh = hi >> 2;
         for (int64_t tg = gl; tg < gh; tg += NCONS, ++tt) {
-          const int s = static_cast<int>(tt % EV_STAGES);
-          if (tt >= EV_STAGES) mbar_wait(empty + s, static_cast<uint32_t>(((tt / EV_STAGES) - 1) & 1));
+          const int s = static_cast<int>(tt % STG);
+          if (tt >= STG) mbar_wait(empty + s, static_cast<uint32_t>(((tt / STG) - 1) & 1));
           const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(NCONS), gh - tg) * 48);
           mbar_expect_tx(full + s, bytes);
           bulk_g2s(tiles + static_cast<size_t>(s) * NCONS * 3, reinterpret_cast<const float4*>(xyz) + 3 * tg, bytes, full + s);
@@ -362,8 +413,8 @@ k_rooms_cuboid_sums_fast(const float* __restrict__ xyz, int64_t n, const __grid_
       const int nfull = static_cast<int>(ngroups / NCONS);
       const int rem_groups = static_cast<int>(ngroups - static_cast<int64_t>(nfull) * NCONS);
       constexpr uint32_t TILE_BYTES = NCONS * 48;
-      uint32_t stage = static_cast<uint32_t>(tt % EV_STAGES);
-      uint32_t parity = static_cast<uint32_t>((tt / EV_STAGES) & 1);
+      uint32_t stage = static_cast<uint32_t>(tt % STG);
+      uint32_t parity = static_cast<uint32_t>((tt / STG) & 1);
       const uint32_t tiles_s = smem_u32(tiles) + threadIdx.x * 12, full_s = smem_u32(full), empty_s = smem_u32(empty);
       int since_flush = 0;
       int t = 0;
@@ -384,7 +435,7 @@ k_rooms_cuboid_sums_fast(const float* __restrict__ xyz, int64_t n, const __grid_
             pz[4 * u + e] = lds_f32(base + e * NCONS * 12 + 8);
           }
           mbar_arrive_s(empty_s + 8 * stage);  // the values are in registers: hand the slot back before the math
-          if (++stage == EV_STAGES) { stage = 0; parity ^= 1u; }
+          if (++stage == STG) { stage = 0; parity ^= 1u; }
         }
 #pragma unroll
         for (int e = 0; e < 4 * TPI; e += 2)
@@ -403,7 +454,7 @@ k_rooms_cuboid_sums_fast(const float* __restrict__ xyz, int64_t n, const __grid_
           pz[e] = lds_f32(base + e * NCONS * 12 + 8);
         }
         mbar_arrive_s(empty_s + 8 * stage);
-        if (++stage == EV_STAGES) { stage = 0; parity ^= 1u; }
+        if (++stage == STG) { stage = 0; parity ^= 1u; }
         add_pair<VAR>(ch, R, pack2(px[0], px[1]), pack2(py[0], py[1]), pack2(pz[0], pz[1]));
         add_pair<VAR>(ch, R, pack2(px[2], px[3]), pack2(py[2], py[3]), pack2(pz[2], pz[3]));
         ++since_flush;
@@ -478,7 +529,7 @@ k_rooms_cuboid_sums_fast(const float* __restrict__ xyz, int64_t n, const __grid_
 
 using namespace hsk;
 
-template <int NCONS, int VAR, int TPI>
+template <int NCONS, int VAR, int TPI, int STG = EV_STAGES>
 static int32_t launch_fast_t(hs_ctx* ctx, const float* xyz, int64_t n, const PairedTable& tbl, double* d_rec_out) {
   const int64_t G = (n + 3) >> 2;
   const int per_sm = ctx->modes[HS_MODE_BLOCKS_PER_SM] > 0 ? ctx->modes[HS_MODE_BLOCKS_PER_SM] : 1;
@@ -491,14 +542,14 @@ static int32_t launch_fast_t(hs_ctx* ctx, const float* xyz, int64_t n, const Pai
   if (int32_t rc = hs_ensure_scratch(ctx, need)) return rc;
   double* partials = reinterpret_cast<double*>(ctx->d_scratch);
   int* meta = reinterpret_cast<int*>(ctx->d_scratch + static_cast<size_t>(nb) * tbl.nrooms * HS_NACC * sizeof(double));
-  const size_t smem = static_cast<size_t>(EV_STAGES) * NCONS * 48 + 2 * EV_STAGES * 8 + static_cast<size_t>(HS_NACC) * NCONS * 8 +
+  const size_t smem = static_cast<size_t>(STG) * NCONS * 48 + 2 * STG * 8 + static_cast<size_t>(HS_NACC) * NCONS * 8 +
                       static_cast<size_t>(NCONS / 32) * HS_NACC * 8 + 6 * 4 * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_rooms_cuboid_sums_fast<NCONS, VAR, TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_rooms_cuboid_sums_fast<NCONS, VAR, TPI, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_set = true;
   }
-  k_rooms_cuboid_sums_fast<NCONS, VAR, TPI><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out);
+  k_rooms_cuboid_sums_fast<NCONS, VAR, TPI, STG><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;
@@ -520,6 +571,20 @@ int32_t launch_rooms_cuboid_sums_fast(hs_ctx* ctx, const float* xyz, int64_t n, 
   // default: ALU-select variant, 16 consumer warps + the producer warp per SM (measured fastest, profiles/r01_*.txt);
   // mode key 3 = 1 selects the all-arithmetic variant (15 consumer warps so that each scheduler holds 4 warps at 128 regs)
   if (ctx->modes[HS_MODE_EVAL_VARIANT] == 1) return launch_fast_t<480, VAR_ARITH, 1>(ctx, xyz, n, t, d_rec_out);
+  if (ctx->modes[HS_MODE_EVAL_VARIANT] == 4) {
+    if (ctx->modes[HS_MODE_EVAL_CONSUMERS] == 256) return launch_fast_t<256, VAR_MNMX, 1>(ctx, xyz, n, t, d_rec_out);
+    if (ctx->modes[HS_MODE_EVAL_CONSUMERS] == 480) return launch_fast_t<480, VAR_MNMX, 1>(ctx, xyz, n, t, d_rec_out);
+    return launch_fast_t<512, VAR_MNMX, 1>(ctx, xyz, n, t, d_rec_out);
+  }
+  switch (ctx->modes[HS_MODE_EVAL_CONSUMERS]) {  // ring-depth experiments (tools/prof_eval.py --cons): consumers * 10 + stages
+    case 256: return launch_fast_t<256, VAR_PRED, 1>(ctx, xyz, n, t, d_rec_out);  // with mode key 1 = 2: two independent rings per SM
+    case 5123: return launch_fast_t<512, VAR_PRED, 1, 3>(ctx, xyz, n, t, d_rec_out);
+    case 4484: return launch_fast_t<448, VAR_PRED, 1, 4>(ctx, xyz, n, t, d_rec_out);
+    case 4486: return launch_fast_t<448, VAR_PRED, 1, 6>(ctx, xyz, n, t, d_rec_out);
+    case 3844: return launch_fast_t<384, VAR_PRED, 1, 4>(ctx, xyz, n, t, d_rec_out);
+    case 3848: return launch_fast_t<384, VAR_PRED, 1, 8>(ctx, xyz, n, t, d_rec_out);
+    default: break;
+  }
   if (ctx->modes[HS_MODE_EVAL_TPI] == 2) return launch_fast_t<480, VAR_PRED, 2>(ctx, xyz, n, t, d_rec_out);
   return launch_fast_t<512, VAR_PRED, 1>(ctx, xyz, n, t, d_rec_out);
 }
