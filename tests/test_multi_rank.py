@@ -53,3 +53,29 @@ def test_two_rank_point_range_sharding_equals_unsharded(tmp_path, built_lib, ora
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(world)] == ["1", "1"]
+
+
+def _cc_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from housescan_b200 import synth
+    from housescan_b200.GroupConnectedComponents import cc_label_sharded
+
+    src, dst, n, _ = synth.voxel_building_graph(nx=32, ny=12, nz=32, seed=4)
+    rng = np.random.default_rng(5)  # plus long-range edges so components straddle the shard boundary several times
+    extra = rng.integers(0, n, size=(40, 2))
+    src = np.concatenate([src, extra[:, 0]]).astype(np.uint32)
+    dst = np.concatenate([dst, extra[:, 1]]).astype(np.uint32)
+    labels, (lo, hi) = cc_label_sharded(lambda s, d, m: O.cc_label(s, d, m), src, dst, n, rank, world)
+    whole = O.cc_label(src, dst, n)
+    ok = np.array_equal(labels, whole[lo:hi])
+    open(os.path.join(tmp, f"cc{rank}"), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_vertex_range_cc_equals_unsharded(tmp_path, built_lib, oracle_lib):
+    world = 2
+    mp.spawn(_cc_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / f"cc{r}").read() for r in range(world)] == ["1", "1"]
