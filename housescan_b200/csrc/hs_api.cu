@@ -380,16 +380,23 @@ int32_t hs_plane_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_of
   HS_LOCK(ctx);
   if (!cloud || !room_offsets || !planes || !out || nrooms < 1) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: bad arguments");
   if (room_offsets[0] < 0 || room_offsets[nrooms] > cloud->n) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: room offsets outside the cloud");
-  for (int r = 0; r < nrooms; ++r) {
-    if (room_offsets[r] > room_offsets[r + 1]) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: room offsets must be non-decreasing");
+  // one launch per room, all enqueued back to back; the K x HS_PS records land side by side and come back in ONE copy
+  const size_t total = static_cast<size_t>(nrooms) * K * HS_PS;
+  double* d_out = ctx->d_small;
+  double* big = nullptr;
+  if (total > static_cast<size_t>(HS_MAX_ROOMS) * HS_REC) { HS_CUDA_TRY(ctx, cudaMalloc(&big, total * sizeof(double))); d_out = big; }
+  int32_t rc = HS_OK;
+  HS_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, total * sizeof(double), ctx->stream));
+  for (int r = 0; r < nrooms && rc == HS_OK; ++r) {
+    if (room_offsets[r] > room_offsets[r + 1]) { ctx->err = "hs_plane_sums: room offsets must be non-decreasing"; rc = HS_EINVAL; break; }
     PlaneTable t;
-    if (int32_t rc = fill_plane_table(ctx, planes + static_cast<size_t>(r) * K * 4, K, HS_MAX_PLANES, t, "hs_plane_sums")) return rc;
-    double* o = out + static_cast<size_t>(r) * K * HS_PS;
-    if (room_offsets[r] == room_offsets[r + 1]) { std::fill(o, o + K * HS_PS, 0.0); continue; }
-    if (int32_t rc = launch_plane_sums(ctx, cloud->d, room_offsets[r], room_offsets[r + 1], t, ctx->d_small)) return rc;
-    if (int32_t rc = copy_d2h_sync(ctx, o, ctx->d_small, sizeof(double) * K * HS_PS)) return rc;
+    if ((rc = fill_plane_table(ctx, planes + static_cast<size_t>(r) * K * 4, K, HS_MAX_PLANES, t, "hs_plane_sums")) != HS_OK) break;
+    if (room_offsets[r] == room_offsets[r + 1]) continue;  // stays zero
+    rc = launch_plane_sums(ctx, cloud->d, room_offsets[r], room_offsets[r + 1], t, d_out + static_cast<size_t>(r) * K * HS_PS);
   }
-  return HS_OK;
+  if (rc == HS_OK) rc = copy_d2h_sync(ctx, out, d_out, total * sizeof(double));
+  if (big) { cudaStreamSynchronize(ctx->stream); cudaFree(big); }
+  return rc;
 }
 
 static int32_t mean_impl(hs_ctx* ctx, const hs_cloud* cloud, double mean[3]) {

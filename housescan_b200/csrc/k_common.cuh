@@ -71,33 +71,60 @@ __device__ __forceinline__ bool last_block_arrives(unsigned int* ticket, unsigne
   return is_last;
 }
 
-// Exclusive scan of ntiles unsigned counts in place by ONE block (chunks of HS_TPB with a running carry);
-// returns the grand total in every thread.  Used by the order-preserving compactions (V.filter semantics).
+// Exclusive scan of ntiles unsigned counts in place by ONE block; returns the grand total in every thread.  Used by the
+// order-preserving compactions (V.filter semantics).  Every thread owns one contiguous chunk of tiles: it sums the chunk,
+// the 256 chunk sums are scanned across the block, and the chunk is rewritten with its running prefix — two sweeps of
+// independent loads per thread instead of ntiles / 256 block-wide synchronised rounds.
 __device__ __forceinline__ unsigned int block_scan_tiles_exclusive(unsigned int* tile_off, int64_t ntiles) {
   __shared__ unsigned int wsum[HS_TPB / 32];
-  __shared__ unsigned int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int64_t base = 0; base < ntiles; base += HS_TPB) {
-    const int64_t t = base + threadIdx.x;
-    const unsigned int v = t < ntiles ? __ldcg(tile_off + t) : 0u;
-    unsigned int incl = v;
+  const int64_t chunk = (ntiles + HS_TPB - 1) / HS_TPB;
+  const int64_t t0 = min(static_cast<int64_t>(threadIdx.x) * chunk, ntiles), t1 = min(t0 + chunk, ntiles);
+  unsigned int mine = 0;
+  for (int64_t t = t0; t < t1; ++t) mine += __ldcg(tile_off + t);
+  unsigned int incl = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((threadIdx.x & 31) >= o) incl += u;
-    }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    unsigned int woff = 0;
-    for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += wsum[w];
-    const unsigned int c0 = carry;
-    if (t < ntiles) tile_off[t] = c0 + woff + incl - v;
-    __syncthreads();
-    if (threadIdx.x == HS_TPB - 1) carry = c0 + woff + incl;
-    __syncthreads();
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += u;
   }
-  return carry;
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  unsigned int run = incl - mine, total = 0;
+#pragma unroll
+  for (int w = 0; w < HS_TPB / 32; ++w) {
+    if (w < (threadIdx.x >> 5)) run += wsum[w];
+    total += wsum[w];
+  }
+  for (int64_t t = t0; t < t1; ++t) {
+    const unsigned int v = __ldcg(tile_off + t);
+    tile_off[t] = run;
+    run += v;
+  }
+  __syncthreads();
+  return total;
+}
+
+// Sum of per-block partial records by the last block: partials[b * N + c] for b < nblocks -> dst[c].  All HS_TPB threads load
+// (slice s = tid / N takes blocks s, s + S, ...), then the slices are added in slice order: a fixed tree for a fixed grid.
+// MAXC >= 0 marks one component that is reduced with max instead of + (non-negative values).
+template <int N, int MAXC = -1>
+__device__ __forceinline__ void last_block_sum(const double* __restrict__ partials, unsigned int nblocks, double* __restrict__ dst, double* smem /* [HS_TPB] */) {
+  constexpr int S = HS_TPB / N;  // slices
+  const int c = threadIdx.x % N, sl = threadIdx.x / N;
+  double acc = 0.0;
+  if (sl < S)
+    for (unsigned int b = sl; b < nblocks; b += S) {
+      const double v = __ldcg(partials + static_cast<int64_t>(b) * N + c);
+      acc = (c == MAXC) ? fmax(acc, v) : acc + v;
+    }
+  smem[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double t = 0.0;
+    for (int q = 0; q < S; ++q) { const double v = smem[q * N + threadIdx.x]; t = (static_cast<int>(threadIdx.x) == MAXC) ? fmax(t, v) : t + v; }
+    dst[threadIdx.x] = t;
+  }
+  __syncthreads();
 }
 
 // exclusive prefix of a per-thread count inside the block (raster order of threads); smem wsum[HS_TPB/32]

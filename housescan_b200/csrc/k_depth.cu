@@ -9,12 +9,24 @@
 
 namespace hsk {
 
-#define BP_TILE 1024  // pixels per block-tile (4 per thread)
+#define BP_TILE 2048  // pixels per block-tile: 8 consecutive pixels (one 16-byte load) per thread
 
 __device__ __forceinline__ void scale_point(int x, int y, unsigned int d, float& X, float& Y, float& Z) {
   X = __fdiv_rn(static_cast<float>(x), 10.0f);
   Y = __fdiv_rn(static_cast<float>(y), 10.0f);
   Z = __fsub_rn(__fdiv_rn(static_cast<float>(d), 20.0f), 30.0f);
+}
+
+// this thread's 8 pixels of tile t (zeros past the end of the frame)
+__device__ __forceinline__ void load_px8(const uint16_t* __restrict__ depth, int64_t npx, int64_t i0, bool aligned, unsigned int (&d)[8]) {
+  if (aligned && i0 + 8 <= npx) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(depth + i0));
+    d[0] = v.x & 0xffffu; d[1] = v.x >> 16; d[2] = v.y & 0xffffu; d[3] = v.y >> 16;
+    d[4] = v.z & 0xffffu; d[5] = v.z >> 16; d[6] = v.w & 0xffffu; d[7] = v.w >> 16;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = (i0 + e < npx) ? depth[i0 + e] : 0u;
+  }
 }
 
 // pass 1: valid-pixel count per tile (+ optional byte mask); the last block turns counts into exclusive offsets
@@ -23,16 +35,24 @@ k_bp_count(const uint16_t* __restrict__ depth, int64_t npx, uint8_t* __restrict_
            unsigned int* ticket, int64_t* __restrict__ n_valid) {
   __shared__ unsigned int wsum[HS_TPB / 32];
   const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
+  const bool aligned = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
+  const bool mask_aligned = mask && (reinterpret_cast<uintptr_t>(mask) & 7) == 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t i0 = t * BP_TILE + 4 * threadIdx.x;
-    unsigned int c = 0;
+    const int64_t i0 = t * BP_TILE + 8 * threadIdx.x;
+    unsigned int d[8], c = 0;
+    load_px8(depth, npx, i0, aligned, d);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int64_t i = i0 + e;
-      if (i < npx) {
-        const unsigned int v = depth[i] != 0;
-        if (mask) mask[i] = static_cast<uint8_t>(v);
-        c += v;
+    for (int e = 0; e < 8; ++e) c += d[e] != 0;
+    if (mask) {
+      if (mask_aligned && i0 + 8 <= npx) {
+        uint2 m;
+        m.x = (d[0] != 0) | ((d[1] != 0) << 8) | ((d[2] != 0) << 16) | ((d[3] != 0) << 24);
+        m.y = (d[4] != 0) | ((d[5] != 0) << 8) | ((d[6] != 0) << 16) | ((d[7] != 0) << 24);
+        __stcs(reinterpret_cast<uint2*>(mask + i0), m);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (i0 + e < npx) mask[i0 + e] = static_cast<uint8_t>(d[e] != 0);
       }
     }
 #pragma unroll
@@ -51,27 +71,38 @@ k_bp_count(const uint16_t* __restrict__ depth, int64_t npx, uint8_t* __restrict_
   if (threadIdx.x == 0) *n_valid = total;
 }
 
-// pass 2: order-preserving scatter of the scaled points
+// pass 2: order-preserving scatter of the scaled points.  The tile's points are compacted in shared memory first and then
+// written as one contiguous run of floats (fully coalesced), instead of 12-byte scattered stores.
 __global__ void __launch_bounds__(HS_TPB)
 k_bp_scatter(const uint16_t* __restrict__ depth, int64_t npx, int w, const unsigned int* __restrict__ tile_off, float* __restrict__ xyz) {
   __shared__ unsigned int wsum[HS_TPB / 32];
+  __shared__ float stage[BP_TILE * 3];
   const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
+  const bool aligned = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t i0 = t * BP_TILE + 4 * threadIdx.x;
-    unsigned int dv[4], c = 0;
+    const int64_t i0 = t * BP_TILE + 8 * threadIdx.x;
+    unsigned int d[8], c = 0;
+    load_px8(depth, npx, i0, aligned, d);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { const int64_t i = i0 + e; dv[e] = i < npx ? depth[i] : 0u; c += dv[e] != 0; }
-    unsigned int pos = tile_off[t] + block_exclusive_prefix(c, wsum);
+    for (int e = 0; e < 8; ++e) c += d[e] != 0;
+    unsigned int pos = block_exclusive_prefix(c, wsum);  // position inside the tile
+    unsigned int total = 0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (dv[e] != 0) {
-        const int64_t i = i0 + e;
-        const int y = static_cast<int>(i / w), x = static_cast<int>(i - static_cast<int64_t>(y) * w);
+    for (int q = 0; q < HS_TPB / 32; ++q) total += wsum[q];
+    int y = static_cast<int>(i0 / w), x = static_cast<int>(i0 - static_cast<int64_t>(y) * w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (d[e] != 0) {
         float X, Y, Z;
-        scale_point(x, y, dv[e], X, Y, Z);
-        xyz[3 * static_cast<int64_t>(pos)] = X; xyz[3 * static_cast<int64_t>(pos) + 1] = Y; xyz[3 * static_cast<int64_t>(pos) + 2] = Z;
+        scale_point(x, y, d[e], X, Y, Z);
+        stage[3 * pos] = X; stage[3 * pos + 1] = Y; stage[3 * pos + 2] = Z;
         ++pos;
       }
+      if (++x == w) { x = 0; ++y; }
+    }
+    __syncthreads();
+    float* dst = xyz + 3 * static_cast<int64_t>(tile_off[t]);
+    for (unsigned int q = threadIdx.x; q < 3 * total; q += HS_TPB) __stcs(dst + q, stage[q]);
     __syncthreads();
   }
 }
@@ -85,16 +116,93 @@ struct FrameGeom {
   float fx, fy, cx, cy;
 };
 
-__global__ void __launch_bounds__(HS_TPB)
+// One pixel's geometry: back-project, (pose), first-minimum plane, J = [p x n, n] and r, all in Float.  Branch-free so that
+// the pixels a thread holds are evaluated with instruction-level parallelism; invalid pixels (d == 0) compute garbage that
+// the caller never accumulates.  KT > 0: number of planes known at compile time (full unroll); KT == 0: tbl.K at run time.
+struct PixelJ { float j[6], r; };
+template <bool INTR, bool POSE, int KT>
+__device__ __forceinline__ PixelJ ne_geometry(const FrameGeom& geo, const float (&M)[12], const PlaneTable& tbl, const float4* __restrict__ spl,
+                                              int x, int y, unsigned int d) {
+  float X, Y, Z;
+  if (INTR) {
+    Z = __fmul_rn(static_cast<float>(d), 0.001f);
+    X = __fdiv_rn(__fmul_rn(__fsub_rn(static_cast<float>(x), geo.cx), Z), geo.fx);
+    Y = __fdiv_rn(__fmul_rn(__fsub_rn(static_cast<float>(y), geo.cy), Z), geo.fy);
+  } else {
+    scale_point(x, y, d, X, Y, Z);
+  }
+  float px = X, py = Y, pz = Z;
+  if (POSE) {
+    px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[0]), __fmul_rn(Y, M[3])), __fmul_rn(Z, M[6])), M[9]);
+    py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[1]), __fmul_rn(Y, M[4])), __fmul_rn(Z, M[7])), M[10]);
+    pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[2]), __fmul_rn(Y, M[5])), __fmul_rn(Z, M[8])), M[11]);
+  }
+  float rb = plane_dist(tbl.pl[0][0], tbl.pl[0][1], tbl.pl[0][2], tbl.pl[0][3], px, py, pz);
+  float ab = fabsf(rb);
+  int kb = 0;
+  if (KT > 0) {
+#pragma unroll
+    for (int k = 1; k < KT; ++k) {
+      const float rk = plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], px, py, pz);
+      const float ak = fabsf(rk);
+      const bool lt = ak < ab;
+      ab = lt ? ak : ab; rb = lt ? rk : rb; kb = lt ? k : kb;
+    }
+  } else {
+    for (int k = 1; k < tbl.K; ++k) {  // planes come from the constant bank with a uniform index
+      const float rk = plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], px, py, pz);
+      const float ak = fabsf(rk);
+      const bool lt = ak < ab;
+      ab = lt ? ak : ab; rb = lt ? rk : rb; kb = lt ? k : kb;
+    }
+  }
+  const float4 nn = spl[kb];  // the winner's normal: a per-lane index, so it is read from shared memory (one LDS.128), not selected
+  PixelJ o;
+  // crossprod p n in Float (y*c - z*b, z*a - x*c, x*b - y*a)
+  o.j[0] = __fsub_rn(__fmul_rn(py, nn.z), __fmul_rn(pz, nn.y));
+  o.j[1] = __fsub_rn(__fmul_rn(pz, nn.x), __fmul_rn(px, nn.z));
+  o.j[2] = __fsub_rn(__fmul_rn(px, nn.y), __fmul_rn(py, nn.x));
+  o.j[3] = nn.x; o.j[4] = nn.y; o.j[5] = nn.z;
+  o.r = rb;
+  return o;
+}
+// every product of the normal equations is formed in Double (exact for Float operands)
+__device__ __forceinline__ void ne_accumulate(double (&acc)[HS_NE], const PixelJ& p) {
+  const double J[6] = {p.j[0], p.j[1], p.j[2], p.j[3], p.j[4], p.j[5]};
+  const double rd = p.r;
+  int t = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a; b < 6; ++b) { acc[t] = fma(J[a], J[b], acc[t]); ++t; }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) acc[21 + a] = fma(J[a], rd, acc[21 + a]);
+  acc[27] = fma(rd, rd, acc[27]);
+  acc[28] += 1.0;
+}
+
+// Frames are handed out to the resident blocks through a counter (any block may take any frame: a frame's record is computed
+// by one block with a fixed thread -> pixel mapping and a fixed reduction tree, so the result does not depend on who took it).
+// Each thread reads 8 consecutive pixels with one 16-byte load and evaluates them four at a time.
+template <bool INTR, bool POSE, int KT>
+__global__ void __launch_bounds__(HS_TPB, 2)
 k_reduce6x6(const uint16_t* __restrict__ frames, int64_t nframes, int w, int h, const FrameGeom geo, const float* __restrict__ poses,
-            const __grid_constant__ PlaneTable tbl, double* __restrict__ out) {
+            const __grid_constant__ PlaneTable tbl, double* __restrict__ out, unsigned int* counters /* [0] next frame, [1] blocks done */) {
   __shared__ double smem[(HS_TPB / 32) * HS_NE];
+  __shared__ float4 spl[16];
+  __shared__ unsigned int s_frame;
+  if (threadIdx.x < tbl.K) spl[threadIdx.x] = make_float4(tbl.pl[threadIdx.x][0], tbl.pl[threadIdx.x][1], tbl.pl[threadIdx.x][2], tbl.pl[threadIdx.x][3]);
   const int npx = w * h;
-  for (int64_t fr = blockIdx.x; fr < nframes; fr += gridDim.x) {
+  const bool vec_ok = (npx & 7) == 0 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_frame = atomicAdd(counters, 1u);
+    __syncthreads();
+    const int64_t fr = s_frame;
+    if (fr >= nframes) break;
     const uint16_t* dep = frames + fr * npx;
     float M[12];
-    const bool has_pose = poses != nullptr;
-    if (has_pose) {
+    if (POSE) {
       const float* pm = poses + 16 * fr;
       M[0] = pm[0]; M[1] = pm[1]; M[2] = pm[2]; M[3] = pm[4]; M[4] = pm[5]; M[5] = pm[6];
       M[6] = pm[8]; M[7] = pm[9]; M[8] = pm[10]; M[9] = pm[12]; M[10] = pm[13]; M[11] = pm[14];
@@ -102,51 +210,41 @@ k_reduce6x6(const uint16_t* __restrict__ frames, int64_t nframes, int w, int h, 
     double acc[HS_NE];
 #pragma unroll
     for (int i = 0; i < HS_NE; ++i) acc[i] = 0.0;
-    for (int i = threadIdx.x; i < npx; i += HS_TPB) {
-      const unsigned int d = dep[i];
-      if (d == 0) continue;
-      const int y = i / w, x = i - y * w;
-      float X, Y, Z;
-      if (geo.use_intr) {
-        Z = __fmul_rn(static_cast<float>(d), 0.001f);
-        X = __fdiv_rn(__fmul_rn(__fsub_rn(static_cast<float>(x), geo.cx), Z), geo.fx);
-        Y = __fdiv_rn(__fmul_rn(__fsub_rn(static_cast<float>(y), geo.cy), Z), geo.fy);
-      } else {
-        scale_point(x, y, d, X, Y, Z);
-      }
-      float px = X, py = Y, pz = Z;
-      if (has_pose) {
-        px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[0]), __fmul_rn(Y, M[3])), __fmul_rn(Z, M[6])), M[9]);
-        py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[1]), __fmul_rn(Y, M[4])), __fmul_rn(Z, M[7])), M[10]);
-        pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[2]), __fmul_rn(Y, M[5])), __fmul_rn(Z, M[8])), M[11]);
-      }
-      float rb = plane_dist(tbl.pl[0][0], tbl.pl[0][1], tbl.pl[0][2], tbl.pl[0][3], px, py, pz);
-      float ab = fabsf(rb);
-      int kb = 0;
-      for (int k = 1; k < tbl.K; ++k) {
-        const float rk = plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], px, py, pz);
-        const float ak = fabsf(rk);
-        const bool lt = ak < ab;
-        ab = lt ? ak : ab; rb = lt ? rk : rb; kb = lt ? k : kb;
-      }
-      const float nx = tbl.pl[kb][0], ny = tbl.pl[kb][1], nz = tbl.pl[kb][2];
-      // crossprod p n in Float (y*c - z*b, z*a - x*c, x*b - y*a)
-      const double J[6] = {static_cast<double>(__fsub_rn(__fmul_rn(py, nz), __fmul_rn(pz, ny))),
-                           static_cast<double>(__fsub_rn(__fmul_rn(pz, nx), __fmul_rn(px, nz))),
-                           static_cast<double>(__fsub_rn(__fmul_rn(px, ny), __fmul_rn(py, nx))),
-                           static_cast<double>(nx), static_cast<double>(ny), static_cast<double>(nz)};
-      const double rd = rb;
-      int t = 0;
+    if (vec_ok) {
+      const uint4* dep8 = reinterpret_cast<const uint4*>(dep);
+      for (int g = threadIdx.x; g < (npx >> 3); g += HS_TPB) {
+        const uint4 v = __ldcs(dep8 + g);
+        const unsigned int wv[4] = {v.x, v.y, v.z, v.w};
+        const int i0 = g << 3;
+        int y = i0 / w, x = i0 - y * w;
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
+        for (int half = 0; half < 2; ++half) {
+          PixelJ pj[4];
+          unsigned int dd[4];
 #pragma unroll
-        for (int b = a; b < 6; ++b) { acc[t] = fma(J[a], J[b], acc[t]); ++t; }
+          for (int e = 0; e < 4; ++e) {
+            dd[e] = (wv[2 * half + (e >> 1)] >> (16 * (e & 1))) & 0xffffu;
+            pj[e] = ne_geometry<INTR, POSE, KT>(geo, M, tbl, spl, x, y, dd[e]);
+            if (++x == w) { x = 0; ++y; }
+          }
 #pragma unroll
-      for (int a = 0; a < 6; ++a) acc[21 + a] = fma(J[a], rd, acc[21 + a]);
-      acc[27] = fma(rd, rd, acc[27]);
-      acc[28] += 1.0;
+          for (int e = 0; e < 4; ++e)
+            if (dd[e] != 0) ne_accumulate(acc, pj[e]);
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < npx; i += HS_TPB) {
+        const unsigned int d = dep[i];
+        if (d == 0) continue;
+        const int y = i / w, x = i - y * w;
+        ne_accumulate(acc, ne_geometry<INTR, POSE, KT>(geo, M, tbl, spl, x, y, d));
+      }
     }
     block_sum_store<HS_NE>(acc, out + fr * HS_NE, smem);
+  }
+  if (threadIdx.x == 0) {  // the last block to run out of frames re-arms the counters for the next launch on this stream
+    __threadfence();
+    if (atomicAdd(counters + 1, 1u) == gridDim.x - 1) { counters[0] = 0u; counters[1] = 0u; }
   }
 }
 
@@ -177,9 +275,22 @@ int32_t launch_reduce6x6(hs_ctx* ctx, const uint16_t* d_frames, int64_t nframes,
   FrameGeom geo{};
   geo.use_intr = intr != nullptr;
   if (intr) { geo.fx = intr[0]; geo.fy = intr[1]; geo.cx = intr[2]; geo.cy = intr[3]; }
-  int64_t nb = std::min<int64_t>(nframes, static_cast<int64_t>(ctx->sm_count) * 4);
+  int64_t nb = std::min<int64_t>(nframes, static_cast<int64_t>(ctx->sm_count) * 2);
   if (nb < 1) nb = 1;
-  k_reduce6x6<<<static_cast<int>(nb), HS_TPB, 0, ctx->stream>>>(d_frames, nframes, w, h, geo, d_poses, tbl, d_out);
+  unsigned int* counters = ctx->d_ticket + 8;  // zero between launches (re-armed by the kernel)
+  const int grid = static_cast<int>(nb);
+#define HS_NE_LAUNCH(I, P, KT_) k_reduce6x6<I, P, KT_><<<grid, HS_TPB, 0, ctx->stream>>>(d_frames, nframes, w, h, geo, d_poses, tbl, d_out, counters)
+#define HS_NE_PICK(KT_)                                  \
+  do {                                                   \
+    if (intr && d_poses) HS_NE_LAUNCH(true, true, KT_);  \
+    else if (intr) HS_NE_LAUNCH(true, false, KT_);       \
+    else if (d_poses) HS_NE_LAUNCH(false, true, KT_);    \
+    else HS_NE_LAUNCH(false, false, KT_);                \
+  } while (0)
+  if (tbl.K == 6) HS_NE_PICK(6);  // a cuboid room's six walls: fully unrolled plane loop
+  else HS_NE_PICK(0);
+#undef HS_NE_PICK
+#undef HS_NE_LAUNCH
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;

@@ -182,6 +182,26 @@ k_plane_assign(const float* __restrict__ xyz, int64_t n, const __grid_constant__
 // generic per-plane sums over one point range [i0, i1): out[k] = count, sum r, sum r^2, sum p(3), sum r p(3), max|r|
 // (one launch per room; wall-alignment inputs, not the throughput path)
 // ------------------------------------------------------------------------------------------------------------------
+// one HS_PS record (9 sums + max|r|) per block at a stride: all threads load, slices are combined in slice order
+__device__ __forceinline__ void last_block_sum_strided(const double* __restrict__ partials, unsigned int nblocks, int stride, double* __restrict__ dst, double* smem) {
+  constexpr int S = HS_TPB / HS_PS;
+  const int c = threadIdx.x % HS_PS, sl = threadIdx.x / HS_PS;
+  double acc = 0.0;
+  if (sl < S)
+    for (unsigned int b = sl; b < nblocks; b += S) {
+      const double v = __ldcg(partials + static_cast<int64_t>(b) * stride + c);
+      acc = (c == 9) ? fmax(acc, v) : acc + v;
+    }
+  smem[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < HS_PS) {
+    double t = 0.0;
+    for (int q = 0; q < S; ++q) { const double v = smem[q * HS_PS + threadIdx.x]; t = (threadIdx.x == 9) ? fmax(t, v) : t + v; }
+    dst[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
 template <int K>
 __global__ void __launch_bounds__(HS_TPB)
 k_plane_sums(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid_constant__ PlaneTable tbl,
@@ -227,15 +247,10 @@ k_plane_sums(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid
     __syncthreads();
   }
   if (!last_block_arrives(ticket, gridDim.x)) return;
-  for (int o = threadIdx.x; o < K * HS_PS; o += HS_TPB) {
-    const int c = o % HS_PS;
-    double s = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) {
-      const double v = __ldcg(partials + static_cast<int64_t>(b) * K * HS_PS + o);
-      s = (c == 9) ? fmax(s, v) : s + v;
-    }
-    out[o] = s;
-  }
+  __shared__ double fin[HS_TPB];
+#pragma unroll
+  for (int k = 0; k < K; ++k)  // record k of block b sits at partials[(b * K + k) * HS_PS]: stride K * HS_PS between blocks
+    last_block_sum_strided(partials + static_cast<int64_t>(k) * HS_PS, gridDim.x, K * HS_PS, out + k * HS_PS, fin);
 }
 
 }  // namespace hsk

@@ -42,22 +42,55 @@ __device__ __forceinline__ void xform(const Affine& A, float& x, float& y, float
   }
 }
 
+// A tile = HS_TPB groups of 4 points (12 KB).  Global traffic is fully coalesced in both directions (lane i moves the i-th
+// 16 bytes of a contiguous 512-byte run per warp instruction); the 48-byte-per-thread AoS view exists only in shared memory,
+// where 3 x LDS.128 / STS.128 at a 48 B lane stride are conflict free.  Direct 48 B-strided LDG/STG.128 touch half of every
+// 32 B sector per instruction and cost ~25 % of the copy rate (profiles/r01_rows.txt).
 template <int KIND>
 __global__ void __launch_bounds__(HS_TPB)
 k_affine(const float* __restrict__ in, float* __restrict__ out, int64_t n, const __grid_constant__ Affine A) {
+  __shared__ float4 tile[3 * HS_TPB];
   const int64_t gfull = n >> 2;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
-  for (int64_t g = static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x; g < gfull; g += stride) {
-    Pts4 p = load_group(in, g);
+  const int64_t ntiles = gfull / HS_TPB;
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  float4* out4 = reinterpret_cast<float4*>(out);
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * (3 * HS_TPB);
+    const float4 a = __ldcs(in4 + base + threadIdx.x), b = __ldcs(in4 + base + HS_TPB + threadIdx.x), c = __ldcs(in4 + base + 2 * HS_TPB + threadIdx.x);
+    tile[threadIdx.x] = a; tile[HS_TPB + threadIdx.x] = b; tile[2 * HS_TPB + threadIdx.x] = c;
+    __syncthreads();
+    const float4 u = tile[3 * threadIdx.x], v = tile[3 * threadIdx.x + 1], w = tile[3 * threadIdx.x + 2];
+    Pts4 p;
+    p.x[0] = u.x; p.y[0] = u.y; p.z[0] = u.z;
+    p.x[1] = u.w; p.y[1] = v.x; p.z[1] = v.y;
+    p.x[2] = v.z; p.y[2] = v.w; p.z[2] = w.x;
+    p.x[3] = w.y; p.y[3] = w.z; p.z[3] = w.w;
 #pragma unroll
     for (int e = 0; e < 4; ++e) xform<KIND>(A, p.x[e], p.y[e], p.z[e]);
-    store_group(out, g, p);
+    tile[3 * threadIdx.x] = make_float4(p.x[0], p.y[0], p.z[0], p.x[1]);
+    tile[3 * threadIdx.x + 1] = make_float4(p.y[1], p.z[1], p.x[2], p.y[2]);
+    tile[3 * threadIdx.x + 2] = make_float4(p.z[2], p.x[3], p.y[3], p.z[3]);
+    __syncthreads();
+    __stcs(out4 + base + threadIdx.x, tile[threadIdx.x]);
+    __stcs(out4 + base + HS_TPB + threadIdx.x, tile[HS_TPB + threadIdx.x]);
+    __stcs(out4 + base + 2 * HS_TPB + threadIdx.x, tile[2 * HS_TPB + threadIdx.x]);
+    __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
-    const int64_t i = gfull * 4 + threadIdx.x;
-    float x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
-    xform<KIND>(A, x, y, z);
-    out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+  // groups past the last whole tile (< HS_TPB of them) and the ragged points (< 4)
+  if (blockIdx.x == 0) {
+    const int64_t g = ntiles * HS_TPB + threadIdx.x;
+    if (g < gfull) {
+      Pts4 p = load_group(in, g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) xform<KIND>(A, p.x[e], p.y[e], p.z[e]);
+      store_group(out, g, p);
+    }
+    if (threadIdx.x < (n & 3)) {
+      const int64_t i = gfull * 4 + threadIdx.x;
+      float x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+      xform<KIND>(A, x, y, z);
+      out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+    }
   }
 }
 
@@ -79,11 +112,8 @@ k_sum3(const float* __restrict__ xyz, int64_t n, double* __restrict__ partials, 
   }
   block_sum_store<3>(acc, partials + 3 * static_cast<int64_t>(blockIdx.x), smem);
   if (!last_block_arrives(ticket, gridDim.x)) return;
-  if (threadIdx.x < 3) {
-    double s = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(partials + 3 * static_cast<int64_t>(b) + threadIdx.x);
-    out[threadIdx.x] = s;
-  }
+  __shared__ double fin[HS_TPB];
+  last_block_sum<3>(partials, gridDim.x, out, fin);
 }
 
 // max over points of normsqr (m - p) in Float (exact order of `distance`), as ordered uint bits
@@ -135,11 +165,8 @@ k_scatter(const float* __restrict__ xyz, int64_t n, float mx, float my, float mz
   }
   block_sum_store<6>(acc, partials + 6 * static_cast<int64_t>(blockIdx.x), smem);
   if (!last_block_arrives(ticket, gridDim.x)) return;
-  if (threadIdx.x < 6) {
-    double s = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(partials + 6 * static_cast<int64_t>(b) + threadIdx.x);
-    out[threadIdx.x] = s;
-  }
+  __shared__ double fin[HS_TPB];
+  last_block_sum<6>(partials, gridDim.x, out, fin);
 }
 
 }  // namespace hsk
