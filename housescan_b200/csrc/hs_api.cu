@@ -336,7 +336,11 @@ static int32_t rooms_sums_enqueue(hs_ctx* ctx, const hs_cloud* cloud, const int6
     const int mode = ctx->modes[HS_MODE_EVAL_KERNEL];
     if (mode == HS_EVAL_FAST && !t.paired) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: fast kernel needs antiparallel plane pairs");
     const bool fast = t.paired && mode != HS_EVAL_EXACT;
-    auto launch = !fast ? launch_rooms_cuboid_sums : (ctx->modes[HS_MODE_EVAL_VARIANT] == 2 ? launch_rooms_cuboid_sums_pred : launch_rooms_cuboid_sums_fast);
+    // mode key 3 picks the throughput kernel: 0 (default) warp-accumulator scalar form, 2 / 5 / 6 its tuning relatives
+    // (k_eval_pred.cu), 7 / 1 / 4 the packed f32x2 forms (k_eval_fast.cu).  All produce the same record.
+    const int var = ctx->modes[HS_MODE_EVAL_VARIANT];
+    const bool scalar_family = var == 0 || var == 2 || var == 5 || var == 6;
+    auto launch = !fast ? launch_rooms_cuboid_sums : (scalar_family ? launch_rooms_cuboid_sums_pred : launch_rooms_cuboid_sums_fast);
     if (int32_t rc = launch(ctx, cloud->d, cloud->n, t, d_out + static_cast<size_t>(r0) * HS_REC)) return rc;
   }
   return HS_OK;

@@ -28,6 +28,11 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
   asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n@!p bra W_%=;\n}"
                ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
+// plain polling flavour (try_wait itself blocks for a hardware-defined time before it returns false)
+__device__ __forceinline__ void mbar_wait_s_spin(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra W_%=;\n}"
+               ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {

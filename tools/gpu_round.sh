@@ -8,4 +8,4 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pyt
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_rooms_cuboid_sums_fast -s 2 -c 1 -o gpurun_out/eval_fast -f python tools/prof_eval.py --reps 1 > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_rooms_cuboid_sums -s 2 -c 1 -o gpurun_out/eval_default -f python tools/prof_eval.py --reps 1 > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log

@@ -21,6 +21,7 @@ ap.add_argument("--cons", type=int, default=0)
 ap.add_argument("--var", type=int, default=0)
 ap.add_argument("--tpi", type=int, default=1)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--psleep", type=int, default=0)
 ap.add_argument("--blocks", action="store_true", help="print the per-block timeline of the last launch")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -33,6 +34,7 @@ if a.cons > 0:
     ctx.set_mode(2, a.cons)
 ctx.set_mode(3, a.var)
 ctx.set_mode(4, a.tpi)
+ctx.set_mode(6, a.psleep)
 s = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(s)
 ctx.set_stream(s.cuda_stream)
@@ -54,7 +56,7 @@ for _ in range(a.reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
-print(f"mode={a.mode} bps={a.bps} cons={a.cons} var={a.var} tpi={a.tpi} n={per*12} {ms*1e3:.1f} us/launch  {per*12/ms/1e6:.1f} Gpts/s  {per*12*12/ms/1e6:.0f} GB/s  frac_of_6553={per*12*12/ms/1e6/6553.3:.3f}")
+print(f"psleep={a.psleep} mode={a.mode} bps={a.bps} cons={a.cons} var={a.var} tpi={a.tpi} n={per*12} {ms*1e3:.1f} us/launch  {per*12/ms/1e6:.1f} Gpts/s  {per*12*12/ms/1e6:.0f} GB/s  frac_of_6553={per*12*12/ms/1e6/6553.3:.3f}")
 
 if a.blocks:
     import ctypes as C
