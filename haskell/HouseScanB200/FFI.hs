@@ -1,0 +1,69 @@
+-- Binding of include/housescan_b200.h for the HouseScan executable (see INTEGRATION.md).  Not compiled in this repository's
+-- image (no GHC); the identical symbols are exercised through ctypes by the test-suite.
+{-# LANGUAGE ForeignFunctionInterface, EmptyDataDecls #-}
+module HouseScanB200.FFI where
+
+import Data.Int (Int32, Int64)
+import Data.Word (Word8, Word16, Word32)
+import Foreign.C.String (CString)
+import Foreign.C.Types (CDouble(..), CFloat(..))
+import Foreign.Ptr (Ptr)
+
+data HsCtx      -- hs_ctx:   one CUDA device + stream; one in-flight call per ctx
+data HsCloud    -- hs_cloud: device-resident `Vector Vec3` (12 B/point AoS, Main.hs:39-42,120)
+
+-- context -----------------------------------------------------------------------------------------------------
+foreign import ccall safe "hs_ctx_create"   c_ctx_create   :: Int32 -> Ptr (Ptr HsCtx) -> IO Int32
+foreign import ccall safe "hs_ctx_destroy"  c_ctx_destroy  :: Ptr HsCtx -> IO Int32
+foreign import ccall unsafe "hs_last_error" c_last_error   :: Ptr HsCtx -> IO CString
+-- clouds (Cloud.cloudPoints, Main.hs:117-121) ---------------------------------------------------------------------
+foreign import ccall safe "hs_cloud_upload"   c_cloud_upload   :: Ptr HsCtx -> Ptr CFloat -> Int64 -> Ptr (Ptr HsCloud) -> IO Int32
+foreign import ccall safe "hs_cloud_alloc"    c_cloud_alloc    :: Ptr HsCtx -> Int64 -> Ptr (Ptr HsCloud) -> IO Int32
+foreign import ccall safe "hs_cloud_download" c_cloud_download :: Ptr HsCtx -> Ptr HsCloud -> Ptr CFloat -> IO Int32
+foreign import ccall unsafe "hs_cloud_size"   c_cloud_size     :: Ptr HsCloud -> IO Int64
+foreign import ccall safe "hs_cloud_free"     c_cloud_free     :: Ptr HsCtx -> Ptr HsCloud -> IO Int32
+-- (1) depth frames: HoniHelper.takeDepthSnapshot's (Vector Word16,(w,h)) -> addDevicePointCloud (Main.hs:1296-1313)
+foreign import ccall safe "hs_backproject_ref"
+  c_backproject_ref :: Ptr HsCtx -> Ptr Word16 -> Int32 -> Int32 -> Ptr CFloat -> Ptr Word8 -> Ptr Int64 -> IO Int32
+foreign import ccall safe "hs_backproject_reduce6x6"
+  c_backproject_reduce6x6 :: Ptr HsCtx -> Ptr Word16 -> Int64 -> Int32 -> Int32 -> Ptr CFloat -> Ptr CFloat
+                          -> Ptr CFloat -> Int32 -> Ptr CDouble -> IO Int32
+-- (2) planes: signedDistanceToPlaneEq (Main.hs:1371-1372), cuboid objective (FitCuboidBFGS.hs:51-76 generalised)
+foreign import ccall safe "hs_plane_assign"
+  c_plane_assign :: Ptr HsCtx -> Ptr HsCloud -> Ptr CFloat -> Int32 -> Ptr Word8 -> Ptr CFloat -> IO Int32
+foreign import ccall safe "hs_cuboid_residual_grad"
+  c_cuboid_residual_grad :: Ptr HsCtx -> Ptr HsCloud -> Ptr CDouble -> Ptr CDouble -> Ptr CDouble -> Ptr Int64 -> IO Int32
+foreign import ccall safe "hs_rooms_cuboid_sums"
+  c_rooms_cuboid_sums :: Ptr HsCtx -> Ptr HsCloud -> Ptr Int64 -> Int32 -> Ptr CDouble -> Ptr CDouble -> IO Int32
+foreign import ccall safe "hs_plane_sums"
+  c_plane_sums :: Ptr HsCtx -> Ptr HsCloud -> Ptr Int64 -> Int32 -> Ptr CFloat -> Int32 -> Ptr CDouble -> IO Int32
+foreign import ccall safe "hs_fit_plane"      c_fit_plane   :: Ptr HsCtx -> Ptr HsCloud -> Ptr CFloat -> IO Int32
+foreign import ccall safe "hs_fit_cuboid_cloud_bfgs"
+  c_fit_cuboid_cloud_bfgs :: Ptr HsCtx -> Ptr HsCloud -> Ptr CDouble -> Int32 -> CDouble -> Ptr CDouble -> Ptr CDouble
+                          -> Ptr Int32 -> Ptr Int32 -> IO Int32
+-- (3) transforms + export: projectRoom (Main.hs:1716-1730), rotateCloudAround (:1657-1659), translateCloud (:1697-1699)
+foreign import ccall safe "hs_transform"     c_transform     :: Ptr HsCtx -> Ptr HsCloud -> Ptr CFloat -> Ptr HsCloud -> IO Int32
+foreign import ccall safe "hs_rotate_around" c_rotate_around :: Ptr HsCtx -> Ptr HsCloud -> Ptr CFloat -> Ptr CFloat -> Ptr HsCloud -> IO Int32
+foreign import ccall safe "hs_translate"     c_translate     :: Ptr HsCtx -> Ptr HsCloud -> Ptr CFloat -> Ptr HsCloud -> IO Int32
+foreign import ccall safe "hs_mean_extent"   c_mean_extent   :: Ptr HsCtx -> Ptr HsCloud -> Ptr CDouble -> Ptr CFloat -> IO Int32
+foreign import ccall safe "hs_write_ply"     c_write_ply     :: Ptr HsCtx -> Ptr HsCloud -> Ptr Word8 -> CString -> IO Int32
+-- (4) connected components on bijected ids (GroupConnectedComponents.hs:39-54)
+foreign import ccall safe "hs_cc_label"
+  c_cc_label :: Ptr HsCtx -> Ptr Word32 -> Ptr Word32 -> Int64 -> Word32 -> Ptr Word32 -> IO Int32
+foreign import ccall safe "hs_group_cc"
+  c_group_cc :: Ptr HsCtx -> Ptr Word32 -> Ptr Word32 -> Int64 -> Word32 -> Ptr Int32 -> Ptr Int64 -> Ptr Int32 -> IO Int32
+-- VectorUtil.kthLargestBy / removeCeiling (VectorUtil.hs:11-19, Main.hs:2643-2664)
+foreign import ccall safe "hs_kth_largest"    c_kth_largest    :: Ptr HsCtx -> Ptr HsCloud -> Int32 -> Int64 -> Ptr CFloat -> IO Int32
+foreign import ccall safe "hs_remove_ceiling"
+  c_remove_ceiling :: Ptr HsCtx -> Ptr HsCloud -> Ptr HsCloud -> Ptr HsCloud -> Ptr HsCloud -> Ptr Int64 -> Ptr CFloat -> IO Int32
+-- host-only mirrors (no device): TranslationOptimizer.lstSqDistancesI, FitCuboidBFGS.fitCuboid*
+foreign import ccall unsafe "hs_lstsq_distances"
+  c_lstsq_distances :: Ptr Int32 -> Ptr Int32 -> Ptr CDouble -> Int32 -> Int32 -> Ptr CDouble -> Ptr CDouble -> IO Int32
+foreign import ccall safe "hs_fit_cuboid"
+  c_fit_cuboid :: Ptr CDouble -> Int32 -> Ptr CDouble -> Ptr Int32 -> Ptr CDouble -> Ptr CDouble -> Int32 -> IO Int32
+
+-- multi-GPU peer group (INTEGRATION.md section 5)
+foreign import ccall safe "hs_peer_mailbox_create"  c_peer_mailbox_create  :: Ptr HsCtx -> Int32 -> Int32 -> Ptr Word8 -> IO Int32
+foreign import ccall safe "hs_peer_mailbox_connect" c_peer_mailbox_connect :: Ptr HsCtx -> Ptr Word8 -> IO Int32
+foreign import ccall safe "hs_rooms_cuboid_sums_allreduce_async"
+  c_rooms_cuboid_sums_allreduce :: Ptr HsCtx -> Ptr HsCloud -> Ptr Int64 -> Int32 -> Ptr CDouble -> Ptr () -> IO Int32

@@ -46,6 +46,9 @@ SIGNATURES = {
     "hs_cuboid_residual_grad": (i32, [vp, vp, vp, C.POINTER(f64), vp, vp]),
     "hs_rooms_cuboid_sums": (i32, [vp, vp, vp, i32, vp, vp]),
     "hs_rooms_cuboid_sums_async": (i32, [vp, vp, vp, i32, vp, vp]),
+    "hs_peer_mailbox_create": (i32, [vp, i32, i32, vp]),
+    "hs_peer_mailbox_connect": (i32, [vp, vp]),
+    "hs_rooms_cuboid_sums_allreduce_async": (i32, [vp, vp, vp, i32, vp, vp]),
     "hs_cuboid_grad_from_sums": (i32, [vp, vp, C.POINTER(f64), vp, vp]),
     "hs_plane_sums": (i32, [vp, vp, vp, i32, vp, i32, vp]),
     "hs_scatter3x3": (i32, [vp, vp, vp, vp]),

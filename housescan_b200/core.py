@@ -148,6 +148,22 @@ class Context:
     def rooms_cuboid_sums_async(self, cloud: Cloud, room_offsets: np.ndarray, params: np.ndarray, d_rec_ptr: int):
         self._chk(self.lib.hs_rooms_cuboid_sums_async(self.h, cloud.h, ptr(room_offsets), room_offsets.size - 1, ptr(params), C.c_void_p(d_rec_ptr)))
 
+    def peer_connect(self, rank: int, world: int, group=None):
+        """Join the NVLink peer-memory all-reduce group of this node (one process per GPU): exchanges the CUDA IPC handles
+        of the mailboxes through torch.distributed and maps the peers' mailboxes."""
+        import torch.distributed as dist
+
+        handle = np.zeros(64, np.uint8)
+        self._chk(self.lib.hs_peer_mailbox_create(self.h, rank, world, ptr(handle)))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handle.tobytes(), group=group)
+        allh = np.frombuffer(b"".join(gathered), dtype=np.uint8).copy()
+        self._chk(self.lib.hs_peer_mailbox_connect(self.h, ptr(allh)))
+        dist.barrier(group=group)
+
+    def rooms_cuboid_sums_allreduce_async(self, cloud: Cloud, room_offsets: np.ndarray, params: np.ndarray, d_rec_ptr: int):
+        self._chk(self.lib.hs_rooms_cuboid_sums_allreduce_async(self.h, cloud.h, ptr(room_offsets), room_offsets.size - 1, ptr(params), C.c_void_p(d_rec_ptr)))
+
     def plane_sums(self, cloud: Cloud, room_offsets, planes, K: int):
         ro = np.ascontiguousarray(room_offsets, dtype=np.int64)
         nrooms = ro.size - 1

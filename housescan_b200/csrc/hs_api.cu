@@ -103,6 +103,8 @@ int32_t hs_ctx_destroy(hs_ctx* ctx) {
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+  for (int p = 0; p < HS_PEER_MAX; ++p) if (ctx->peer_mapped[p]) cudaIpcCloseMemHandle(ctx->peer_mapped[p]);
+  if (ctx->d_mailbox) cudaFree(ctx->d_mailbox);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -313,7 +315,7 @@ int32_t hs_planes_from_cuboid(const double params[10], float planes_out[24]) {
   return HS_OK;
 }
 
-static int32_t rooms_sums_enqueue(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, const double* params, double* d_out) {
+static int32_t rooms_sums_enqueue(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, const double* params, double* d_out, bool exchange = false) {
   if (!cloud || !room_offsets || !params || nrooms < 1) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: bad arguments");
   for (int r = 0; r < nrooms; ++r)
     if (room_offsets[r] > room_offsets[r + 1]) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: room offsets must be non-decreasing");
@@ -341,7 +343,15 @@ static int32_t rooms_sums_enqueue(hs_ctx* ctx, const hs_cloud* cloud, const int6
     const int var = ctx->modes[HS_MODE_EVAL_VARIANT];
     const bool scalar_family = var == 0 || var == 2 || var == 5 || var == 6;
     auto launch = !fast ? launch_rooms_cuboid_sums : (scalar_family ? launch_rooms_cuboid_sums_pred : launch_rooms_cuboid_sums_fast);
-    if (int32_t rc = launch(ctx, cloud->d, cloud->n, t, d_out + static_cast<size_t>(r0) * HS_REC)) return rc;
+    const bool want_exchange = exchange && ctx->px.world > 1;
+    ctx->px_next = want_exchange;  // the default kernel folds the exchange into its tail and clears this
+    if (int32_t rc = launch(ctx, cloud->d, cloud->n, t, d_out + static_cast<size_t>(r0) * HS_REC)) { ctx->px_next = false; return rc; }
+    if (ctx->px_next) {  // any other kernel: one more (single-block) launch does the exchange
+      ctx->px_next = false;
+      PeerExchange px = ctx->px;
+      px.epoch = ++ctx->px.epoch;
+      if (int32_t rc = launch_peer_allreduce(ctx, d_out + static_cast<size_t>(r0) * HS_REC, t.nrooms * HS_REC, px)) return rc;
+    }
   }
   return HS_OK;
 }
@@ -350,6 +360,52 @@ int32_t hs_rooms_cuboid_sums_async(hs_ctx* ctx, const hs_cloud* cloud, const int
   HS_LOCK(ctx);
   if (!d_rec_out) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums_async: null output");
   return rooms_sums_enqueue(ctx, cloud, room_offsets, nrooms, params, static_cast<double*>(d_rec_out));
+}
+
+int32_t hs_rooms_cuboid_sums_allreduce_async(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, const double* params, void* d_rec_out) {
+  HS_LOCK(ctx);
+  if (!d_rec_out) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums_allreduce_async: null output");
+  if (ctx->px.world < 1) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums_allreduce_async: no peer group (hs_peer_mailbox_create / hs_peer_mailbox_connect first)");
+  return rooms_sums_enqueue(ctx, cloud, room_offsets, nrooms, params, static_cast<double*>(d_rec_out), true);
+}
+
+// ---- peer group: CUDA IPC mailboxes between the per-GPU processes of one node ------------------------------------------
+int32_t hs_peer_mailbox_create(hs_ctx* ctx, int32_t rank, int32_t world, uint8_t handle_out[64]) {
+  HS_LOCK(ctx);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!handle_out || world < 1 || world > HS_PEER_MAX || rank < 0 || rank >= world) HS_FAIL(ctx, HS_EINVAL, "hs_peer_mailbox_create: need 0 <= rank < world <= 8");
+  if (ctx->d_mailbox) HS_FAIL(ctx, HS_EINVAL, "hs_peer_mailbox_create: this context already has a mailbox");
+  const size_t bytes = static_cast<size_t>(2) * HS_PEER_MAX * HS_MAX_ROOMS * HS_REC * sizeof(double) + HS_PEER_MAX * 32 * sizeof(uint32_t);
+  HS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_mailbox, bytes));
+  HS_CUDA_TRY(ctx, cudaMemset(ctx->d_mailbox, 0, bytes));
+  HS_CUDA_TRY(ctx, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  HS_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->d_mailbox));
+  std::memcpy(handle_out, &h, 64);
+  ctx->px = PeerExchange{};
+  ctx->px.rank = rank;
+  ctx->px.world = 0;  // not usable until connected
+  ctx->px.pad = static_cast<uint32_t>(world);
+  return HS_OK;
+}
+
+int32_t hs_peer_mailbox_connect(hs_ctx* ctx, const uint8_t* handles) {
+  HS_LOCK(ctx);
+  if (!handles || !ctx->d_mailbox) HS_FAIL(ctx, HS_EINVAL, "hs_peer_mailbox_connect: create the local mailbox first");
+  const int world = static_cast<int>(ctx->px.pad), rank = ctx->px.rank;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) { ctx->px.mailbox[p] = reinterpret_cast<unsigned long long>(ctx->d_mailbox); continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * p, 64);
+    void* ptr = nullptr;
+    HS_CUDA_TRY(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_mapped[p] = ptr;
+    ctx->px.mailbox[p] = reinterpret_cast<unsigned long long>(ptr);
+  }
+  ctx->px.world = world;
+  ctx->px.epoch = 0;
+  ctx->px.pad = 0;
+  return HS_OK;
 }
 
 int32_t hs_rooms_cuboid_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, const double* params, double* rec_out) {

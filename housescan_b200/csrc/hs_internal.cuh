@@ -11,7 +11,16 @@
 #define HS_MAX_ROOMS 32   // rooms per launch (kernel-parameter table); larger calls are chunked
 #define HS_MAX_PLANES 8   // generic planes per room
 #define HS_TPB 256        // threads per block of the streaming kernels
+#define HS_PEER_MAX 8     // ranks in a peer-memory all-reduce group (one NVSwitch domain)
 #define HS_NACC 22        // accumulators of a cuboid-sums record actually reduced (f, Sr[6], B[9], cnt[6])
+
+// peer-memory all-reduce of the record (k_peer.cuh); world == 0: no exchange
+struct PeerExchange {
+  unsigned long long mailbox[HS_PEER_MAX];  // device address of every rank's mailbox; [rank] is the local one
+  int32_t rank, world;
+  uint32_t epoch;  // launch counter, > 0, identical on all ranks
+  uint32_t pad;
+};
 
 struct hs_cloud {
   float* d = nullptr;
@@ -36,6 +45,11 @@ struct hs_ctx {
   char* h_pinned = nullptr;
   size_t pinned_bytes = 0;
   int modes[16] = {0};
+  // peer mailbox (multi-GPU): local allocation, the peers' mappings, the running epoch, and whether the next reduction exchanges
+  char* d_mailbox = nullptr;
+  void* peer_mapped[HS_PEER_MAX] = {nullptr};
+  PeerExchange px = {};
+  bool px_next = false;
   unsigned long long* d_dbg = nullptr;  // per-block timestamps of the evaluation kernel (mode key 5; tools only)
   std::mutex mu;
 };
@@ -72,6 +86,7 @@ int32_t hs_ensure_pinned(hs_ctx* ctx, size_t bytes);
 int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);       // exact Double products
 int32_t launch_rooms_cuboid_sums_fast(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);  // packed f32x2 + TMA ring
 int32_t launch_rooms_cuboid_sums_pred(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);  // scalar predicated + TMA ring
+int32_t launch_peer_allreduce(hs_ctx* ctx, double* d_buf, int count, const PeerExchange& px);  // standalone exchange kernel
 int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const PlaneTable& tbl, uint8_t* d_assign, float* d_resid);
 int32_t launch_plane_sums(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out /*K*HS_PS*/);
 

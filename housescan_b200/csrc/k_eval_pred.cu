@@ -18,6 +18,7 @@
 #include "k_ring.cuh"
 #include "k_eval_point.cuh"
 #include "k_eval_group_gen.cuh"
+#include "k_peer.cuh"
 
 namespace hsk {
 
@@ -404,7 +405,8 @@ __device__ __forceinline__ void point(ChainsP& c, const RoomK& R, float x, float
 template <int NCONS, int STAGES, int GPT, int PT, int WH>
 __global__ void __launch_bounds__(NCONS + 32, 1)
 k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_constant__ PredTable tbl, int64_t gpb,
-                         double* __restrict__ partials, int* __restrict__ meta, unsigned int* ticket, double* __restrict__ out) {
+                         double* __restrict__ partials, int* __restrict__ meta, unsigned int* ticket, double* __restrict__ out,
+                         const __grid_constant__ PeerExchange px) {
   constexpr int NW = NCONS / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
@@ -493,7 +495,7 @@ k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_
       const uint32_t tiles_s = smem_u32(tiles) + threadIdx.x * 48, full_s = smem_u32(full), empty_s = smem_u32(empty);
       int since_flush = 0;
       for (int t = 0; t < nfull; ++t) {
-        if (WH) mbar_wait_s(full_s + 8 * stage, parity); else mbar_wait(full + stage, parity);
+        if (WH == 2) mbar_wait_s_test(full_s + 8 * stage, parity); else if (WH == 1) mbar_wait_s(full_s + 8 * stage, parity); else mbar_wait(full + stage, parity);
         // this thread's GPT groups of the tile (group g * NCONS + tid): 4 consecutive points = 3 x LDS.128 each (48 B lane stride:
         // conflict-free quarter-warps)
         const uint32_t base = tiles_s + stage * TILE_BYTES;
@@ -514,7 +516,7 @@ k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_
       }
       tt += nfull;
       if (rem_groups) {  // partial last tile of the room segment: the threads whose group is in range
-        if (WH) mbar_wait_s(full_s + 8 * stage, parity); else mbar_wait(full + stage, parity);
+        if (WH == 2) mbar_wait_s_test(full_s + 8 * stage, parity); else if (WH == 1) mbar_wait_s(full_s + 8 * stage, parity); else mbar_wait(full + stage, parity);
         const uint32_t base = tiles_s + stage * TILE_BYTES;
         float4 q[GPT][3];
 #pragma unroll
@@ -599,19 +601,24 @@ k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_
         for (int k = 0; k < s_nbr[r]; ++k) sum += stage_d[(s_base[r] + k) * HS_NACC + c];
       out[o] = sum;
     }
-    return;
-  }
-  for (int o = threadIdx.x; o < nrooms * HS_REC; o += NCONS) {  // general fallback: one dependent load per block
-    const int r = o / HS_REC, c = o % HS_REC;
-    double sum = 0.0;
-    if (c < HS_NACC && tbl.off[r + 1] > tbl.off[r]) {
-      const int64_t b_lo = tbl.off[r] / ppb, b_hi = (tbl.off[r + 1] - 1) / ppb;
-      for (int64_t b = b_lo; b <= b_hi; ++b) {
-        const int slot = r - __ldcg(meta + b);
-        sum += __ldcg(partials + (b * nrooms + slot) * HS_NACC + c);
+  } else {
+    for (int o = threadIdx.x; o < nrooms * HS_REC; o += NCONS) {  // general fallback: one dependent load per block
+      const int r = o / HS_REC, c = o % HS_REC;
+      double sum = 0.0;
+      if (c < HS_NACC && tbl.off[r + 1] > tbl.off[r]) {
+        const int64_t b_lo = tbl.off[r] / ppb, b_hi = (tbl.off[r + 1] - 1) / ppb;
+        for (int64_t b = b_lo; b <= b_hi; ++b) {
+          const int slot = r - __ldcg(meta + b);
+          sum += __ldcg(partials + (b * nrooms + slot) * HS_NACC + c);
+        }
       }
+      out[o] = sum;
     }
-    out[o] = sum;
+  }
+  // ---------------- multi-GPU: the records of all ranks are summed over peer memory before the kernel ends (k_peer.cuh)
+  if (px.world > 1) {
+    consumers_sync_p<NCONS>();
+    peer_allreduce(px, out, nrooms * HS_REC, static_cast<int>(threadIdx.x), NCONS, [] { consumers_sync_p<NCONS>(); });
   }
 }
 
@@ -805,9 +812,21 @@ k_rooms_cuboid_sums_wring(const float* __restrict__ xyz, int64_t n, const __grid
   }
 }
 
+// standalone exchange for the kernels that do not carry it in their tail (one block)
+__global__ void __launch_bounds__(HS_TPB) k_peer_allreduce(double* buf, int count, const __grid_constant__ PeerExchange px) {
+  peer_allreduce(px, buf, count, static_cast<int>(threadIdx.x), HS_TPB, [] { __syncthreads(); });
+}
+
 }  // namespace hsk
 
 using namespace hsk;
+
+int32_t launch_peer_allreduce(hs_ctx* ctx, double* d_buf, int count, const PeerExchange& px) {
+  k_peer_allreduce<<<1, HS_TPB, 0, ctx->stream>>>(d_buf, count, px);
+  ctx->launches++;
+  HS_CUDA_TRY(ctx, cudaGetLastError());
+  return HS_OK;
+}
 
 template <int NCONS, int STAGES, int BPS, int GPT, int FORM>
 static int32_t launch_pred_t(hs_ctx* ctx, const float* xyz, int64_t n, const PredTable& tbl, double* d_rec_out) {
@@ -853,7 +872,9 @@ static int32_t launch_warp_t(hs_ctx* ctx, const float* xyz, int64_t n, const Pre
     HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_rooms_cuboid_sums_warp<NCONS, STAGES, GPT, PT, WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_set = true;
   }
-  k_rooms_cuboid_sums_warp<NCONS, STAGES, GPT, PT, WH><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out);
+  PeerExchange px = {};
+  if (ctx->px_next) { px = ctx->px; px.epoch = ++ctx->px.epoch; ctx->px_next = false; }  // fused exchange: consumed by this launch
+  k_rooms_cuboid_sums_warp<NCONS, STAGES, GPT, PT, WH><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out, px);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;
@@ -918,6 +939,7 @@ int32_t launch_rooms_cuboid_sums_pred(hs_ctx* ctx, const float* xyz, int64_t n, 
       case 5123: return launch_warp_t<512, 4, 2, 2>(ctx, xyz, n, t, d_rec_out);   // both
       case 7683: return launch_warp_t<768, 3, 2, 2>(ctx, xyz, n, t, d_rec_out);
       case 5124: return launch_warp_t<512, 4, 2, 2, 1>(ctx, xyz, n, t, d_rec_out);  // parked consumer waits
+      case 38435: return launch_warp_t<384, 3, 4, 2, 2>(ctx, xyz, n, t, d_rec_out);  // test_wait polling
       case 5133: return launch_warp_t<512, 3, 3, 2>(ctx, xyz, n, t, d_rec_out);     // three groups per thread per tile
       case 3843: return launch_warp_t<384, 4, 3, 2>(ctx, xyz, n, t, d_rec_out);
       case 6402: return launch_warp_t<640, 3, 2, 2>(ctx, xyz, n, t, d_rec_out);

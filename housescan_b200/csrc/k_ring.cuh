@@ -33,6 +33,12 @@ __device__ __forceinline__ void mbar_wait_s_spin(uint32_t bar, uint32_t parity) 
   asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra W_%=;\n}"
                ::"r"(bar), "r"(parity) : "memory");
 }
+// non-blocking flavour: test_wait returns at once, so a waiter notices the phase flip within a few cycles (try_wait may park
+// the thread for a hardware-defined quantum, which shows up as microseconds of start-up latency per launch)
+__device__ __forceinline__ void mbar_wait_s_test(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra W_%=;\n}"
+               ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {

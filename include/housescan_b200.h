@@ -98,6 +98,15 @@ HS_API int32_t hs_rooms_cuboid_sums(hs_ctx* ctx, const hs_cloud* cloud, const in
 /* same, enqueued on the ctx stream with the result left in device memory (nrooms x HS_REC doubles). */
 HS_API int32_t hs_rooms_cuboid_sums_async(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets,
                                           int32_t nrooms, const double* params, void* d_rec_out);
+/* multi-GPU (one process per GPU, one NVSwitch domain, <= 8 ranks): every rank reduces its point range and the records are
+ * summed over NVLink peer memory inside the same kernel launch (no NCCL call, no second launch); every rank ends up with
+ * the identical total in d_rec_out.  Setup once: each rank creates a mailbox and publishes its 64-byte CUDA IPC handle
+ * (any transport: torch.distributed, MPI, a file), then connects with the world's handles in rank order.  All ranks must
+ * issue the same sequence of hs_rooms_cuboid_sums_allreduce_async calls. */
+HS_API int32_t hs_peer_mailbox_create(hs_ctx* ctx, int32_t rank, int32_t world, uint8_t handle_out[64]);
+HS_API int32_t hs_peer_mailbox_connect(hs_ctx* ctx, const uint8_t* handles /* world x 64 bytes */);
+HS_API int32_t hs_rooms_cuboid_sums_allreduce_async(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets,
+                                                    int32_t nrooms, const double* params, void* d_rec_out);
 /* host chain rule: (params, summed record) -> f, grad, counts */
 HS_API int32_t hs_cuboid_grad_from_sums(const double params[10], const double rec[HS_REC], double* f, double grad[10],
                                         int64_t counts[6]);

@@ -22,6 +22,7 @@ ap.add_argument("--var", type=int, default=0)
 ap.add_argument("--tpi", type=int, default=1)
 ap.add_argument("--time", action="store_true")
 ap.add_argument("--psleep", type=int, default=0)
+ap.add_argument("--rooms", type=int, default=12)
 ap.add_argument("--blocks", action="store_true", help="print the per-block timeline of the last launch")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -40,11 +41,13 @@ torch.cuda.set_stream(s)
 ctx.set_stream(s.cuda_stream)
 params = bench.room_params()
 pe = np.ascontiguousarray(bench.eval_params(params))
-per = a.n // 12
-offs = np.arange(13, dtype=np.int64) * per
-buf, pts = bench.gen_points_torch(torch, dev, params, [per] * 12, seed=3)
-cloud = ctx.wrap(buf.data_ptr(), per * 12, keepalive=buf)
-rec = torch.zeros(12 * hb.HS_REC, dtype=torch.float64, device=dev)
+NR = a.rooms
+per = a.n // NR
+offs = np.arange(NR + 1, dtype=np.int64) * per
+params, pe = params[:NR], np.ascontiguousarray(pe[:NR])
+buf, pts = bench.gen_points_torch(torch, dev, params, [per] * NR, seed=3)
+cloud = ctx.wrap(buf.data_ptr(), per * NR, keepalive=buf)
+rec = torch.zeros(NR * hb.HS_REC, dtype=torch.float64, device=dev)
 torch.cuda.synchronize()
 for _ in range(3):
     ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
@@ -56,7 +59,7 @@ for _ in range(a.reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
-print(f"psleep={a.psleep} mode={a.mode} bps={a.bps} cons={a.cons} var={a.var} tpi={a.tpi} n={per*12} {ms*1e3:.1f} us/launch  {per*12/ms/1e6:.1f} Gpts/s  {per*12*12/ms/1e6:.0f} GB/s  frac_of_6553={per*12*12/ms/1e6/6553.3:.3f}")
+print(f"psleep={a.psleep} mode={a.mode} bps={a.bps} cons={a.cons} var={a.var} tpi={a.tpi} n={per*NR} rooms={NR} {ms*1e3:.1f} us/launch  {per*NR/ms/1e6:.1f} Gpts/s  {per*NR*12/ms/1e6:.0f} GB/s  frac_of_6553={per*NR*12/ms/1e6/6553.3:.3f}")
 
 if a.blocks:
     import ctypes as C
