@@ -1,0 +1,188 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle is only used where it finishes in
+seconds).  Inputs are generated on the device with torch (plumbing); every product call goes through the C ABI.
+
+C2  8 M-point room: rigid transforms, mean/extent, ceiling cut
+C3  100 M-point apartment: record additivity over shards, kernel forms agree, counts
+C4  voxel-plane graph, 20 M vertices: canonical labels bit-exact against the oracle + label properties
+C5  replayed depth stream: mask / count / compaction order, fused 6x6 records deterministic
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def _cloud(ctx, dev, n, seed):
+    """n room-like points on the device, wrapped as a cloud (padded, 16 B aligned)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    buf = torch.empty(3 * n + 32, dtype=torch.float32, device=dev)
+    pts = buf[: 3 * n].view(n, 3)
+    pts.copy_((torch.rand(n, 3, device=dev, generator=g) - 0.5) * torch.tensor([5.0, 2.6, 4.0], device=dev) + torch.tensor([0.3, 1.4, 4.0], device=dev))
+    return ctx.wrap(buf.data_ptr(), n, keepalive=buf), buf, pts
+
+
+def test_c2_transforms_8m(ctx, dev):
+    n = 8_000_000
+    cloud, buf, pts = _cloud(ctx, dev, n, 2)
+    out_buf = torch.empty_like(buf)
+    out = ctx.wrap(out_buf.data_ptr(), n, keepalive=out_buf)
+    o = out_buf[: 3 * n].view(n, 3)
+    # cyclic axis permutation about the origin is exact in Float (1*x + 0*y + 0*z): three applications are the identity
+    P = np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0]], np.float32)
+    zero = np.zeros(3, np.float32)
+    ctx.rotate_around(cloud, zero, P, out)
+    assert torch.equal(o, pts[:, [2, 0, 1]])
+    ctx.rotate_around(out, zero, P, out)  # in place
+    ctx.rotate_around(out, zero, P, out)
+    assert torch.equal(o, pts)
+    # projectRoom with the identity is the identity; with a pure translation it equals hs_translate, bit for bit
+    m = np.eye(4, dtype=np.float32)
+    ctx.transform(cloud, m, out)
+    assert torch.equal(o, pts)
+    off = np.array([1.5, -0.25, 3.0], np.float32)
+    m[3, :3] = off
+    ctx.transform(cloud, m, out)
+    first = o.clone()
+    ctx.translate(cloud, off, out)
+    assert torch.equal(o, first)
+    assert torch.equal(o, pts + torch.from_numpy(off).to(dev))
+    # mean is linear; the extent is translation invariant up to Float rounding of the mean
+    mean0, ext0 = ctx.mean_extent(cloud)
+    mean1, ext1 = ctx.mean_extent(out)
+    assert np.allclose(mean1 - mean0, off.astype(np.float64), rtol=0, atol=2e-7)
+    assert np.allclose(mean0, pts.double().mean(dim=0).cpu().numpy(), rtol=1e-12)
+    assert abs(float(ext1) - float(ext0)) < 1e-5
+
+
+def test_c2_ceiling_cut_8m(ctx, dev):
+    n = 8_000_000
+    cloud, buf, pts = _cloud(ctx, dev, n, 22)
+    y = pts[:, 1]
+    k = n // 5
+    v = float(ctx.kth_largest(cloud, 1, k))
+    assert int((y > v).sum().item()) < k <= int((y >= v).sum().item())  # definition of the k-th largest value
+    assert v == float(torch.topk(y, k).values[-1].item())
+    out, _, ylim = ctx.remove_ceiling(cloud)
+    assert float(ylim) == v
+    kept = y <= v
+    n_kept = int(kept.sum().item())
+    got = torch.empty(3 * n_kept, dtype=torch.float32, device=dev)
+    lib = ctx.lib
+    # the filtered cloud keeps input order (V.filter): compare against the torch boolean mask, bit for bit
+    host = out.download()[:n_kept]
+    assert np.array_equal(host.view(np.uint32), pts[kept].cpu().numpy().view(np.uint32))
+    # idempotent: cutting the already cut cloud at the same limit changes nothing
+    c2 = ctx.upload(host)
+    again, _ = ctx.filter_le(c2, 1, v)
+    assert np.array_equal(again.download()[:n_kept].view(np.uint32), host.view(np.uint32))
+    del got, lib
+
+
+def test_c3_apartment_records_100m(ctx, dev):
+    import bench
+    import housescan_b200 as hb
+
+    params = bench.room_params()
+    pe = np.ascontiguousarray(bench.eval_params(params))
+    per = 8_333_334
+    n = per * 12
+    buf, pts = bench.gen_points_torch(torch, dev, params, [per] * 12, seed=3)
+    cloud = ctx.wrap(buf.data_ptr(), n, keepalive=buf)
+    offs = np.arange(13, dtype=np.int64) * per
+    rec = ctx.rooms_cuboid_sums(cloud, offs, pe)
+    assert np.array_equal(rec[:, 16:22].sum(axis=1), np.full(12, per, np.float64))  # every point lands on exactly one wall
+    # additive over point shards that cut through rooms (what the multi-GPU path relies on)
+    from housescan_b200.rooms import local_room_offsets, shard_range
+
+    total = np.zeros_like(rec)
+    for r in range(3):
+        lo, hi = shard_range(n, r, 3)
+        sh = ctx.wrap(buf.data_ptr() + 12 * lo, hi - lo, keepalive=buf)
+        total += ctx.rooms_cuboid_sums(sh, local_room_offsets(offs, lo, hi), pe)
+    assert np.array_equal(total[:, 16:22], rec[:, 16:22])
+    scale = np.abs(rec) + 1e-9 * np.abs(rec).max(axis=1, keepdims=True)
+    assert np.max(np.abs(total - rec) / scale) < 1e-6
+    # the three kernel forms (default, packed f32x2, exact Double products) agree: counts bit-exact, sums within the bar
+    for key0, key3 in ((2, 7), (1, 0)):
+        ctx.set_mode(0, key0)
+        ctx.set_mode(3, key3)
+        other = ctx.rooms_cuboid_sums(cloud, offs, pe)
+        ctx.set_mode(0, 0)
+        ctx.set_mode(3, 0)
+        assert np.array_equal(other[:, 16:22], rec[:, 16:22])
+        assert abs(other[:, 0] - rec[:, 0]).max() <= 1e-6 * rec[:, 0].max()
+    # one room against the oracle (8.3 M points: a second on the CPU)
+    import oracle as O
+
+    r0 = O.cuboid_sums(pts[:per].cpu().numpy(), pe[0])
+    assert np.array_equal(r0[16:22], rec[0, 16:22]) and abs(r0[0] - rec[0, 0]) <= 1e-6 * r0[0]
+    f, g, cnt = hb.cuboid_grad_from_sums(pe[0], rec[0])
+    assert np.isfinite(g).all() and cnt.sum() == per
+
+
+def test_c4_components_20m(ctx, dev):
+    P, S = 20, 1000
+    N = P * S * S
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    vid = torch.arange(N, device=dev, dtype=torch.int64).view(P, S, S)
+    e = torch.cat([torch.stack([vid[:, :, :-1].reshape(-1), vid[:, :, 1:].reshape(-1)]),
+                   torch.stack([vid[:, :-1, :].reshape(-1), vid[:, 1:, :].reshape(-1)])], dim=1)
+    e = e[:, torch.rand(e.shape[1], device=dev, generator=g) >= 0.03]
+    src, dst = e[0].to(torch.int32).contiguous(), e[1].to(torch.int32).contiguous()
+    E = src.numel()
+    lab = torch.empty(N, dtype=torch.int32, device=dev)
+    ctx._chk(ctx.lib.hs_cc_label_dev(ctx.h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), E, N, C.c_void_p(lab.data_ptr())))
+    torch.cuda.synchronize()
+    l64 = lab.long()
+    ar = torch.arange(N, device=dev)
+    assert bool((l64 <= ar).all()) and torch.equal(l64[l64], l64)       # label = a vertex of the component, itself a fixed point
+    assert torch.equal(l64[src.long()], l64[dst.long()])                  # every edge joins equal labels
+    import oracle as O
+
+    ref = O.cc_label(src.cpu().numpy().astype(np.uint32), dst.cpu().numpy().astype(np.uint32), N)
+    assert np.array_equal(ref, lab.cpu().numpy().astype(np.uint32))       # canonical min-index labels, bit-exact
+
+
+def test_c5_depth_stream_200_frames(ctx, dev):
+    import housescan_b200 as hb
+    from housescan_b200 import synth
+    from housescan_b200._lib import ptr
+
+    w, h, nf = 640, 480, 200
+    base, _ = synth.depth_stream(8, w, h)
+    frames = torch.from_numpy(base.astype(np.int32)).to(dev).to(torch.int16).repeat(nf // 8, 1, 1).contiguous()
+    npx = nf * w * h
+    out = torch.empty(npx * 3 + 16, dtype=torch.float32, device=dev)
+    cloud = ctx.wrap(out.data_ptr(), npx, keepalive=out)
+    mask = torch.empty(npx, dtype=torch.uint8, device=dev)
+    nv = C.c_int64()
+    ctx._chk(ctx.lib.hs_backproject_ref_dev(ctx.h, C.c_void_p(frames.data_ptr()), w, h * nf, cloud.h, C.c_void_p(mask.data_ptr()), C.byref(nv)))
+    torch.cuda.synchronize()
+    valid = frames.view(-1) != 0
+    assert nv.value == int(valid.sum().item()) and torch.equal(mask.bool(), valid)
+    idx = torch.nonzero(valid).view(-1)
+    d = (frames.view(-1)[idx].int() & 0xFFFF).float()
+    ten, twenty = torch.full_like(d, 10.0), torch.full_like(d, 20.0)  # tensor divisors: true IEEE division, as Main.hs:1311-1313
+    exp = torch.stack([torch.div((idx % w).float(), ten), torch.div((idx // w).float(), ten), torch.div(d, twenty) - 30.0], dim=1)
+    assert torch.equal(out[: 3 * nv.value].view(-1, 3), exp)              # raster order kept, scaling bit-exact
+    planes = hb.planes_from_cuboid(synth.C1_PARAMS)
+    intr = np.array(synth.KINFU_INTR, np.float32)
+    rec = torch.empty(nf * hb.HS_NE, dtype=torch.float64, device=dev)
+    ctx._chk(ctx.lib.hs_backproject_reduce6x6_dev(ctx.h, C.c_void_p(frames.data_ptr()), nf, w, h, ptr(intr), None, ptr(planes), 6, C.c_void_p(rec.data_ptr())))
+    torch.cuda.synchronize()
+    r = rec.view(nf, hb.HS_NE)
+    assert torch.equal(r[:, 28].long(), (frames != 0).view(nf, -1).sum(dim=1))
+    assert torch.equal(r[:8].repeat(nf // 8, 1), r)                       # replayed frames: bit-identical records whoever computed them
+    host = ctx.backproject_reduce6x6(base[:2], w, h, planes, intr=intr)   # host-buffer entry point, same records
+    assert np.array_equal(host, r[:2].cpu().numpy())
