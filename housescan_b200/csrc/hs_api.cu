@@ -196,7 +196,7 @@ int32_t hs_cloud_free(hs_ctx* ctx, hs_cloud* cloud) {
 // ---- (1) depth frames ----------------------------------------------------------------------------------------------
 int32_t hs_backproject_ref_dev(hs_ctx* ctx, const void* d_depth, int32_t w, int32_t h, hs_cloud* cloud_out, void* d_mask, int64_t* n_valid) {
   HS_LOCK(ctx);
-  if (w <= 0 || h <= 0 || !d_depth) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_ref: bad frame");
+  if (w <= 0 || h <= 0 || w > 65535 || h > 65535 || !d_depth) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_ref: bad frame");
   const int64_t npx = static_cast<int64_t>(w) * h;
   if (cloud_out && cloud_out->cap < npx) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_ref: output cloud smaller than w*h");
   int64_t* d_n = reinterpret_cast<int64_t*>(ctx->d_small);
@@ -248,15 +248,18 @@ int32_t hs_backproject_reduce6x6_dev(hs_ctx* ctx, const void* d_frames, int64_t 
   if (!d_frames || nframes < 0 || w <= 0 || h <= 0 || !d_out) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_reduce6x6: bad arguments");
   PlaneTable t;
   if (int32_t rc = fill_plane_table(ctx, planes, K, 16, t, "hs_backproject_reduce6x6")) return rc;
+  if (w > 65535 || h > 65535) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_reduce6x6: frame sides are limited to 65535");
   float* d_poses = nullptr;
+  const size_t pose_bytes = poses ? static_cast<size_t>(nframes) * 64 : 0;  // multiple of 64: the work area stays aligned
+  if (int32_t rc = hs_ensure_scratch(ctx, pose_bytes + reduce6x6_work_bytes(ctx, nframes, w, h))) return rc;
   if (poses) {
-    if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(nframes) * 64)) return rc;
     d_poses = reinterpret_cast<float*>(ctx->d_scratch);
-    if (int32_t rc = copy_h2d(ctx, d_poses, poses, static_cast<size_t>(nframes) * 64)) return rc;
+    if (int32_t rc = copy_h2d(ctx, d_poses, poses, pose_bytes)) return rc;
     HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // caller's pose buffer is not retained
   }
   if (nframes == 0) return HS_OK;
-  return launch_reduce6x6(ctx, static_cast<const uint16_t*>(d_frames), nframes, w, h, intr, d_poses, t, static_cast<double*>(d_out));
+  return launch_reduce6x6(ctx, static_cast<const uint16_t*>(d_frames), nframes, w, h, intr, d_poses, t, static_cast<double*>(d_out),
+                          ctx->d_scratch + pose_bytes);
 }
 
 int32_t hs_backproject_reduce6x6(hs_ctx* ctx, const uint16_t* frames, int64_t nframes, int32_t w, int32_t h, const float* intr,

@@ -54,7 +54,11 @@ struct hs_ctx {
   std::mutex mu;
 };
 
-enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1, HS_MODE_EVAL_CONSUMERS = 2, HS_MODE_EVAL_VARIANT = 3, HS_MODE_EVAL_TPI = 4, HS_MODE_DEBUG_TIMES = 5 };
+enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1, HS_MODE_EVAL_CONSUMERS = 2, HS_MODE_EVAL_VARIANT = 3, HS_MODE_EVAL_TPI = 4, HS_MODE_DEBUG_TIMES = 5,
+       HS_MODE_NE_KERNEL = 6,   // 6x6 record: 0 = throughput form (Float chains), 1 = all-Double form
+       HS_MODE_PS_KERNEL = 7,   // per-plane sums: 0 = throughput form, 1 = all-Double form
+       HS_MODE_SEL_KERNEL = 8   // k-th: 0 = 11/11/10-bit passes over compacted keys, 1 = four 8-bit passes over the cloud
+};
 enum { HS_EVAL_AUTO = 0, HS_EVAL_EXACT = 1, HS_EVAL_FAST = 2 };  // values of modes[HS_MODE_EVAL_KERNEL]
 
 // table of rooms passed by value to the evaluation kernels
@@ -96,8 +100,9 @@ int32_t launch_max_nsq(hs_ctx* ctx, const float* xyz, int64_t n, const float m[3
 int32_t launch_scatter(hs_ctx* ctx, const float* xyz, int64_t n, const float m[3], double* d_sc6);
 
 int32_t launch_backproject(hs_ctx* ctx, const uint16_t* d_depth, int32_t w, int32_t h, float* d_xyz, uint8_t* d_mask, int64_t* d_nvalid);
+size_t reduce6x6_work_bytes(const hs_ctx* ctx, int64_t nframes, int32_t w, int32_t h);  // d_work of launch_reduce6x6
 int32_t launch_reduce6x6(hs_ctx* ctx, const uint16_t* d_frames, int64_t nframes, int32_t w, int32_t h, const float* intr,
-                         const float* d_poses, const PlaneTable& tbl, double* d_out);
+                         const float* d_poses, const PlaneTable& tbl, double* d_out, char* d_work);
 
 int32_t launch_cc(hs_ctx* ctx, const uint32_t* d_src, const uint32_t* d_dst, int64_t E, uint32_t N, uint32_t* d_label);
 

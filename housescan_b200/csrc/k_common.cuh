@@ -10,6 +10,23 @@ __device__ __forceinline__ float plane_dist(float nx, float ny, float nz, float 
   return __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, x), __fmul_rn(ny, y)), __fmul_rn(nz, z)), d);
 }
 
+// Correctly rounded Float division by a divisor that is the same for every point, without the MUFU.RCP + range-check sequence
+// that `/` compiles to (~12 instructions and a slow-path branch per quotient).  y must be RN(1/b) (computed once on the host with
+// an IEEE division).  q0 = RN(a y) is within 2 ulp of a/b; one residual step makes it faithful; by Markstein's theorem
+// (y = RN(1/b), q faithful, r = a - b q exact in an FMA  =>  RN(q + r y) = RN(a/b)) the second step is the IEEE quotient.
+// Valid while nothing under/overflows, which holds for pixel coordinates and depths.
+__device__ __forceinline__ float div_rn_by(float a, float b, float y) {
+  const float q0 = __fmul_rn(a, y);
+  const float q1 = __fmaf_rn(__fmaf_rn(-b, q0, a), y, q0);
+  return __fmaf_rn(__fmaf_rn(-b, q1, a), y, q1);
+}
+// Same for integer-valued a in [0, 65535] and b in {10, 20}: one residual step already gives the IEEE quotient for every such a
+// (checked exhaustively: tests/test_host_logic.py::test_constant_division_sequence).
+__device__ __forceinline__ float div_rn_small(float a, float b, float y) {
+  const float q0 = __fmul_rn(a, y);
+  return __fmaf_rn(__fmaf_rn(-b, q0, a), y, q0);
+}
+
 // one thread's 4 consecutive AoS points = 3 x float4 (48 B, 16 B aligned)
 struct Pts4 {
   float x[4], y[4], z[4];

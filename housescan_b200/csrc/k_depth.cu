@@ -11,10 +11,13 @@ namespace hsk {
 
 #define BP_TILE 2048  // pixels per block-tile: 8 consecutive pixels (one 16-byte load) per thread
 
+// x, y < 65536 (checked by the API) and d is a uint16, so the quotients come from div_rn_small: bit-identical to `/`.
+#define HS_RCP10 __fdiv_rn(1.0f, 10.0f)
+#define HS_RCP20 __fdiv_rn(1.0f, 20.0f)
 __device__ __forceinline__ void scale_point(int x, int y, unsigned int d, float& X, float& Y, float& Z) {
-  X = __fdiv_rn(static_cast<float>(x), 10.0f);
-  Y = __fdiv_rn(static_cast<float>(y), 10.0f);
-  Z = __fsub_rn(__fdiv_rn(static_cast<float>(d), 20.0f), 30.0f);
+  X = div_rn_small(static_cast<float>(x), 10.0f, HS_RCP10);
+  Y = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
+  Z = __fsub_rn(div_rn_small(static_cast<float>(d), 20.0f, HS_RCP20), 30.0f);
 }
 
 // this thread's 8 pixels of tile t (zeros past the end of the frame)
@@ -248,6 +251,175 @@ k_reduce6x6(const uint16_t* __restrict__ frames, int64_t nframes, int w, int h, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Throughput form of the same record (default).  Identical per-pixel Float geometry (so the plane choice, J and r are
+// bit-identical to k_reduce6x6 and to the oracle); what changes is everything around it:
+//   * the two back-projection quotients per pixel use the exact constant-divisor sequences of k_common.cuh instead of `/`;
+//   * the winner's residual is recomputed from the winner's plane (one LDS.128 + 6 ops) instead of being carried through the
+//     selection chain, and the running minimum is an FMNMX: 5 issue cycles per plane instead of 8;
+//   * the 29 sums run as Float FMA chains over 16 pixels per thread and are then added into per-thread Doubles (the product
+//     inside an FMA is exact; only the 16-term partial sums are rounded to Float, ~1e-8 of the record after the Double sums) —
+//     29 FFMA + 7 F2F/DADD per pixel-row instead of 29 DFMA at half rate;
+//   * a frame is cut into `parts` row bands handed out through the item counter, so 1000 frames fill 296 resident blocks
+//     evenly; the band that finishes a frame last adds the bands in band order (deterministic).
+// Requires w % 8 == 0 (a thread's 8 pixels share a row) and 16-byte aligned frames; the launcher falls back otherwise.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool INTR, bool POSE, int KT>
+__device__ __forceinline__ PixelJ ne_geometry_fast(const FrameGeom& geo, float rfx, float rfy, const float (&M)[12], const PlaneTable& tbl,
+                                                   const float4* __restrict__ spl, float xf, float yc /* INTR: y - cy; else y/10 */, unsigned int d) {
+  float X, Y, Z;
+  const float df = static_cast<float>(d);
+  if (INTR) {
+    Z = __fmul_rn(df, 0.001f);
+    X = div_rn_by(__fmul_rn(__fsub_rn(xf, geo.cx), Z), geo.fx, rfx);
+    Y = div_rn_by(__fmul_rn(yc, Z), geo.fy, rfy);
+  } else {
+    X = div_rn_small(xf, 10.0f, HS_RCP10);
+    Y = yc;
+    Z = __fsub_rn(div_rn_small(df, 20.0f, HS_RCP20), 30.0f);
+  }
+  float px = X, py = Y, pz = Z;
+  if (POSE) {
+    px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[0]), __fmul_rn(Y, M[3])), __fmul_rn(Z, M[6])), M[9]);
+    py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[1]), __fmul_rn(Y, M[4])), __fmul_rn(Z, M[7])), M[10]);
+    pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[2]), __fmul_rn(Y, M[5])), __fmul_rn(Z, M[8])), M[11]);
+  }
+  float ab = fabsf(plane_dist(tbl.pl[0][0], tbl.pl[0][1], tbl.pl[0][2], tbl.pl[0][3], px, py, pz));
+  int kb = 0;
+  if (KT > 0) {
+#pragma unroll
+    for (int k = 1; k < KT; ++k) {
+      const float ak = fabsf(plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], px, py, pz));
+      kb = (ak < ab) ? k : kb;  // strict: ties keep the lower index
+      ab = fminf(ab, ak);
+    }
+  } else {
+    for (int k = 1; k < tbl.K; ++k) {
+      const float ak = fabsf(plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], px, py, pz));
+      kb = (ak < ab) ? k : kb;
+      ab = fminf(ab, ak);
+    }
+  }
+  const float4 nn = spl[kb];
+  PixelJ o;
+  o.j[0] = __fsub_rn(__fmul_rn(py, nn.z), __fmul_rn(pz, nn.y));
+  o.j[1] = __fsub_rn(__fmul_rn(pz, nn.x), __fmul_rn(px, nn.z));
+  o.j[2] = __fsub_rn(__fmul_rn(px, nn.y), __fmul_rn(py, nn.x));
+  o.j[3] = nn.x; o.j[4] = nn.y; o.j[5] = nn.z;
+  o.r = plane_dist(nn.x, nn.y, nn.z, nn.w, px, py, pz);  // same operations on the same operands as in the loop: same bits
+  return o;
+}
+__device__ __forceinline__ void ne_accumulate_f32(float (&acc)[HS_NE], const PixelJ& p) {
+  int t = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a; b < 6; ++b) { acc[t] = __fmaf_rn(p.j[a], p.j[b], acc[t]); ++t; }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) acc[21 + a] = __fmaf_rn(p.j[a], p.r, acc[21 + a]);
+  acc[27] = __fmaf_rn(p.r, p.r, acc[27]);
+  acc[28] = __fadd_rn(acc[28], 1.0f);
+}
+
+#ifndef NE_ILP
+#define NE_ILP 4
+#endif
+template <bool INTR, bool POSE, int KT>
+__global__ void __launch_bounds__(HS_TPB, 2)
+k_reduce6x6_f32(const uint16_t* __restrict__ frames, int64_t nframes, int w, int h, const FrameGeom geo, float rfx, float rfy,
+                const float* __restrict__ poses, const __grid_constant__ PlaneTable tbl, int parts, double* __restrict__ partials,
+                unsigned int* __restrict__ part_done, double* __restrict__ out, unsigned int* counters /* [0] next item, [1] blocks done */) {
+  extern __shared__ double sdacc[];  // [HS_NE][HS_TPB]: every thread's Double sums (registers are for the Float chains)
+  __shared__ double smem[(HS_TPB / 32) * HS_NE];
+  __shared__ float4 spl[16];
+  __shared__ unsigned int s_item;
+  __shared__ bool s_last;
+  if (threadIdx.x < tbl.K) spl[threadIdx.x] = make_float4(tbl.pl[threadIdx.x][0], tbl.pl[threadIdx.x][1], tbl.pl[threadIdx.x][2], tbl.pl[threadIdx.x][3]);
+  const int npx = w * h;
+  const int ng = npx >> 3;                    // 8-pixel groups per frame
+  const int gpp = (ng + parts - 1) / parts;   // groups per band
+  const int64_t nitems = nframes * parts;
+  const int dy = (8 * HS_TPB) / w, dx = (8 * HS_TPB) - dy * w;  // one loop step = 2048 pixels further on
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(counters, 1u);
+    __syncthreads();
+    const int64_t item = s_item;
+    if (item >= nitems) break;
+    const int64_t fr = item / parts;
+    const int part = static_cast<int>(item - fr * parts);
+    const uint4* dep8 = reinterpret_cast<const uint4*>(frames + fr * npx);
+    float M[12];
+    if (POSE) {
+      const float* pm = poses + 16 * fr;
+      M[0] = pm[0]; M[1] = pm[1]; M[2] = pm[2]; M[3] = pm[4]; M[4] = pm[5]; M[5] = pm[6];
+      M[6] = pm[8]; M[7] = pm[9]; M[8] = pm[10]; M[9] = pm[12]; M[10] = pm[13]; M[11] = pm[14];
+    }
+    float acc[HS_NE];
+#pragma unroll
+    for (int i = 0; i < HS_NE; ++i) { sdacc[i * HS_TPB + threadIdx.x] = 0.0; acc[i] = 0.0f; }
+    const int g_lo = part * gpp, g_hi = min(g_lo + gpp, ng);
+    int g = g_lo + threadIdx.x;
+    int y = (g << 3) / w, x = (g << 3) - y * w;
+    int it = 0;
+    for (; g < g_hi; g += HS_TPB, ++it) {
+      const uint4 v = __ldcs(dep8 + g);
+      const unsigned int wv[4] = {v.x, v.y, v.z, v.w};
+      const float x0f = static_cast<float>(x), yf = static_cast<float>(y);
+      const float yc = INTR ? __fsub_rn(yf, geo.cy) : div_rn_small(yf, 10.0f, HS_RCP10);
+#pragma unroll
+      for (int q = 0; q < 8 / NE_ILP; ++q) {  // NE_ILP pixels' geometry in flight, then their accumulation
+        PixelJ pj[NE_ILP];
+        unsigned int dd[NE_ILP];
+#pragma unroll
+        for (int e = 0; e < NE_ILP; ++e) {
+          const int px = NE_ILP * q + e;
+          dd[e] = (wv[px >> 1] >> (16 * (px & 1))) & 0xffffu;
+          pj[e] = ne_geometry_fast<INTR, POSE, KT>(geo, rfx, rfy, M, tbl, spl, __fadd_rn(x0f, static_cast<float>(px)), yc, dd[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < NE_ILP; ++e)
+          if (dd[e] != 0) ne_accumulate_f32(acc, pj[e]);
+      }
+      if (it & 1) {  // 16 pixels per chain
+#pragma unroll
+        for (int i = 0; i < HS_NE; ++i) { sdacc[i * HS_TPB + threadIdx.x] += static_cast<double>(acc[i]); acc[i] = 0.0f; }
+      }
+      x += dx; y += dy;
+      if (x >= w) { x -= w; ++y; }
+    }
+    double dacc[HS_NE];
+#pragma unroll
+    for (int i = 0; i < HS_NE; ++i) dacc[i] = sdacc[i * HS_TPB + threadIdx.x] + static_cast<double>(acc[i]);
+    if (parts == 1) {
+      block_sum_store<HS_NE>(dacc, out + fr * HS_NE, smem);
+      continue;
+    }
+    block_sum_store<HS_NE>(dacc, partials + item * HS_NE, smem);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(part_done + fr, 1u);
+      s_last = (t == static_cast<unsigned int>(parts) - 1u);
+      if (s_last) part_done[fr] = 0u;  // re-armed for the next launch
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (threadIdx.x < HS_NE) {
+        double s = 0.0;
+        for (int p = 0; p < parts; ++p) s += __ldcg(partials + (fr * parts + p) * HS_NE + threadIdx.x);
+        out[fr * HS_NE + threadIdx.x] = s;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(counters + 1, 1u) == gridDim.x - 1) { counters[0] = 0u; counters[1] = 0u; }
+  }
+}
+
 }  // namespace hsk
 
 using namespace hsk;
@@ -270,14 +442,53 @@ int32_t launch_backproject(hs_ctx* ctx, const uint16_t* d_depth, int32_t w, int3
   return HS_OK;
 }
 
+// bands per frame so that the item count is >= 16 x the resident blocks (even tail), 1 when there are plenty of frames
+static int ne_parts(const hs_ctx* ctx, int64_t nframes, int32_t w, int32_t h) {
+  const int64_t want = static_cast<int64_t>(ctx->sm_count) * 2 * 16;
+  int parts = 1;
+  while (parts < 8 && nframes * parts < want && (static_cast<int64_t>(w) * h >> 3) / (parts * 2) >= 4 * HS_TPB) parts *= 2;
+  return parts;
+}
+size_t reduce6x6_work_bytes(const hs_ctx* ctx, int64_t nframes, int32_t w, int32_t h) {
+  const int parts = ne_parts(ctx, nframes, w, h);
+  return static_cast<size_t>(nframes) * parts * HS_NE * sizeof(double) + static_cast<size_t>(nframes) * sizeof(unsigned int) + 64;
+}
+
 int32_t launch_reduce6x6(hs_ctx* ctx, const uint16_t* d_frames, int64_t nframes, int32_t w, int32_t h, const float* intr,
-                         const float* d_poses, const PlaneTable& tbl, double* d_out) {
+                         const float* d_poses, const PlaneTable& tbl, double* d_out, char* d_work) {
   FrameGeom geo{};
   geo.use_intr = intr != nullptr;
   if (intr) { geo.fx = intr[0]; geo.fy = intr[1]; geo.cx = intr[2]; geo.cy = intr[3]; }
+  unsigned int* counters = ctx->d_ticket + 8;  // zero between launches (re-armed by the kernel)
+  const bool fast_ok = (w % 8) == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15) == 0 && d_work != nullptr;
+  if (ctx->modes[HS_MODE_NE_KERNEL] != 1 && fast_ok) {
+    const int parts = ne_parts(ctx, nframes, w, h);
+    double* partials = reinterpret_cast<double*>(d_work);
+    unsigned int* part_done = reinterpret_cast<unsigned int*>(d_work + static_cast<size_t>(nframes) * parts * HS_NE * sizeof(double));
+    if (parts > 1) HS_CUDA_TRY(ctx, cudaMemsetAsync(part_done, 0, static_cast<size_t>(nframes) * sizeof(unsigned int), ctx->stream));
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nframes * parts, static_cast<int64_t>(ctx->sm_count) * 2)));
+    const float rfx = intr ? 1.0f / geo.fx : 0.f, rfy = intr ? 1.0f / geo.fy : 0.f;  // RN(1/f): IEEE division on the host
+    const int dsm = HS_NE * HS_TPB * static_cast<int>(sizeof(double));
+#define HS_NEF_LAUNCH(I, P, KT_)                                                                                       \
+  cudaFuncSetAttribute(k_reduce6x6_f32<I, P, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm);                  \
+  k_reduce6x6_f32<I, P, KT_><<<grid, HS_TPB, dsm, ctx->stream>>>(d_frames, nframes, w, h, geo, rfx, rfy, d_poses, tbl, parts, partials, part_done, d_out, counters)
+#define HS_NEF_PICK(KT_)                                  \
+  do {                                                    \
+    if (intr && d_poses) { HS_NEF_LAUNCH(true, true, KT_); }  \
+    else if (intr) { HS_NEF_LAUNCH(true, false, KT_); }       \
+    else if (d_poses) { HS_NEF_LAUNCH(false, true, KT_); }    \
+    else { HS_NEF_LAUNCH(false, false, KT_); }                \
+  } while (0)
+    if (tbl.K == 6) HS_NEF_PICK(6);
+    else HS_NEF_PICK(0);
+#undef HS_NEF_PICK
+#undef HS_NEF_LAUNCH
+    ctx->launches++;
+    HS_CUDA_TRY(ctx, cudaGetLastError());
+    return HS_OK;
+  }
   int64_t nb = std::min<int64_t>(nframes, static_cast<int64_t>(ctx->sm_count) * 2);
   if (nb < 1) nb = 1;
-  unsigned int* counters = ctx->d_ticket + 8;  // zero between launches (re-armed by the kernel)
   const int grid = static_cast<int>(nb);
 #define HS_NE_LAUNCH(I, P, KT_) k_reduce6x6<I, P, KT_><<<grid, HS_TPB, 0, ctx->stream>>>(d_frames, nframes, w, h, geo, d_poses, tbl, d_out, counters)
 #define HS_NE_PICK(KT_)                                  \

@@ -153,9 +153,28 @@ __device__ __forceinline__ int nearestK(const PlaneTable& t, float x, float y, f
   return kb;
 }
 
+// same choice with a cheaper selection chain: only the index is carried (FSETP + SEL) and the running minimum is an FMNMX;
+// the winner's residual is recomputed from its plane (one LDS.128 + the same six operations => the same bits)
+__device__ __forceinline__ int nearestK_lds(const PlaneTable& t, const float4* __restrict__ spl, float x, float y, float z, float& r) {
+  float ab = fabsf(plane_dist(t.pl[0][0], t.pl[0][1], t.pl[0][2], t.pl[0][3], x, y, z));
+  int kb = 0;
+  for (int k = 1; k < t.K; ++k) {
+    const float ak = fabsf(plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z));
+    kb = (ak < ab) ? k : kb;
+    ab = fminf(ab, ak);
+  }
+  const float4 nn = spl[kb];
+  r = plane_dist(nn.x, nn.y, nn.z, nn.w, x, y, z);
+  return kb;
+}
+#define nearestK(tbl, x, y, z, r) nearestK_lds(tbl, spl, x, y, z, r)
+
 __global__ void __launch_bounds__(HS_TPB)
 k_plane_assign(const float* __restrict__ xyz, int64_t n, const __grid_constant__ PlaneTable tbl, uint8_t* __restrict__ assign,
                float* __restrict__ resid) {
+  __shared__ float4 spl[16];
+  if (threadIdx.x < tbl.K) spl[threadIdx.x] = make_float4(tbl.pl[threadIdx.x][0], tbl.pl[threadIdx.x][1], tbl.pl[threadIdx.x][2], tbl.pl[threadIdx.x][3]);
+  __syncthreads();
   const int64_t gfull = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
   for (int64_t g = static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x; g < gfull; g += stride) {
@@ -177,6 +196,8 @@ k_plane_assign(const float* __restrict__ xyz, int64_t n, const __grid_constant__
     if (resid) resid[i] = r;
   }
 }
+
+#undef nearestK
 
 // ------------------------------------------------------------------------------------------------------------------
 // generic per-plane sums over one point range [i0, i1): out[k] = count, sum r, sum r^2, sum p(3), sum r p(3), max|r|
@@ -253,6 +274,103 @@ k_plane_sums(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid
     last_block_sum_strided(partials + static_cast<int64_t>(k) * HS_PS, gridDim.x, K * HS_PS, out + k * HS_PS, fin);
 }
 
+
+// Throughput form of the same record (default for K <= 6).  The plane choice and the residual are the same Float operations as
+// above (bit-identical); the nine sums per plane run as predicated Float chains over 32 points per thread (the product inside an
+// FMA is exact, only the short partial sums are rounded to Float), and are then added into per-thread Doubles that live in shared
+// memory, so the registers hold the 10 K chains and four points in flight instead of 9 K Doubles.  Points are read as 4-point
+// groups (3 x LDG.128); the ragged head and tail of the range (room offsets are arbitrary) are taken one point per thread.
+template <int K>
+__device__ __forceinline__ void ps_add(float (&a)[K][9], float (&mx)[K], const PlaneTable& tbl, const float4* __restrict__ spl, float x, float y, float z) {
+  float ab = fabsf(plane_dist(tbl.pl[0][0], tbl.pl[0][1], tbl.pl[0][2], tbl.pl[0][3], x, y, z));
+  int kb = 0;
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    const float ak = fabsf(plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], x, y, z));
+    kb = (ak < ab) ? k : kb;  // strict: ties keep the lower index
+    ab = fminf(ab, ak);
+  }
+  const float4 nn = spl[kb];
+  const float r = plane_dist(nn.x, nn.y, nn.z, nn.w, x, y, z);  // the winner's residual: same operations, same bits
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (kb == k) {
+      a[k][0] = __fadd_rn(a[k][0], 1.0f);
+      a[k][1] = __fadd_rn(a[k][1], r);
+      a[k][2] = __fmaf_rn(r, r, a[k][2]);
+      a[k][3] = __fadd_rn(a[k][3], x); a[k][4] = __fadd_rn(a[k][4], y); a[k][5] = __fadd_rn(a[k][5], z);
+      a[k][6] = __fmaf_rn(r, x, a[k][6]); a[k][7] = __fmaf_rn(r, y, a[k][7]); a[k][8] = __fmaf_rn(r, z, a[k][8]);
+      mx[k] = fmaxf(mx[k], ab);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(HS_TPB, 2)
+k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid_constant__ PlaneTable tbl,
+                 double* __restrict__ partials, unsigned int* ticket, double* __restrict__ out) {
+  extern __shared__ double sdacc[];  // [K * 9][HS_TPB]
+  __shared__ double smem[(HS_TPB / 32) * 9];
+  __shared__ float smax[HS_TPB / 32];
+  __shared__ float4 spl[HS_MAX_PLANES];
+  if (threadIdx.x < K) spl[threadIdx.x] = make_float4(tbl.pl[threadIdx.x][0], tbl.pl[threadIdx.x][1], tbl.pl[threadIdx.x][2], tbl.pl[threadIdx.x][3]);
+  float a[K][9], mx[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    mx[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) { a[k][c] = 0.f; sdacc[(k * 9 + c) * HS_TPB + threadIdx.x] = 0.0; }
+  }
+  __syncthreads();
+  const int64_t gl = (i0 + 3) >> 2, gh = i1 >> 2;  // whole groups inside [i0, i1)
+  if (gl <= gh) {
+    if (blockIdx.x == 0) {  // ragged head / tail points (at most 3 each)
+      const int64_t nh = gl * 4 - i0, nt = i1 - gh * 4;
+      if (threadIdx.x < nh) { const int64_t i = i0 + threadIdx.x; ps_add<K>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+      else if (threadIdx.x >= 32 && threadIdx.x - 32 < nt) { const int64_t i = gh * 4 + threadIdx.x - 32; ps_add<K>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+    }
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
+    int it = 0;
+    for (int64_t g = gl + static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x; g < gh; g += stride) {
+      const Pts4 p = load_group(xyz, g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ps_add<K>(a, mx, tbl, spl, p.x[e], p.y[e], p.z[e]);
+      if ((++it & 7) == 0) {  // 32 points per chain
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int c = 0; c < 9; ++c) { sdacc[(k * 9 + c) * HS_TPB + threadIdx.x] += static_cast<double>(a[k][c]); a[k][c] = 0.f; }
+      }
+    }
+  } else if (blockIdx.x == 0) {  // the whole range lies inside one group
+    const int64_t i = i0 + threadIdx.x;
+    if (i < i1) ps_add<K>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double v[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = sdacc[(k * 9 + c) * HS_TPB + threadIdx.x] + static_cast<double>(a[k][c]);
+    block_sum_store<9>(v, partials + (static_cast<int64_t>(blockIdx.x) * K + k) * HS_PS, smem);
+    float m = mx[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) smax[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < HS_TPB / 32; ++w) t = fmaxf(t, smax[w]);
+      partials[(static_cast<int64_t>(blockIdx.x) * K + k) * HS_PS + 9] = t;
+    }
+    __syncthreads();
+  }
+  if (!last_block_arrives(ticket, gridDim.x)) return;
+  __shared__ double fin[HS_TPB];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    last_block_sum_strided(partials + static_cast<int64_t>(k) * HS_PS, gridDim.x, K * HS_PS, out + k * HS_PS, fin);
+}
+
 }  // namespace hsk
 
 // ======================================================== launchers ==================================================
@@ -293,6 +411,16 @@ template <int K>
 static int32_t launch_plane_sums_k(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out) {
   const int nb = pick_blocks(ctx, i1 - i0, 4 * HS_TPB, 2);
   if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(nb) * K * HS_PS * sizeof(double))) return rc;
+  if constexpr (K <= 6) {
+    if (ctx->modes[HS_MODE_PS_KERNEL] != 1 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
+      const int dsm = K * 9 * HS_TPB * static_cast<int>(sizeof(double));
+      HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_f32<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
+      k_plane_sums_f32<K><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, reinterpret_cast<double*>(ctx->d_scratch), ctx->d_ticket, d_out);
+      ctx->launches++;
+      HS_CUDA_TRY(ctx, cudaGetLastError());
+      return HS_OK;
+    }
+  }
   k_plane_sums<K><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, i0, i1, tbl, reinterpret_cast<double*>(ctx->d_scratch), ctx->d_ticket, d_out);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());

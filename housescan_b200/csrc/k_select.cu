@@ -60,6 +60,117 @@ k_sel_pass(const float* __restrict__ xyz, int64_t n, int axis, int shift, SelSta
   st->hist[threadIdx.x] = 0;
 }
 
+// ---- k-th over compacted keys (default) ------------------------------------------------------------------------------
+// The cloud is AoS, so a pass over one coordinate still moves all 12 B/point.  The first pass therefore also writes the
+// order-preserving uint image of the key as a dense 4 B/point array; the remaining passes read only that.  Three passes of
+// 11 + 11 + 10 bits: 12 + 4 (write) + 4 + 4 = 24 B/point of traffic instead of 4 x 12 = 48.
+#define SEL_BINS 2048
+struct SelState2 {
+  unsigned int prefix;
+  unsigned int mask;
+  unsigned long long k_rem;
+  unsigned int hist[SEL_BINS];
+};
+
+__global__ void k_sel2_init(SelState2* st, unsigned long long k) {
+  if (threadIdx.x == 0) { st->prefix = 0; st->mask = 0; st->k_rem = k; }
+  for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) st->hist[i] = 0;
+}
+
+// merge the block histogram, and in the last block pick the digit that holds the k-th key (all 256 threads: 8 bins each)
+template <bool LARGEST>
+__device__ __forceinline__ void sel2_finish(unsigned int* sh, int shift, int bits, SelState2* st, unsigned int* ticket, float* __restrict__ out) {
+  __shared__ unsigned int wsum[HS_TPB / 32];
+  const int nbins = 1 << bits;
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbins; b += HS_TPB)
+    if (sh[b]) atomicAdd(&st->hist[b], sh[b]);
+  if (!last_block_arrives(ticket, gridDim.x)) return;
+  // scan order: descending bins for the k-th largest, ascending for the k-th smallest; thread t owns 8 consecutive bins of it
+  unsigned int c[SEL_BINS / HS_TPB], mine = 0;
+#pragma unroll
+  for (int j = 0; j < SEL_BINS / HS_TPB; ++j) {
+    const int pos = threadIdx.x * (SEL_BINS / HS_TPB) + j;
+    const int b = LARGEST ? nbins - 1 - pos : pos;
+    c[j] = (pos < nbins) ? __ldcg(&st->hist[b]) : 0u;
+    mine += c[j];
+  }
+  const unsigned long long before = block_exclusive_prefix(mine, wsum);  // counts fit 32 bits per pass only if n < 2^32: checked by the launcher
+  const unsigned long long k = st->k_rem;
+  const unsigned int prefix = st->prefix, mask = st->mask;
+  __syncthreads();
+  if (before < k && k <= before + mine) {  // exactly one thread
+    unsigned long long cum = before;
+#pragma unroll
+    for (int j = 0; j < SEL_BINS / HS_TPB; ++j) {
+      if (cum + c[j] >= k) {
+        const int pos = threadIdx.x * (SEL_BINS / HS_TPB) + j;
+        const unsigned int digit = static_cast<unsigned int>(LARGEST ? nbins - 1 - pos : pos);
+        st->k_rem = k - cum;
+        st->prefix = prefix | (digit << shift);
+        st->mask = mask | (static_cast<unsigned int>(nbins - 1) << shift);
+        if (shift == 0) *out = ord2f(prefix | digit);
+        break;
+      }
+      cum += c[j];
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < SEL_BINS; b += HS_TPB) st->hist[b] = 0;
+}
+
+// pass 1: key image + histogram of the top 11 bits
+template <bool LARGEST>
+__global__ void __launch_bounds__(HS_TPB)
+k_sel2_first(const float* __restrict__ xyz, int64_t n, int axis, unsigned int* __restrict__ keys, SelState2* st, unsigned int* ticket, float* __restrict__ out) {
+  __shared__ unsigned int sh[SEL_BINS];
+  for (int b = threadIdx.x; b < SEL_BINS; b += HS_TPB) sh[b] = 0;
+  __syncthreads();
+  const int64_t gfull = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x; g < gfull; g += stride) {
+    const Pts4 p = load_group(xyz, g);
+    uint4 u;
+    u.x = f2ord(axis == 0 ? p.x[0] : (axis == 1 ? p.y[0] : p.z[0]));
+    u.y = f2ord(axis == 0 ? p.x[1] : (axis == 1 ? p.y[1] : p.z[1]));
+    u.z = f2ord(axis == 0 ? p.x[2] : (axis == 1 ? p.y[2] : p.z[2]));
+    u.w = f2ord(axis == 0 ? p.x[3] : (axis == 1 ? p.y[3] : p.z[3]));
+    reinterpret_cast<uint4*>(keys)[g] = u;
+    atomicAdd(&sh[u.x >> 21], 1u); atomicAdd(&sh[u.y >> 21], 1u); atomicAdd(&sh[u.z >> 21], 1u); atomicAdd(&sh[u.w >> 21], 1u);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = gfull * 4 + threadIdx.x;
+    const unsigned int u = f2ord(xyz[3 * i + axis]);
+    keys[i] = u;
+    atomicAdd(&sh[u >> 21], 1u);
+  }
+  sel2_finish<LARGEST>(sh, 21, 11, st, ticket, out);
+}
+
+// passes 2 and 3: histogram of the next digit over the keys that match the prefix so far
+template <bool LARGEST>
+__global__ void __launch_bounds__(HS_TPB)
+k_sel2_next(const unsigned int* __restrict__ keys, int64_t n, int shift, int bits, SelState2* st, unsigned int* ticket, float* __restrict__ out) {
+  __shared__ unsigned int sh[SEL_BINS];
+  for (int b = threadIdx.x; b < SEL_BINS; b += HS_TPB) sh[b] = 0;
+  __syncthreads();
+  const unsigned int prefix = st->prefix, mask = st->mask, dm = (1u << bits) - 1u;
+  const int64_t gfull = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x; g < gfull; g += stride) {
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(keys) + g);
+    if ((u.x & mask) == prefix) atomicAdd(&sh[(u.x >> shift) & dm], 1u);
+    if ((u.y & mask) == prefix) atomicAdd(&sh[(u.y >> shift) & dm], 1u);
+    if ((u.z & mask) == prefix) atomicAdd(&sh[(u.z >> shift) & dm], 1u);
+    if ((u.w & mask) == prefix) atomicAdd(&sh[(u.w >> shift) & dm], 1u);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const unsigned int u = keys[gfull * 4 + threadIdx.x];
+    if ((u & mask) == prefix) atomicAdd(&sh[(u >> shift) & dm], 1u);
+  }
+  sel2_finish<LARGEST>(sh, shift, bits, st, ticket, out);
+}
+
 // ---- order-preserving filter  (comp axis) <= limit -----------------------------------------------------------------
 #define FL_TILE 1024  // points per tile: one group of 4 per thread
 
@@ -129,6 +240,30 @@ k_filter_scatter(const float* __restrict__ xyz, int64_t n, int axis, float limit
 using namespace hsk;
 
 int32_t launch_kth(hs_ctx* ctx, const float* xyz, int64_t n, int axis, int64_t k, bool largest, float* d_out) {
+  if (ctx->modes[HS_MODE_SEL_KERNEL] != 1 && n < (1ll << 32) && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
+    const size_t keys_off = (sizeof(SelState2) + 255) & ~static_cast<size_t>(255);
+    if (int32_t rc = hs_ensure_scratch(ctx, keys_off + static_cast<size_t>(n) * 4 + 16)) return rc;
+    SelState2* st = reinterpret_cast<SelState2*>(ctx->d_scratch);
+    unsigned int* keys = reinterpret_cast<unsigned int*>(ctx->d_scratch + keys_off);
+    k_sel2_init<<<1, 256, 0, ctx->stream>>>(st, static_cast<unsigned long long>(k));
+    int64_t nb = ((n >> 2) + HS_TPB - 1) / HS_TPB;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    const int g = static_cast<int>(nb);
+    if (largest) {
+      k_sel2_first<true><<<g, HS_TPB, 0, ctx->stream>>>(xyz, n, axis, keys, st, ctx->d_ticket, d_out);
+      k_sel2_next<true><<<g, HS_TPB, 0, ctx->stream>>>(keys, n, 10, 11, st, ctx->d_ticket, d_out);
+      k_sel2_next<true><<<g, HS_TPB, 0, ctx->stream>>>(keys, n, 0, 10, st, ctx->d_ticket, d_out);
+    } else {
+      k_sel2_first<false><<<g, HS_TPB, 0, ctx->stream>>>(xyz, n, axis, keys, st, ctx->d_ticket, d_out);
+      k_sel2_next<false><<<g, HS_TPB, 0, ctx->stream>>>(keys, n, 10, 11, st, ctx->d_ticket, d_out);
+      k_sel2_next<false><<<g, HS_TPB, 0, ctx->stream>>>(keys, n, 0, 10, st, ctx->d_ticket, d_out);
+    }
+    ctx->launches += 4;
+    HS_CUDA_TRY(ctx, cudaGetLastError());
+    return HS_OK;
+  }
   if (int32_t rc = hs_ensure_scratch(ctx, sizeof(SelState))) return rc;
   SelState* st = reinterpret_cast<SelState*>(ctx->d_scratch);
   k_sel_init<<<1, 256, 0, ctx->stream>>>(st, static_cast<unsigned long long>(k));

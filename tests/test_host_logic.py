@@ -137,3 +137,35 @@ def test_optimize_room_positions_reference_semantics():
     # o = (2.0 - 0) - (2.8 - 5.3) = 4.5; desired centre offset = 4.5 + 0.1 => room 2 sits at x = 4.6
     assert abs(moved[2][0] - (4.6 - 5.3)) < 1e-6 and moved[1][0] == 0 and not moved[2][1:].any()
     assert any("Aligning the X (1 components)" in l for l in log)
+
+
+# ------------------------------------------------------------------ exact constant-divisor division used by the depth kernels
+def _fma32(a, b, c):
+    """RN_f32(a*b + c) for float32 arrays: the product of two floats is exact in float64 and the sum is rounded once there;
+    the second rounding to float32 can differ from a fused one only on exact float64 ties, which the checks below would catch."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def test_constant_division_sequence():
+    """k_common.cuh div_rn_small: q0 = RN(a y), q = RN(q0 + RN(a - b q0) y) with y = RN(1/b) equals a / b for EVERY integer
+    a in [0, 65535] and b in {10, 20} (scalePoints, Main.hs:1311-1313: x/10, y/10, d/20)."""
+    a = np.arange(65536, dtype=np.float32)
+    for b in (np.float32(10.0), np.float32(20.0)):
+        y = np.float32(1.0) / b
+        q0 = a * y
+        q = _fma32(_fma32(np.full_like(a, -b), q0, a), np.full_like(a, y), q0)
+        assert np.array_equal(q.view(np.uint32), (a / b).view(np.uint32))
+        assert (q0 != a / b).any()  # the multiplication alone is NOT enough
+
+
+def test_general_division_sequence_random():
+    """k_common.cuh div_rn_by (two residual steps, Markstein): equals IEEE division on random pinhole-style operands"""
+    rng = np.random.default_rng(7)
+    for b in (np.float32(525.0), np.float32(131.25), np.float32(570.3422), np.float32(3.0), np.float32(0.7071)):
+        a = ((rng.integers(0, 640, 2_000_00).astype(np.float32) - np.float32(319.5)) * (rng.integers(1, 65536, 2_000_00).astype(np.float32) * np.float32(0.001))).astype(np.float32)
+        y = np.float32(1.0) / b
+        nb, yy = np.full_like(a, -b), np.full_like(a, y)
+        q0 = a * y
+        q1 = _fma32(_fma32(nb, q0, a), yy, q0)
+        q2 = _fma32(_fma32(nb, q1, a), yy, q1)
+        assert np.array_equal(q2.view(np.uint32), (a / b).view(np.uint32)), b

@@ -130,19 +130,26 @@ if want("A5"):
 if want("A13"):
     offs = np.arange(13, dtype=np.int64) * per
     allp = np.stack([hb.planes_from_cuboid(params[r]) for r in range(12)])
-    t0 = time.perf_counter()
-    ps = ctx.plane_sums(cloud, offs, allp, 6)
-    ms = (time.perf_counter() - t0) * 1e3
-    ms = min(ms, timed(lambda: ctx.plane_sums(cloud, offs, allp, 6), reps=3, warm=1))
-    report("A13", "hs_plane_sums (12 rooms x 6)", n, "pts", 12.0, ms, bool(int(ps[:, :, 0].sum()) == n), note="counts sum to n")
+    for mode, tag in ((1, "all-Double"), (0, "Float chains")):
+        ctx.set_mode(7, mode)
+        ps = ctx.plane_sums(cloud, offs, allp, 6)
+        ms = timed(lambda: ctx.plane_sums(cloud, offs, allp, 6), reps=3, warm=1)
+        ok = int(ps[:, :, 0].sum()) == n
+        if mode == 1:
+            ps_ref = ps
+        else:  # the two forms agree to the north-star bar on every sum, exactly on counts and max |r|
+            ok = ok and np.array_equal(ps[..., 0], ps_ref[..., 0]) and np.array_equal(ps[..., 9], ps_ref[..., 9]) and np.allclose(ps, ps_ref, rtol=1e-6, atol=1e-6 * np.abs(ps_ref).max())
+        report("A13", f"hs_plane_sums 12x6 ({tag})", n, "pts", 12.0, ms, bool(ok), note="counts sum to n; forms agree")
 
 if want("A12"):
     k = n // 5
-    ms = timed(lambda: ctx.kth_largest(cloud, 1, k), reps=5)
-    v = ctx.kth_largest(cloud, 1, k)
     y = pts[:, 1]
-    ok = int((y > float(v)).sum().item()) < k <= int((y >= float(v)).sum().item())
-    report("A12", "hs_kth_largest (4 radix passes)", n, "pts", 16.0, ms, bool(ok), note="4 B key x 4 passes algorithmic; AoS stride makes it 12 B x 4 physical")
+    for mode, tag in ((1, "4 passes over the cloud"), (0, "3 passes, compact keys")):
+        ctx.set_mode(8, mode)
+        ms = timed(lambda: ctx.kth_largest(cloud, 1, k), reps=5)
+        v = ctx.kth_largest(cloud, 1, k)
+        ok = int((y > float(v)).sum().item()) < k <= int((y >= float(v)).sum().item())
+        report("A12", f"hs_kth_largest ({tag})", n, "pts", 16.0, ms, bool(ok), note="algorithmic 4 B key x 4; physical 12 B x 4 (cloud passes) or 12 + 4 + 4 + 4 (compact keys)")
     n_out = C.c_int64()
     yl = C.c_float()
     fn = lambda: ctx._chk(lib.hs_remove_ceiling(ctx.h, cloud.h, None, out_cloud.h, None, C.byref(n_out), C.byref(yl)))
@@ -183,11 +190,23 @@ if want("A1"):
     intr = np.array(synth.KINFU_INTR, np.float32)
     d_out = torch.empty(nf * hb.HS_NE, dtype=torch.float64, device=dev)
     fn = lambda: ctx._chk(lib.hs_backproject_reduce6x6_dev(ctx.h, C.c_void_p(frames.data_ptr()), nf, w, h, ptr(intr), None, ptr(planes), 6, C.c_void_p(d_out.data_ptr())))
-    ms = timed(fn, reps=5)
-    o = d_out.view(nf, hb.HS_NE)
-    cnt_ok = bool(torch.equal(o[:, 28].long(), (frames != 0).view(nf, -1).sum(dim=1)))
-    rep_ok = bool(torch.equal(o[:8], o[8:16])) if nf >= 16 else True  # replayed frames give identical records (deterministic)
-    report("A4", "hs_backproject_reduce6x6_dev", npx, "px", 2.0, ms, cnt_ok and rep_ok, note=f"{nf} frames, 232 B out per frame; counts == valid pixels, replayed frames bit-identical")
+    poses8 = synth.depth_stream(8, 8, 8)[1]
+    poses = np.ascontiguousarray(np.tile(poses8, ((nf + 7) // 8, 1))[:nf])
+    fn_pose = lambda: ctx._chk(lib.hs_backproject_reduce6x6_dev(ctx.h, C.c_void_p(frames.data_ptr()), nf, w, h, ptr(intr), ptr(poses), ptr(planes), 6, C.c_void_p(d_out.data_ptr())))
+    for mode, tag in ((1, "all-Double"), (0, "Float chains")):
+        ctx.set_mode(6, mode)
+        ms = timed(fn, reps=5)
+        o = d_out.view(nf, hb.HS_NE).clone()
+        cnt_ok = bool(torch.equal(o[:, 28].long(), (frames != 0).view(nf, -1).sum(dim=1)))
+        rep_ok = bool(torch.equal(o[:8], o[8:16])) if nf >= 16 else True  # replayed frames give identical records (deterministic)
+        if mode == 1:
+            o_ref = o
+        else:
+            diag = o_ref[:, [0, 6, 11, 15, 18, 20]].max(dim=1, keepdim=True).values
+            rep_ok = rep_ok and bool(((o - o_ref).abs() <= 1e-6 * diag).all().item())
+        report("A4", f"hs_backproject_reduce6x6_dev ({tag})", npx, "px", 2.0, ms, cnt_ok and rep_ok, note=f"{nf} frames, intrinsics, 232 B out per frame; counts == valid pixels, replayed frames bit-identical, forms agree")
+        ms = timed(fn_pose, reps=5)
+        report("A4", f"  + per-frame pose ({tag})", npx, "px", 2.0, ms, True, note="includes the H2D copy of the poses (64 B/frame)")
     del frames, d_out
 
 if want("A10"):
