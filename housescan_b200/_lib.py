@@ -74,6 +74,12 @@ SIGNATURES = {
     "hs_fit_cuboid_cloud_bfgs": (i32, [vp, vp, vp, i32, f64, vp, C.POINTER(f64), C.POINTER(i32), C.POINTER(i32)]),
     "hs_lstsq_distances": (i32, [vp, vp, vp, i32, i32, vp, C.POINTER(f64)]),
     "hs_group_cc": (i32, [vp, vp, vp, i64, u32, vp, vp, C.POINTER(i32)]),
+    "hs_plane_eqs_from_text": (i32, [C.c_char_p, i64, vp, i32, C.POINTER(i32)]),
+    "hs_plane_eqs_from_file": (i32, [C.c_char_p, vp, i32, C.POINTER(i32)]),
+    "hs_cloud_from_pcd": (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(vp)]),
+    "hs_pcd_info": (i32, [C.c_char_p, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
+    "hs_make_inward_facing": (i32, [vp, vp, vp, i32]),
+    "hs_load_room": (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(vp), vp, i32, C.POINTER(i32)]),
     "hs_version": (C.c_char_p, []),
 }
 

@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libhousescan_b200.so")
-CU = ["hs_api.cu", "k_planes.cu", "k_eval_fast.cu", "k_eval_pred.cu", "k_transform.cu", "k_depth.cu", "k_graph.cu", "k_select.cu"]
-HOST = ["hs_host.cpp"]
+CU = ["hs_api.cu", "k_planes.cu", "k_eval_fast.cu", "k_eval_pred.cu", "k_transform.cu", "k_depth.cu", "k_graph.cu", "k_select.cu", "k_pcd.cu"]
+HOST = ["hs_host.cpp", "hs_roomio.cpp"]
 HEADERS = [
     os.path.join(ROOT, "include", "housescan_b200.h"),
     os.path.join(HERE, "csrc", "hs_internal.cuh"),

@@ -196,7 +196,7 @@ int32_t hs_cloud_free(hs_ctx* ctx, hs_cloud* cloud) {
 // ---- (1) depth frames ----------------------------------------------------------------------------------------------
 int32_t hs_backproject_ref_dev(hs_ctx* ctx, const void* d_depth, int32_t w, int32_t h, hs_cloud* cloud_out, void* d_mask, int64_t* n_valid) {
   HS_LOCK(ctx);
-  if (w <= 0 || h <= 0 || w > 65535 || h > 65535 || !d_depth) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_ref: bad frame");
+  if (w <= 0 || h <= 0 || w > (1 << 24) || h > (1 << 24) || !d_depth) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_ref: bad frame");  // pixel coordinates must be exact in Float
   const int64_t npx = static_cast<int64_t>(w) * h;
   if (cloud_out && cloud_out->cap < npx) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_ref: output cloud smaller than w*h");
   int64_t* d_n = reinterpret_cast<int64_t*>(ctx->d_small);
@@ -248,7 +248,7 @@ int32_t hs_backproject_reduce6x6_dev(hs_ctx* ctx, const void* d_frames, int64_t 
   if (!d_frames || nframes < 0 || w <= 0 || h <= 0 || !d_out) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_reduce6x6: bad arguments");
   PlaneTable t;
   if (int32_t rc = fill_plane_table(ctx, planes, K, 16, t, "hs_backproject_reduce6x6")) return rc;
-  if (w > 65535 || h > 65535) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_reduce6x6: frame sides are limited to 65535");
+  if (w > (1 << 24) || h > (1 << 24)) HS_FAIL(ctx, HS_EINVAL, "hs_backproject_reduce6x6: frame sides are limited to 2^24");
   float* d_poses = nullptr;
   const size_t pose_bytes = poses ? static_cast<size_t>(nframes) * 64 : 0;  // multiple of 64: the work area stays aligned
   if (int32_t rc = hs_ensure_scratch(ctx, pose_bytes + reduce6x6_work_bytes(ctx, nframes, w, h))) return rc;
@@ -636,6 +636,163 @@ int32_t hs_remove_ceiling(hs_ctx* ctx, const hs_cloud* cloud, const hs_cloud* co
   if (int32_t rc = kth_impl(ctx, cloud, 1, cloud->n / 5, true, &ylim)) return rc;  // n < 5 => k = 0 => the reference errors too
   if (y_limit) *y_limit = ylim;
   return filter_impl(ctx, cloud, 1, ylim, colors, out, colors_out, n_out);
+}
+
+// ---- room input formats ------------------------------------------------------------------------------------
+int32_t hs_plane_eqs_from_text(const char* text, int64_t len, float* planes_out, int32_t cap, int32_t* n_out) {
+  if (!text || len < 0 || !n_out || (cap > 0 && !planes_out)) return HS_EINVAL;
+  std::vector<float> pl;
+  const int n = hs::parse_planes_txt(text, static_cast<size_t>(len), &pl);
+  if (n < 0) { *n_out = 0; return HS_EIO; }  // "Could not load planes" (Main.hs:1388)
+  *n_out = n;
+  if (n > cap) return HS_EINVAL;  // n_out tells the caller how much room it needs
+  std::memcpy(planes_out, pl.data(), sizeof(float) * 4 * n);
+  return HS_OK;
+}
+
+int32_t hs_plane_eqs_from_file(const char* path, float* planes_out, int32_t cap, int32_t* n_out) {
+  if (!path) return HS_EINVAL;
+  std::vector<char> buf;
+  std::string err;
+  if (!hs::read_file(path, &buf, &err)) return HS_EIO;
+  return hs_plane_eqs_from_text(buf.data(), static_cast<int64_t>(buf.size()), planes_out, cap, n_out);
+}
+
+int32_t hs_make_inward_facing(const float room_center[3], const float* plane_means, float* planes_inout, int32_t K) {
+  if (!room_center || !plane_means || !planes_inout || K < 0) return HS_EINVAL;
+  hs::make_inward_facing(room_center, plane_means, planes_inout, K);
+  return HS_OK;
+}
+
+// host side of a PCD load: header, then the DATA section in the form the unpack kernel takes
+struct PcdStaged {
+  hs::PcdHeader h;
+  std::vector<char> file;
+  std::vector<uint8_t> soa;     // binary_compressed after LZF
+  std::vector<uint32_t> rec;    // ascii records
+  const uint8_t* raw = nullptr;
+  size_t raw_bytes = 0;
+  int64_t off[4] = {0, 0, 0, -1}, stride[4] = {0, 0, 0, 0};
+  bool has_rgb = false;
+};
+static bool pcd_stage(const char* path, PcdStaged* st, std::string* err) {
+  if (!hs::read_file(path, &st->file, err)) return false;
+  if (!hs::pcd_parse_header(st->file.data(), st->file.size(), &st->h, err)) return false;
+  const hs::PcdHeader& h = st->h;
+  int f[4];
+  if (!hs::pcd_layout(h, &f[0], &f[1], &f[2], &f[3], err)) return false;
+  st->has_rgb = f[3] >= 0;
+  const int64_t n = h.points;
+  if (h.data_kind == 0) {
+    int W = 3;
+    if (!hs::pcd_ascii_records(st->file.data(), st->file.size(), h, &st->rec, &W, err)) return false;
+    st->raw = reinterpret_cast<const uint8_t*>(st->rec.data());
+    st->raw_bytes = st->rec.size() * 4;
+    for (int c = 0; c < 4; ++c) { st->off[c] = 4 * c; st->stride[c] = 4 * W; }
+  } else if (h.data_kind == 1) {
+    st->raw = reinterpret_cast<const uint8_t*>(st->file.data()) + h.data_offset;
+    st->raw_bytes = static_cast<size_t>(n) * h.point_step;
+    if (h.data_offset + st->raw_bytes > st->file.size()) { *err = "PCD: binary data ends early"; return false; }
+    for (int c = 0; c < 4; ++c) { st->off[c] = f[c] >= 0 ? h.field_offset[f[c]] : -1; st->stride[c] = h.point_step; }
+  } else {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(st->file.data()) + h.data_offset;
+    if (h.data_offset + 8 > st->file.size()) { *err = "PCD: compressed data ends early"; return false; }
+    uint32_t csz, usz;
+    std::memcpy(&csz, p, 4); std::memcpy(&usz, p + 4, 4);
+    if (h.data_offset + 8 + csz > st->file.size() || usz != static_cast<uint64_t>(n) * h.point_step) { *err = "PCD: bad compressed sizes"; return false; }
+    st->soa.resize(usz);
+    if (!hs::lzf_decompress(p + 8, csz, st->soa.data(), usz)) { *err = "PCD: LZF stream is corrupt"; return false; }
+    st->raw = st->soa.data();
+    st->raw_bytes = usz;
+    for (int c = 0; c < 4; ++c) {  // field-major: all values of field 0, then field 1, ...
+      st->off[c] = f[c] >= 0 ? static_cast<int64_t>(h.field_offset[f[c]]) * n : -1;
+      st->stride[c] = f[c] >= 0 ? h.size[f[c]] * h.count[f[c]] : 0;
+    }
+  }
+  return true;
+}
+
+int32_t hs_pcd_info(const char* path, int64_t* n_points, int32_t* has_rgb, int32_t* data_kind) {
+  if (!path) return HS_EINVAL;
+  std::vector<char> buf;
+  std::string err;
+  hs::PcdHeader h;
+  int f[4];
+  if (!hs::read_file(path, &buf, &err) || !hs::pcd_parse_header(buf.data(), buf.size(), &h, &err) || !hs::pcd_layout(h, &f[0], &f[1], &f[2], &f[3], &err)) return HS_EIO;
+  if (n_points) *n_points = h.points;
+  if (has_rgb) *has_rgb = f[3] >= 0;
+  if (data_kind) *data_kind = h.data_kind;
+  return HS_OK;
+}
+
+int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out) {
+  if (!ctx) return HS_EINVAL;
+  if (!path || !cloud_out) { ctx->err = "hs_cloud_from_pcd: bad arguments"; return HS_EINVAL; }
+  *cloud_out = nullptr;
+  if (colors_out) *colors_out = nullptr;
+  PcdStaged st;
+  std::string err;
+  if (!pcd_stage(path, &st, &err)) { ctx->err = err; return HS_EIO; }
+  const int64_t n = st.h.points;
+  if (n == 0) { ctx->err = std::string("File ") + path + " contains no points!"; return HS_EIO; }  // Main.hs:1344
+  hs_cloud *cl = nullptr, *col = nullptr;
+  int32_t rc = hs_cloud_alloc(ctx, n, &cl);
+  const bool want_rgb = colors_out && st.has_rgb;
+  if (rc == HS_OK && want_rgb) rc = hs_cloud_alloc(ctx, n, &col);
+  if (rc == HS_OK) {
+    HS_LOCK(ctx);
+    uint8_t* d_raw = nullptr;
+    cudaError_t e = cudaMalloc(&d_raw, st.raw_bytes + 16);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); rc = HS_ENOMEM; }
+    if (rc == HS_OK) rc = copy_h2d(ctx, d_raw, st.raw, st.raw_bytes);
+    if (rc == HS_OK) rc = launch_pcd_unpack(ctx, d_raw, n, st.off, st.stride, cl->d, want_rgb ? col->d : nullptr);
+    cudaStreamSynchronize(ctx->stream);  // the staged host buffers die with this call
+    if (d_raw) cudaFree(d_raw);
+  }
+  if (rc != HS_OK) { if (cl) hs_cloud_free(ctx, cl); if (col) hs_cloud_free(ctx, col); return rc; }
+  *cloud_out = cl;
+  if (colors_out) *colors_out = col;
+  return HS_OK;
+}
+
+// the plane hulls are a few dozen points each: read on the host, mean as the reference's Float fold (planeMean, Main.hs:1608)
+static bool pcd_host_mean(const char* path, float mean[3], std::string* err) {
+  PcdStaged st;
+  if (!pcd_stage(path, &st, err)) return false;
+  const int64_t n = st.h.points;
+  std::vector<float> xyz(static_cast<size_t>(n) * 3);
+  for (int64_t i = 0; i < n; ++i)
+    for (int c = 0; c < 3; ++c) std::memcpy(&xyz[3 * i + c], st.raw + st.off[c] + i * st.stride[c], 4);
+  if (!hs::point_mean_f32seq(xyz.data(), n, mean)) { *err = "pointMean: empty"; return false; }  // Main.hs:1597
+  return true;
+}
+
+int32_t hs_load_room(hs_ctx* ctx, const char* dir, hs_cloud** cloud_out, hs_cloud** colors_out, float* planes_out, int32_t cap, int32_t* K_out) {
+  if (!ctx) return HS_EINVAL;
+  if (!dir || !cloud_out || !planes_out || !K_out) { ctx->err = "hs_load_room: bad arguments"; return HS_EINVAL; }
+  const std::string d(dir);
+  if (int32_t rc = hs_cloud_from_pcd(ctx, (d + "/cloud_downsampled.pcd").c_str(), cloud_out, colors_out)) return rc;  // Main.hs:1742-1744
+  auto fail = [&](int32_t rc, const std::string& msg) {
+    ctx->err = msg;
+    hs_cloud_free(ctx, *cloud_out); *cloud_out = nullptr;
+    if (colors_out && *colors_out) { hs_cloud_free(ctx, *colors_out); *colors_out = nullptr; }
+    return rc;
+  };
+  int32_t K = 0;
+  int32_t rc = hs_plane_eqs_from_file((d + "/planes.txt").c_str(), planes_out, cap, &K);
+  if (rc != HS_OK) return fail(rc, rc == HS_EIO ? "Could not load planes: " + d + "/planes.txt" : "hs_load_room: more planes than the caller has room for");
+  std::vector<float> means(static_cast<size_t>(K) * 3);
+  for (int k = 0; k < K; ++k) {  // planesFromDir, Main.hs:1391-1404
+    std::string err;
+    if (!pcd_host_mean((d + "/cloud_plane_hull" + std::to_string(k) + ".pcd").c_str(), &means[3 * k], &err)) return fail(HS_EIO, err);
+  }
+  double m[3];
+  float md;
+  if ((rc = hs_mean_extent(ctx, *cloud_out, m, &md)) != HS_OK) return fail(rc, ctx->err);  // roomCenter = cloudMean cloud, Double sums on the GPU
+  const float center[3] = {static_cast<float>(m[0]), static_cast<float>(m[1]), static_cast<float>(m[2])};
+  hs::make_inward_facing(center, means.data(), planes_out, K);
+  *K_out = K;
+  return HS_OK;
 }
 
 // ---- host-side module mirrors ------------------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ __device__ __forceinline__ float div_rn_by(float a, float b, float y) {
   const float q1 = __fmaf_rn(__fmaf_rn(-b, q0, a), y, q0);
   return __fmaf_rn(__fmaf_rn(-b, q1, a), y, q1);
 }
-// Same for integer-valued a in [0, 65535] and b in {10, 20}: one residual step already gives the IEEE quotient for every such a
+// Same for integer-valued a in [0, 2^24) and b in {10, 20}: one residual step already gives the IEEE quotient for every such a
 // (checked exhaustively: tests/test_host_logic.py::test_constant_division_sequence).
 __device__ __forceinline__ float div_rn_small(float a, float b, float y) {
   const float q0 = __fmul_rn(a, y);

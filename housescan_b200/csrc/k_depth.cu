@@ -11,7 +11,7 @@ namespace hsk {
 
 #define BP_TILE 2048  // pixels per block-tile: 8 consecutive pixels (one 16-byte load) per thread
 
-// x, y < 65536 (checked by the API) and d is a uint16, so the quotients come from div_rn_small: bit-identical to `/`.
+// x, y < 2^24 (checked by the API) and d is a uint16, so the quotients come from div_rn_small: bit-identical to `/`.
 #define HS_RCP10 __fdiv_rn(1.0f, 10.0f)
 #define HS_RCP20 __fdiv_rn(1.0f, 20.0f)
 __device__ __forceinline__ void scale_point(int x, int y, unsigned int d, float& X, float& Y, float& Z) {
@@ -310,16 +310,42 @@ __device__ __forceinline__ PixelJ ne_geometry_fast(const FrameGeom& geo, float r
   o.r = plane_dist(nn.x, nn.y, nn.z, nn.w, px, py, pz);  // same operations on the same operands as in the loop: same bits
   return o;
 }
-__device__ __forceinline__ void ne_accumulate_f32(float (&acc)[HS_NE], const PixelJ& p) {
-  int t = 0;
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int b = a; b < 6; ++b) { acc[t] = __fmaf_rn(p.j[a], p.j[b], acc[t]); ++t; }
-#pragma unroll
-  for (int a = 0; a < 6; ++a) acc[21 + a] = __fmaf_rn(p.j[a], p.r, acc[21 + a]);
-  acc[27] = __fmaf_rn(p.r, p.r, acc[27]);
-  acc[28] = __fadd_rn(acc[28], 1.0f);
+// every accumulation is a predicated FP instruction (no branch around the block, no selects): the four pixels a thread has in
+// flight stay independent instruction streams for the scheduler
+__device__ __forceinline__ void ne_accumulate_f32(float (&acc)[HS_NE], const PixelJ& p, unsigned int d) {
+  asm("{\n .reg .pred p;\n setp.ne.u32 p, %36, 0;\n"
+      "@p fma.rn.f32 %0, %29, %29, %0;\n"
+      "@p fma.rn.f32 %1, %29, %30, %1;\n"
+      "@p fma.rn.f32 %2, %29, %31, %2;\n"
+      "@p fma.rn.f32 %3, %29, %32, %3;\n"
+      "@p fma.rn.f32 %4, %29, %33, %4;\n"
+      "@p fma.rn.f32 %5, %29, %34, %5;\n"
+      "@p fma.rn.f32 %6, %30, %30, %6;\n"
+      "@p fma.rn.f32 %7, %30, %31, %7;\n"
+      "@p fma.rn.f32 %8, %30, %32, %8;\n"
+      "@p fma.rn.f32 %9, %30, %33, %9;\n"
+      "@p fma.rn.f32 %10, %30, %34, %10;\n"
+      "@p fma.rn.f32 %11, %31, %31, %11;\n"
+      "@p fma.rn.f32 %12, %31, %32, %12;\n"
+      "@p fma.rn.f32 %13, %31, %33, %13;\n"
+      "@p fma.rn.f32 %14, %31, %34, %14;\n"
+      "@p fma.rn.f32 %15, %32, %32, %15;\n"
+      "@p fma.rn.f32 %16, %32, %33, %16;\n"
+      "@p fma.rn.f32 %17, %32, %34, %17;\n"
+      "@p fma.rn.f32 %18, %33, %33, %18;\n"
+      "@p fma.rn.f32 %19, %33, %34, %19;\n"
+      "@p fma.rn.f32 %20, %34, %34, %20;\n"
+      "@p fma.rn.f32 %21, %29, %35, %21;\n"
+      "@p fma.rn.f32 %22, %30, %35, %22;\n"
+      "@p fma.rn.f32 %23, %31, %35, %23;\n"
+      "@p fma.rn.f32 %24, %32, %35, %24;\n"
+      "@p fma.rn.f32 %25, %33, %35, %25;\n"
+      "@p fma.rn.f32 %26, %34, %35, %26;\n"
+      "@p fma.rn.f32 %27, %35, %35, %27;\n"
+      "@p add.rn.f32 %28, %28, 0f3F800000;\n"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7]), "+f"(acc[8]), "+f"(acc[9]), "+f"(acc[10]), "+f"(acc[11]), "+f"(acc[12]), "+f"(acc[13]), "+f"(acc[14]), "+f"(acc[15]), "+f"(acc[16]), "+f"(acc[17]), "+f"(acc[18]), "+f"(acc[19]), "+f"(acc[20]), "+f"(acc[21]), "+f"(acc[22]), "+f"(acc[23]), "+f"(acc[24]), "+f"(acc[25]), "+f"(acc[26]), "+f"(acc[27]), "+f"(acc[28])
+      : "f"(p.j[0]), "f"(p.j[1]), "f"(p.j[2]), "f"(p.j[3]), "f"(p.j[4]), "f"(p.j[5]), "f"(p.r), "r"(d));
 }
 
 #ifndef NE_ILP
@@ -379,8 +405,7 @@ k_reduce6x6_f32(const uint16_t* __restrict__ frames, int64_t nframes, int w, int
           pj[e] = ne_geometry_fast<INTR, POSE, KT>(geo, rfx, rfy, M, tbl, spl, __fadd_rn(x0f, static_cast<float>(px)), yc, dd[e]);
         }
 #pragma unroll
-        for (int e = 0; e < NE_ILP; ++e)
-          if (dd[e] != 0) ne_accumulate_f32(acc, pj[e]);
+        for (int e = 0; e < NE_ILP; ++e) ne_accumulate_f32(acc, pj[e], dd[e]);
       }
       if (it & 1) {  // 16 pixels per chain
 #pragma unroll

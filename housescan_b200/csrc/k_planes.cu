@@ -154,21 +154,33 @@ __device__ __forceinline__ int nearestK(const PlaneTable& t, float x, float y, f
 }
 
 // same choice with a cheaper selection chain: only the index is carried (FSETP + SEL) and the running minimum is an FMNMX;
-// the winner's residual is recomputed from its plane (one LDS.128 + the same six operations => the same bits)
+// the winner's residual is recomputed from its plane (one LDS.128 + the same six operations => the same bits).
+// KT > 0: the number of planes is known at compile time (unrolled, plane constants straight from the constant bank).
+template <int KT>
 __device__ __forceinline__ int nearestK_lds(const PlaneTable& t, const float4* __restrict__ spl, float x, float y, float z, float& r) {
   float ab = fabsf(plane_dist(t.pl[0][0], t.pl[0][1], t.pl[0][2], t.pl[0][3], x, y, z));
   int kb = 0;
-  for (int k = 1; k < t.K; ++k) {
-    const float ak = fabsf(plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z));
-    kb = (ak < ab) ? k : kb;
-    ab = fminf(ab, ak);
+  if (KT > 0) {
+#pragma unroll
+    for (int k = 1; k < KT; ++k) {
+      const float ak = fabsf(plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z));
+      kb = (ak < ab) ? k : kb;
+      ab = fminf(ab, ak);
+    }
+  } else {
+    for (int k = 1; k < t.K; ++k) {
+      const float ak = fabsf(plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z));
+      kb = (ak < ab) ? k : kb;
+      ab = fminf(ab, ak);
+    }
   }
   const float4 nn = spl[kb];
   r = plane_dist(nn.x, nn.y, nn.z, nn.w, x, y, z);
   return kb;
 }
-#define nearestK(tbl, x, y, z, r) nearestK_lds(tbl, spl, x, y, z, r)
+#define nearestK(tbl, x, y, z, r) nearestK_lds<KT>(tbl, spl, x, y, z, r)
 
+template <int KT>
 __global__ void __launch_bounds__(HS_TPB)
 k_plane_assign(const float* __restrict__ xyz, int64_t n, const __grid_constant__ PlaneTable tbl, uint8_t* __restrict__ assign,
                float* __restrict__ resid) {
@@ -196,7 +208,6 @@ k_plane_assign(const float* __restrict__ xyz, int64_t n, const __grid_constant__
     if (resid) resid[i] = r;
   }
 }
-
 #undef nearestK
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -292,16 +303,16 @@ __device__ __forceinline__ void ps_add(float (&a)[K][9], float (&mx)[K], const P
   }
   const float4 nn = spl[kb];
   const float r = plane_dist(nn.x, nn.y, nn.z, nn.w, x, y, z);  // the winner's residual: same operations, same bits
+  // predicated FP instructions, no branches and no selects: the four points a thread holds stay independent streams
 #pragma unroll
   for (int k = 0; k < K; ++k)
-    if (kb == k) {
-      a[k][0] = __fadd_rn(a[k][0], 1.0f);
-      a[k][1] = __fadd_rn(a[k][1], r);
-      a[k][2] = __fmaf_rn(r, r, a[k][2]);
-      a[k][3] = __fadd_rn(a[k][3], x); a[k][4] = __fadd_rn(a[k][4], y); a[k][5] = __fadd_rn(a[k][5], z);
-      a[k][6] = __fmaf_rn(r, x, a[k][6]); a[k][7] = __fmaf_rn(r, y, a[k][7]); a[k][8] = __fmaf_rn(r, z, a[k][8]);
-      mx[k] = fmaxf(mx[k], ab);
-    }
+    asm("{\n .reg .pred p;\n setp.eq.s32 p, %14, %15;\n"
+        "@p add.rn.f32 %0, %0, 0f3F800000;\n @p add.rn.f32 %1, %1, %10;\n @p fma.rn.f32 %2, %10, %10, %2;\n"
+        "@p add.rn.f32 %3, %3, %11;\n @p add.rn.f32 %4, %4, %12;\n @p add.rn.f32 %5, %5, %13;\n"
+        "@p fma.rn.f32 %6, %10, %11, %6;\n @p fma.rn.f32 %7, %10, %12, %7;\n @p fma.rn.f32 %8, %10, %13, %8;\n"
+        "@p max.f32 %9, %9, %16;\n}\n"
+        : "+f"(a[k][0]), "+f"(a[k][1]), "+f"(a[k][2]), "+f"(a[k][3]), "+f"(a[k][4]), "+f"(a[k][5]), "+f"(a[k][6]), "+f"(a[k][7]), "+f"(a[k][8]), "+f"(mx[k])
+        : "f"(r), "f"(x), "f"(y), "f"(z), "r"(kb), "r"(k), "f"(ab));
 }
 
 template <int K>
@@ -401,7 +412,8 @@ int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const
 
 int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const PlaneTable& tbl, uint8_t* d_assign, float* d_resid) {
   const int nb = pick_blocks(ctx, (n + 3) >> 2, HS_TPB, 8);
-  k_plane_assign<<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);
+  if (tbl.K == 6) k_plane_assign<6><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);  // a cuboid room's walls
+  else k_plane_assign<0><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;

@@ -52,4 +52,26 @@ std::string proj_to_xf(const float m[16]);
 bool write_ply(const char* path, const float* xyz, const uint8_t* rgb, int64_t n, std::string* err);
 void group_edges_by_label(const uint32_t* src, const uint32_t* label, int64_t E, int32_t* comp_out, int64_t* order_out, int32_t* ncomp);
 
+
+// ---- room input formats (hs_roomio.cpp) ------------------------------------------------------------------------------
+int parse_planes_txt(const char* text, size_t len, std::vector<float>* planes);  // planes as nx ny nz d; -1 = no plane parsed
+void make_inward_facing(const float center[3], const float* plane_means, float* planes, int K);
+bool point_mean_f32seq(const float* xyz, int64_t n, float out[3]);
+
+struct PcdHeader {
+  std::vector<std::string> fields;
+  std::vector<int> size, count, field_offset;
+  std::vector<char> type;  // 'F', 'U', 'I'
+  int64_t width = 0, height = 1, points = -1;
+  int data_kind = -1;      // 0 ascii, 1 binary, 2 binary_compressed
+  size_t data_offset = 0;  // first byte after the DATA line
+  int point_step = 0;      // bytes per point in DATA binary
+  int find(const std::string& name) const;
+};
+bool pcd_parse_header(const char* buf, size_t len, PcdHeader* h, std::string* err);
+bool pcd_layout(const PcdHeader& h, int* fx, int* fy, int* fz, int* frgb, std::string* err);
+bool pcd_ascii_records(const char* buf, size_t len, const PcdHeader& h, std::vector<uint32_t>* rec, int* rec_words, std::string* err);
+bool lzf_decompress(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len);
+bool read_file(const char* path, std::vector<char>* out, std::string* err);
+
 }  // namespace hs

@@ -133,6 +133,23 @@ HS_API int32_t hs_mean_extent(hs_ctx* ctx, const hs_cloud* cloud, double mean[3]
 /* full-resolution export (README.md:16 step 4; replaces the external plyxform / pcl_transform_point_cloud of
  * Main.hs:2311-2313): binary little-endian PLY, float x y z [+ uchar red green blue]. */
 HS_API int32_t hs_write_ply(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb_or_null, const char* path);
+/* ---- room input formats: the step before the hot path (README.md:13-16) ----------------------- */
+/* planeEqsFromFile (Main.hs:1379-1389): PCL's planes.txt, one `a b c d` per line meaning ax + by + cz + d = 0; the result is
+ * mkPlaneEqABCD a b c (-d).  Parsing stops at the first line that does not match (attoparsec parseOnly); no plane at all is
+ * HS_EIO ("Could not load planes").  *n_out receives the number parsed; HS_EINVAL if it exceeds cap. */
+HS_API int32_t hs_plane_eqs_from_text(const char* text, int64_t len, float* planes_out, int32_t cap, int32_t* n_out);
+HS_API int32_t hs_plane_eqs_from_file(const char* path, float* planes_out, int32_t cap, int32_t* n_out);
+/* cloudFromFile (Main.hs:1332-1345) over loadPCDFileXyzFloat / loadPCDFileXyzRgbNormalFloat (:1318-1329): PCD v0.7, DATA ascii,
+ * binary or binary_compressed; x y z must be 4-byte floats.  The DATA section goes to the GPU as it lies in the file and is
+ * unpacked there.  *colors_out (may be NULL) receives the `ManyColors` cloud r/255 g/255 b/255 when the file has an rgb field,
+ * else NULL (`OneColor`).  A file without points is HS_EIO with the reference's message. */
+HS_API int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out);
+HS_API int32_t hs_pcd_info(const char* path, int64_t* n_points, int32_t* has_rgb, int32_t* data_kind /* 0 ascii 1 binary 2 compressed */);
+/* makeInwardFacing (Main.hs:1746-1751): flip (n, d) of every plane unless (roomCenter - planeMean) . n > 0 */
+HS_API int32_t hs_make_inward_facing(const float room_center[3], const float* plane_means /* K x 3 */, float* planes_inout /* K x 4 */, int32_t K);
+/* loadRoom (Main.hs:1740-1765): dir/cloud_downsampled.pcd, dir/planes.txt, dir/cloud_plane_hull<i>.pcd; planes inward facing */
+HS_API int32_t hs_load_room(hs_ctx* ctx, const char* dir, hs_cloud** cloud_out, hs_cloud** colors_out, float* planes_out, int32_t cap, int32_t* K_out);
+
 /* roomProjectionToString / roomProjectionToXfFormat (Main.hs:2271-2302); buf receives a NUL-terminated string */
 HS_API int32_t hs_proj_to_string(const float m_rowmajor[16], char* buf, int32_t buflen);
 HS_API int32_t hs_proj_to_xf(const float m_rowmajor[16], char* buf, int32_t buflen);

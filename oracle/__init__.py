@@ -611,3 +611,138 @@ def diagonal_pairs(n):
                 break
         k += 1
     return out
+
+
+# ------------------------------------------------------------------ room input formats
+# Restatement of planeEqsFromFile (Main.hs:1379-1389), loadPCDFileXyzFloat / loadPCDFileXyzRgbNormalFloat (Main.hs:1318-1329)
+# and makeInwardFacing (Main.hs:1746-1751).  pcd-loader and attoparsec are not mounted: PCD follows the published v0.7 layout,
+# numbers follow attoparsec's documented `double` grammar; parity unpinned by reference fixtures (the reference ships none).
+import re as _re
+
+_ATTO_DOUBLE = _re.compile(rb"[+-]?[0-9]+(?:\.[0-9]+)?(?:[eE][+-]?[0-9]+)?")
+_ATTO_SPACE = _re.compile(rb"[ \t\n\v\f\r]*")
+
+
+def plane_eqs_from_text(text):
+    if isinstance(text, str):
+        text = text.encode()
+    i, out = 0, []
+    while True:
+        vals, j, ok = [], i, True
+        for c in range(4):
+            m = _ATTO_DOUBLE.match(text, j)
+            if not m:
+                ok = False
+                break
+            vals.append(float(m.group()))
+            j = m.end()
+            if c < 3:
+                j = _ATTO_SPACE.match(text, j).end()
+        if not ok:
+            break
+        out.append(mk_plane_eq(np.array(vals[:3], np.float32), -np.float32(vals[3])))
+        i = j
+        if text[i:i + 1] == b"\n":
+            i += 1
+        elif text[i:i + 2] == b"\r\n":
+            i += 2
+        else:
+            break
+    if not out:
+        raise ValueError("Could not load planes")
+    return np.stack(out)
+
+
+def make_inward_facing(center, plane_means, planes):
+    planes = np.array(planes, np.float32).reshape(-1, 4)
+    c = np.asarray(center, np.float32)
+    for k in range(len(planes)):
+        inward = c - np.asarray(plane_means[k], np.float32)
+        n = planes[k, :3]
+        d = np.float32(np.float32(np.float32(inward[0] * n[0]) + np.float32(inward[1] * n[1])) + np.float32(inward[2] * n[2]))
+        if not d > 0:
+            planes[k] = -planes[k]
+    return planes
+
+
+def _lzf_decompress(data, out_len):
+    out = bytearray()
+    i = 0
+    while i < len(data):
+        ctrl = data[i]
+        i += 1
+        if ctrl < 32:
+            out += data[i:i + ctrl + 1]
+            i += ctrl + 1
+        else:
+            ln = ctrl >> 5
+            if ln == 7:
+                ln += data[i]
+                i += 1
+            back = ((ctrl & 0x1F) << 8) + data[i] + 1
+            i += 1
+            for _ in range(ln + 2):
+                out.append(out[-back])
+    assert len(out) == out_len
+    return bytes(out)
+
+
+def pcd_load(path):
+    """-> (xyz float32 [n,3], colours float32 [n,3] or None)"""
+    raw = open(path, "rb").read()
+    hdr, pos = {}, 0
+    while True:
+        e = raw.index(b"\n", pos)
+        line = raw[pos:e].decode().strip()
+        pos = e + 1
+        if not line or line.startswith("#"):
+            continue
+        k, *v = line.split()
+        hdr[k] = v
+        if k == "DATA":
+            break
+    fields, size, typ = hdr["FIELDS"], [int(x) for x in hdr["SIZE"]], hdr["TYPE"]
+    count = [int(x) for x in hdr.get("COUNT", ["1"] * len(fields))]
+    n = int(hdr["POINTS"][0]) if "POINTS" in hdr else int(hdr["WIDTH"][0]) * int(hdr["HEIGHT"][0])
+    kind = hdr["DATA"][0]
+    rgb_name = "rgb" if "rgb" in fields else ("rgba" if "rgba" in fields else None)
+    if kind == "ascii":
+        toks = raw[pos:].split()
+        ncol = sum(count)
+        col0 = np.cumsum([0] + count)[:-1]
+        tab = [toks[i * ncol:(i + 1) * ncol] for i in range(n)]
+        xyz = np.array([[np.float32(float(r[col0[fields.index(a)]])) for a in "xyz"] for r in tab], np.float32).reshape(n, 3)
+        bits = None
+        if rgb_name:
+            f = fields.index(rgb_name)
+            if typ[f] == "U":
+                bits = np.array([int(r[col0[f]]) for r in tab], np.uint32)
+            else:
+                bits = np.array([np.float32(float(r[col0[f]])) for r in tab], np.float32).view(np.uint32)
+    else:
+        dt = np.dtype({"names": fields, "formats": [({"F": "f", "U": "u", "I": "i"}[t] + str(s), c) if c != 1 else {"F": "f", "U": "u", "I": "i"}[t] + str(s)
+                                                    for t, s, c in zip(typ, size, count)]})
+        if kind == "binary":
+            rec = np.frombuffer(raw, dt, n, pos)
+            get = lambda name: rec[name]
+        else:
+            csz, usz = np.frombuffer(raw, np.uint32, 2, pos)
+            soa = _lzf_decompress(raw[pos + 8:pos + 8 + int(csz)], int(usz))
+            offs = np.cumsum([0] + [s * c * n for s, c in zip(size, count)])
+            get = lambda name: np.frombuffer(soa, dt[name], n, int(offs[fields.index(name)]))
+        xyz = np.stack([get(a).astype(np.float32) for a in "xyz"], axis=1)
+        bits = get(rgb_name).view(np.uint32) if rgb_name else None
+    cols = None
+    if bits is not None:
+        cols = np.stack([((bits >> 16) & 255).astype(np.float32) / np.float32(255), ((bits >> 8) & 255).astype(np.float32) / np.float32(255),
+                         (bits & 255).astype(np.float32) / np.float32(255)], axis=1).astype(np.float32)
+    return np.ascontiguousarray(xyz), cols
+
+
+def load_room(directory):
+    import os as _os
+    xyz, cols = pcd_load(_os.path.join(directory, "cloud_downsampled.pcd"))
+    planes = plane_eqs_from_text(open(_os.path.join(directory, "planes.txt"), "rb").read())
+    means = np.stack([point_mean_f32seq(pcd_load(_os.path.join(directory, f"cloud_plane_hull{k}.pcd"))[0]) for k in range(len(planes))])
+    center = point_mean_f64(xyz).astype(np.float32)
+    return xyz, cols, make_inward_facing(center, means, planes)

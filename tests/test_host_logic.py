@@ -148,8 +148,8 @@ def _fma32(a, b, c):
 
 def test_constant_division_sequence():
     """k_common.cuh div_rn_small: q0 = RN(a y), q = RN(q0 + RN(a - b q0) y) with y = RN(1/b) equals a / b for EVERY integer
-    a in [0, 65535] and b in {10, 20} (scalePoints, Main.hs:1311-1313: x/10, y/10, d/20)."""
-    a = np.arange(65536, dtype=np.float32)
+    a in [0, 2^24) and b in {10, 20} (scalePoints, Main.hs:1311-1313: x/10, y/10, d/20; a tall raster of many frames has y > 65535)."""
+    a = np.arange(1 << 24, dtype=np.float32)
     for b in (np.float32(10.0), np.float32(20.0)):
         y = np.float32(1.0) / b
         q0 = a * y

@@ -1,0 +1,166 @@
+"""Room input formats: planes.txt, PCD clouds, makeInwardFacing, loadRoom.
+CPU part: the host-side parsers of the C ABI against the oracle restatement.  GPU part (-m gpu): PCD -> device cloud through
+hs_cloud_from_pcd / hs_load_room, bit-exact against the oracle's loader for every DATA kind."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import oracle as O
+from pcd_util import write_pcd
+
+import housescan_b200 as hb
+from housescan_b200 import RoomIO
+
+PLANE_TEXTS = [
+    "1 0 0 -2\n0 2 0 4.0\r\n0.1e1 1 1 3\n",                     # LF and CRLF, trailing newline
+    "0.5 0.5 0.70710678 1.25",                                   # no trailing newline
+    "-0.0123 9.99e-1 4E-2 -17.25\n3 4 0 +5\n",                   # exponents, explicit plus
+    "1 0 0 -2 \n0 1 0 3\n",                                      # blank after d: endOfLine fails, parsing stops after one plane
+    "1 0 0 2\n 0 1 0 3\n",                                       # next line starts with a blank: stops after one plane
+    "1\n0\n0\n5\n0 0 1 7",                                       # skipSpace between a b c d spans newlines
+    "1 0 0 2\n\n0 1 0 3\n",                                      # empty line: stops
+    "1. 0 0 2\n",                                                # `1.` is not consumed as a number: no plane at all -> error
+    ".5 0 0 2\n",                                                # needs a leading digit: error
+    "",                                                          # error
+    "2 0 0 1e400\n",                                             # overflow to inf
+    "0 0 3 -0\n0 0 3 0\n",
+    "1 2 3 4\n5 6 7 x\n",                                        # second line broken: one plane
+]
+
+
+@pytest.mark.parametrize("text", PLANE_TEXTS)
+def test_plane_eqs_from_text_matches_oracle(built_lib, text):
+    try:
+        exp = O.plane_eqs_from_text(text)
+    except ValueError:
+        with pytest.raises(hb.HsError, match="Could not load planes"):
+            RoomIO.planeEqsFromText(text)
+        return
+    got = RoomIO.planeEqsFromText(text)
+    assert got.shape == exp.shape
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+def test_plane_eq_is_pcl_convention(built_lib):
+    """PCL writes ax + by + cz + d = 0; the reference wants n.x = d (Main.hs:1383-1386): d changes sign, both get normalised"""
+    pl = RoomIO.planeEqsFromText("0 0 2 -6\n")
+    assert np.allclose(pl, [[0, 0, 1, 3]])
+    assert abs(float(np.dot(pl[0, :3], [5, 5, 3]) - pl[0, 3])) < 1e-6  # the point (5, 5, 3) lies on 2z - 6 = 0
+
+
+def test_make_inward_facing_matches_oracle(built_lib):
+    rng = np.random.default_rng(3)
+    planes = np.stack([O.mk_plane_eq(rng.normal(size=3), rng.normal()) for _ in range(64)])
+    means = rng.normal(size=(64, 3)).astype(np.float32) * 3
+    center = rng.normal(size=3).astype(np.float32)
+    means[5] = center  # inward vector zero: not > 0, so the plane flips
+    got = RoomIO.makeInwardFacing(center, means, planes)
+    exp = O.make_inward_facing(center, means, planes)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+    assert (np.einsum("kc,kc->k", center[None] - means, got[:, :3]) >= 0).sum() >= 62
+    assert not np.array_equal(got, planes)
+
+
+def test_pcd_info_and_header_errors(built_lib, tmp_path):
+    xyz = np.arange(30, dtype=np.float32).reshape(10, 3)
+    for kind in ("ascii", "binary", "binary_compressed"):
+        p = str(tmp_path / f"{kind}.pcd")
+        write_pcd(p, xyz, rgb=np.zeros((10, 3), int) if kind != "ascii" else None, kind=kind)
+        assert RoomIO.pcdInfo(p) == (10, kind != "ascii", kind)
+    bad = tmp_path / "bad.pcd"
+    bad.write_bytes(b"VERSION 0.7\nFIELDS a b c\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n" + b"\0" * 12)
+    with pytest.raises(hb.HsError):
+        RoomIO.pcdInfo(str(bad))  # no x y z
+    with pytest.raises(hb.HsError):
+        RoomIO.pcdInfo(str(tmp_path / "missing.pcd"))
+
+
+# ------------------------------------------------------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def ctx():
+    c = hb.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["ascii", "binary", "binary_compressed"])
+@pytest.mark.parametrize("rgb_type", [None, "F", "U"])
+def test_cloud_from_pcd_bit_exact(ctx, tmp_path, kind, rgb_type):
+    rng = np.random.default_rng(21)
+    for n in (1, 255, 256, 257, 5000):
+        xyz = (rng.normal(size=(n, 3)) * 4).astype(np.float32)
+        xyz[n // 3: n // 2] = xyz[0]  # repeated records: LZF back references
+        rgb = rng.integers(0, 256, (n, 3)) if rgb_type else None
+        nrm = rng.normal(size=(n, 4)) if rgb_type else None  # x y z rgb normal_x normal_y normal_z curvature, as KinFu exports
+        p = str(tmp_path / f"c_{n}.pcd")
+        write_pcd(p, xyz, rgb, nrm, kind=kind, rgb_type=rgb_type or "F")
+        cl, col = RoomIO.cloudFromFile(ctx, p)
+        xo, co = O.pcd_load(p)
+        assert np.array_equal(cl.download().view(np.uint32), xo.view(np.uint32)) and np.array_equal(xo, xyz)
+        if rgb_type:
+            assert np.array_equal(col.download().view(np.uint32), co.view(np.uint32))
+        else:
+            assert col is None
+
+
+@pytest.mark.gpu
+def test_cloud_from_pcd_unaligned_fields_and_errors(ctx, tmp_path):
+    rng = np.random.default_rng(22)
+    xyz = rng.normal(size=(1001, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, (1001, 3))
+    for kind in ("binary", "binary_compressed"):
+        p = str(tmp_path / f"u_{kind}.pcd")
+        write_pcd(p, xyz, rgb, kind=kind, extra_front=True)  # a 1-byte field first: 17-byte records, nothing 4-byte aligned
+        cl, col = RoomIO.cloudFromFile(ctx, p)
+        assert np.array_equal(cl.download(), xyz)
+        assert np.array_equal(col.download(), O.pcd_load(p)[1])
+    empty = str(tmp_path / "empty.pcd")
+    write_pcd(empty, np.zeros((0, 3), np.float32))
+    with pytest.raises(hb.HsError, match="contains no points"):  # Main.hs:1344
+        RoomIO.cloudFromFile(ctx, empty)
+    trunc = tmp_path / "trunc.pcd"
+    trunc.write_bytes(open(str(tmp_path / "u_binary.pcd"), "rb").read()[:-100])
+    with pytest.raises(hb.HsError, match="ends early"):
+        RoomIO.cloudFromFile(ctx, str(trunc))
+
+
+def _write_room(directory, seed, flip_some=True, n=200_000):
+    from housescan_b200 import synth
+    rng = np.random.default_rng(seed)
+    os.makedirs(directory, exist_ok=True)
+    xyz, face = synth.cuboid_room_cloud(n, synth.C1_PARAMS, sigma=0.004, seed=seed)
+    write_pcd(os.path.join(directory, "cloud_downsampled.pcd"), xyz, rng.integers(0, 256, (n, 3)), rng.normal(size=(n, 4)), kind="binary")
+    planes = O.planes_from_cuboid(synth.C1_PARAMS)  # inward-facing n.x = d
+    lines = []
+    for k in range(6):
+        a, b, c, d = (float(v) for v in planes[k])
+        s = -1.0 if (flip_some and k % 2) else 1.0  # PCL's sign is arbitrary: makeInwardFacing has to repair it
+        scale = 1.0 + 0.5 * k
+        lines.append(f"{s * a * scale!r} {s * b * scale!r} {s * c * scale!r} {-s * d * scale!r}")  # ax + by + cz + d = 0
+        hull = xyz[face == k][:40]
+        write_pcd(os.path.join(directory, f"cloud_plane_hull{k}.pcd"), hull, kind="ascii")
+    with open(os.path.join(directory, "planes.txt"), "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return xyz
+
+
+@pytest.mark.gpu
+def test_load_room_matches_oracle(ctx, tmp_path):
+    d = str(tmp_path / "room0")
+    xyz = _write_room(d, 31)
+    cl, col, planes = RoomIO.loadRoom(ctx, d)
+    xo, co, po = O.load_room(d)
+    assert np.array_equal(cl.download().view(np.uint32), xo.view(np.uint32)) and np.array_equal(col.download(), co)
+    assert planes.shape == (6, 4) and np.array_equal(planes.view(np.uint32), po.view(np.uint32))
+    # every plane faces the room centre again, and the loaded room feeds the hot path: all six walls get their share of points
+    c = xyz.astype(np.float64).mean(axis=0)
+    assert ((planes[:, :3] @ c - planes[:, 3]) > 0).all()
+    a, _ = ctx.plane_assign(cl, planes)
+    assert (np.bincount(a, minlength=6) > 1000).all()
+    os.remove(os.path.join(d, "cloud_plane_hull3.pcd"))
+    with pytest.raises(hb.HsError):
+        RoomIO.loadRoom(ctx, d)
