@@ -32,6 +32,14 @@ __device__ __forceinline__ void load_px8(const uint16_t* __restrict__ depth, int
   }
 }
 
+// bit 15 / bit 31 set iff the low / high uint16 of w is non-zero (carry-free SWAR test: 3 logic ops for two pixels)
+__device__ __forceinline__ unsigned int nz16x2(unsigned int w) {
+  return (((w & 0x7fff7fffu) + 0x7fff7fffu) | w) & 0x80008000u;
+}
+// uint16 -> Float without I2F (quarter-rate XU pipe): 2^23 + d has d in its low mantissa bits
+__device__ __forceinline__ float u16_lo_f(unsigned int w) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), 8388608.0f); }
+__device__ __forceinline__ float u16_hi_f(unsigned int w) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)), 8388608.0f); }
+
 // pass 1: valid-pixel count per tile (+ optional byte mask); the last block turns counts into exclusive offsets
 __global__ void __launch_bounds__(HS_TPB)
 k_bp_count(const uint16_t* __restrict__ depth, int64_t npx, uint8_t* __restrict__ mask, unsigned int* __restrict__ tile_off,
@@ -40,19 +48,26 @@ k_bp_count(const uint16_t* __restrict__ depth, int64_t npx, uint8_t* __restrict_
   const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
   const bool aligned = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   const bool mask_aligned = mask && (reinterpret_cast<uintptr_t>(mask) & 7) == 0;
+  const bool swar = aligned && (!mask || mask_aligned);
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t i0 = t * BP_TILE + 8 * threadIdx.x;
-    unsigned int d[8], c = 0;
-    load_px8(depth, npx, i0, aligned, d);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) c += d[e] != 0;
-    if (mask) {
-      if (mask_aligned && i0 + 8 <= npx) {
-        uint2 m;
-        m.x = (d[0] != 0) | ((d[1] != 0) << 8) | ((d[2] != 0) << 16) | ((d[3] != 0) << 24);
-        m.y = (d[4] != 0) | ((d[5] != 0) << 8) | ((d[6] != 0) << 16) | ((d[7] != 0) << 24);
+    unsigned int c = 0;
+    if (swar && i0 + 8 <= npx) {  // whole 16-byte group: two pixels per logic op, no per-pixel compare
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(depth + i0));
+      const unsigned int n0 = nz16x2(v.x), n1 = nz16x2(v.y), n2 = nz16x2(v.z), n3 = nz16x2(v.w);
+      c = __popc(n0 | (n1 >> 1) | (n2 >> 2) | (n3 >> 3));
+      if (mask) {
+        uint2 m;  // byte e = (pixel e != 0)
+        m.x = __byte_perm(n0 >> 15, n1 >> 15, 0x6420);
+        m.y = __byte_perm(n2 >> 15, n3 >> 15, 0x6420);
         __stcs(reinterpret_cast<uint2*>(mask + i0), m);
-      } else {
+      }
+    } else {
+      unsigned int d[8];
+      load_px8(depth, npx, i0, aligned, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) c += d[e] != 0;
+      if (mask) {
 #pragma unroll
         for (int e = 0; e < 8; ++e)
           if (i0 + e < npx) mask[i0 + e] = static_cast<uint8_t>(d[e] != 0);
@@ -74,38 +89,63 @@ k_bp_count(const uint16_t* __restrict__ depth, int64_t npx, uint8_t* __restrict_
   if (threadIdx.x == 0) *n_valid = total;
 }
 
-// pass 2: order-preserving scatter of the scaled points.  The tile's points are compacted in shared memory first and then
-// written as one contiguous run of floats (fully coalesced), instead of 12-byte scattered stores.
+// pass 2: order-preserving scatter of the scaled points.  The tile's points are compacted in shared memory first, shifted so
+// that a shared-memory float index and its global float index agree modulo 4; the run then leaves as 16-byte stores
+// (fully coalesced STG.128) with at most three scalar floats at either end, instead of 12-byte scattered stores.
 __global__ void __launch_bounds__(HS_TPB)
 k_bp_scatter(const uint16_t* __restrict__ depth, int64_t npx, int w, const unsigned int* __restrict__ tile_off, float* __restrict__ xyz) {
   __shared__ unsigned int wsum[HS_TPB / 32];
-  __shared__ float stage[BP_TILE * 3];
+  __shared__ __align__(16) float stage[BP_TILE * 3 + 4];
   const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
   const bool aligned = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t i0 = t * BP_TILE + 8 * threadIdx.x;
-    unsigned int d[8], c = 0;
-    load_px8(depth, npx, i0, aligned, d);
+    unsigned int wv[4];
+    if (aligned && i0 + 8 <= npx) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(depth + i0));
+      wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
+    } else {
+      unsigned int d[8];
+      load_px8(depth, npx, i0, aligned, d);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) c += d[e] != 0;
+      for (int q = 0; q < 4; ++q) wv[q] = d[2 * q] | (d[2 * q + 1] << 16);
+    }
+    const unsigned int c = __popc(nz16x2(wv[0]) | (nz16x2(wv[1]) >> 1) | (nz16x2(wv[2]) >> 2) | (nz16x2(wv[3]) >> 3));
+    const int64_t dst0 = 3 * static_cast<int64_t>(tile_off[t]);  // first float of the tile's run in xyz
+    const int a = static_cast<int>(dst0 & 3);
     unsigned int pos = block_exclusive_prefix(c, wsum);  // position inside the tile
     unsigned int total = 0;
 #pragma unroll
     for (int q = 0; q < HS_TPB / 32; ++q) total += wsum[q];
     int y = static_cast<int>(i0 / w), x = static_cast<int>(i0 - static_cast<int64_t>(y) * w);
+    float xf = static_cast<float>(x);
+    float Y = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
+    float* sp = stage + a + 3 * pos;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (d[e] != 0) {
-        float X, Y, Z;
-        scale_point(x, y, d[e], X, Y, Z);
-        stage[3 * pos] = X; stage[3 * pos + 1] = Y; stage[3 * pos + 2] = Z;
-        ++pos;
+      const float df = (e & 1) ? u16_hi_f(wv[e >> 1]) : u16_lo_f(wv[e >> 1]);
+      if (df != 0.0f) {
+        sp[0] = div_rn_small(xf, 10.0f, HS_RCP10);
+        sp[1] = Y;
+        sp[2] = __fsub_rn(div_rn_small(df, 20.0f, HS_RCP20), 30.0f);
+        sp += 3;
       }
-      if (++x == w) { x = 0; ++y; }
+      xf = __fadd_rn(xf, 1.0f);
+      if (++x == w) { x = 0; xf = 0.0f; ++y; Y = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10); }
     }
     __syncthreads();
-    float* dst = xyz + 3 * static_cast<int64_t>(tile_off[t]);
-    for (unsigned int q = threadIdx.x; q < 3 * total; q += HS_TPB) __stcs(dst + q, stage[q]);
+    const int lo = a, hi = a + 3 * static_cast<int>(total);  // the run in shared-memory float indices; global index = dst0 - a + s
+    float* gbase = xyz + (dst0 - a);                          // 16-byte aligned
+    const int lo4 = (lo + 3) & ~3, hi4 = hi & ~3;
+    if (lo4 < hi4) {
+      if (static_cast<int>(threadIdx.x) < lo4 - lo) gbase[lo + threadIdx.x] = stage[lo + threadIdx.x];
+      const float4* s4 = reinterpret_cast<const float4*>(stage);
+      float4* g4 = reinterpret_cast<float4*>(gbase);
+      for (int v = (lo4 >> 2) + threadIdx.x; v < (hi4 >> 2); v += HS_TPB) __stcs(g4 + v, s4[v]);
+      if (static_cast<int>(threadIdx.x) < hi - hi4) gbase[hi4 + threadIdx.x] = stage[hi4 + threadIdx.x];
+    } else {
+      for (int q = lo + threadIdx.x; q < hi; q += HS_TPB) gbase[q] = stage[q];
+    }
     __syncthreads();
   }
 }

@@ -561,7 +561,7 @@ static int32_t launch_fast_t(hs_ctx* ctx, const float* xyz, int64_t n, const Pai
     HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_rooms_cuboid_sums_fast<NCONS, VAR, TPI, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_set = true;
   }
-  k_rooms_cuboid_sums_fast<NCONS, VAR, TPI, STG><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out, static_cast<unsigned int>(ctx->modes[6]));
+  k_rooms_cuboid_sums_fast<NCONS, VAR, TPI, STG><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out, static_cast<unsigned int>(ctx->modes[HS_MODE_PRODUCER_SLEEP]));
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;

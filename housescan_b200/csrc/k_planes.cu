@@ -341,8 +341,12 @@ k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __
     }
     const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
     int it = 0;
-    for (int64_t g = gl + static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x; g < gh; g += stride) {
-      const Pts4 p = load_group(xyz, g);
+    int64_t g = gl + static_cast<int64_t>(blockIdx.x) * HS_TPB + threadIdx.x;
+    Pts4 p, nx;
+    if (g < gh) nx = load_group(xyz, g);
+    for (; g < gh; g += stride) {
+      p = nx;
+      if (g + stride < gh) nx = load_group(xyz, g + stride);  // the next group is in flight while this one is evaluated
 #pragma unroll
       for (int e = 0; e < 4; ++e) ps_add<K>(a, mx, tbl, spl, p.x[e], p.y[e], p.z[e]);
       if ((++it & 7) == 0) {  // 32 points per chain
@@ -376,10 +380,25 @@ k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __
     __syncthreads();
   }
   if (!last_block_arrives(ticket, gridDim.x)) return;
+  // all K records at once: value idx = k * HS_PS + c of block b sits at partials[b * NV + idx]; slices of blocks are summed in
+  // slice order (a fixed tree for a fixed grid); component 9 is max |r|
   __shared__ double fin[HS_TPB];
-#pragma unroll
-  for (int k = 0; k < K; ++k)
-    last_block_sum_strided(partials + static_cast<int64_t>(k) * HS_PS, gridDim.x, K * HS_PS, out + k * HS_PS, fin);
+  constexpr int NV = K * HS_PS, S = HS_TPB / NV;
+  const int idx = threadIdx.x % NV, sl = threadIdx.x / NV;
+  const bool is_max = (idx % HS_PS) == 9;
+  double acc = 0.0;
+  if (sl < S)
+    for (unsigned int b = sl; b < gridDim.x; b += S) {
+      const double v = __ldcg(partials + static_cast<int64_t>(b) * NV + idx);
+      acc = is_max ? fmax(acc, v) : acc + v;
+    }
+  fin[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double t = 0.0;
+    for (int q = 0; q < S; ++q) { const double v = fin[q * NV + threadIdx.x]; t = is_max ? fmax(t, v) : t + v; }
+    out[threadIdx.x] = t;
+  }
 }
 
 }  // namespace hsk

@@ -174,6 +174,18 @@ k_sel2_next(const unsigned int* __restrict__ keys, int64_t n, int shift, int bit
 // ---- order-preserving filter  (comp axis) <= limit -----------------------------------------------------------------
 #define FL_TILE 1024  // points per tile: one group of 4 per thread
 
+// this thread's group of 4 points of tile t (whole group: 3 x LDG.128; ragged end: scalar loads, missing points flagged)
+__device__ __forceinline__ int load_tile_group(const float* __restrict__ xyz, int64_t n, int64_t i0, Pts4& p) {
+  if (i0 + 4 <= n) { p = load_group(xyz, i0 >> 2); return 4; }
+  int m = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    p.x[e] = p.y[e] = p.z[e] = 0.f;
+    if (i0 + e < n) { p.x[e] = __ldg(xyz + 3 * (i0 + e)); p.y[e] = __ldg(xyz + 3 * (i0 + e) + 1); p.z[e] = __ldg(xyz + 3 * (i0 + e) + 2); m = e + 1; }
+  }
+  return m;
+}
+
 __global__ void __launch_bounds__(HS_TPB)
 k_filter_count(const float* __restrict__ xyz, int64_t n, int axis, float limit, unsigned int* __restrict__ tile_off,
                unsigned int* ticket, int64_t* __restrict__ n_out) {
@@ -181,9 +193,11 @@ k_filter_count(const float* __restrict__ xyz, int64_t n, int axis, float limit, 
   const int64_t ntiles = (n + FL_TILE - 1) / FL_TILE;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t i0 = t * FL_TILE + 4 * threadIdx.x;
+    Pts4 p;
+    const int m = load_tile_group(xyz, n, i0, p);
     unsigned int c = 0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { const int64_t i = i0 + e; if (i < n) c += __ldg(xyz + 3 * i + axis) <= limit; }
+    for (int e = 0; e < 4; ++e) c += (e < m) && ((axis == 0 ? p.x[e] : (axis == 1 ? p.y[e] : p.z[e])) <= limit);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
@@ -200,37 +214,56 @@ k_filter_count(const float* __restrict__ xyz, int64_t n, int axis, float limit, 
   if (threadIdx.x == 0) *n_out = total;
 }
 
+// the tile's kept points are compacted in shared memory, shifted so that shared and global float indices agree modulo 4,
+// and leave as 16-byte stores (same scheme as k_bp_scatter); the colour cloud rides along with the same positions
+__device__ __forceinline__ void store_run(const float* stage, int a, int nfloats, float* __restrict__ out, int64_t dst0) {
+  const int lo = a, hi = a + nfloats;
+  float* gbase = out + (dst0 - a);
+  const int lo4 = (lo + 3) & ~3, hi4 = hi & ~3;
+  if (lo4 < hi4) {
+    if (static_cast<int>(threadIdx.x) < lo4 - lo) gbase[lo + threadIdx.x] = stage[lo + threadIdx.x];
+    const float4* s4 = reinterpret_cast<const float4*>(stage);
+    float4* g4 = reinterpret_cast<float4*>(gbase);
+    for (int v = (lo4 >> 2) + threadIdx.x; v < (hi4 >> 2); v += HS_TPB) __stcs(g4 + v, s4[v]);
+    if (static_cast<int>(threadIdx.x) < hi - hi4) gbase[hi4 + threadIdx.x] = stage[hi4 + threadIdx.x];
+  } else {
+    for (int q = lo + threadIdx.x; q < hi; q += HS_TPB) gbase[q] = stage[q];
+  }
+}
+
 __global__ void __launch_bounds__(HS_TPB)
 k_filter_scatter(const float* __restrict__ xyz, int64_t n, int axis, float limit, const unsigned int* __restrict__ tile_off,
                  const float* __restrict__ extra_in, float* __restrict__ out, float* __restrict__ extra_out) {
   __shared__ unsigned int wsum[HS_TPB / 32];
+  __shared__ __align__(16) float stage[FL_TILE * 3 + 4];
+  __shared__ __align__(16) float stage2[FL_TILE * 3 + 4];
   const int64_t ntiles = (n + FL_TILE - 1) / FL_TILE;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t i0 = t * FL_TILE + 4 * threadIdx.x;
-    float p[4][3];
+    Pts4 p, q;
+    const int m = load_tile_group(xyz, n, i0, p);
+    if (extra_in) load_tile_group(extra_in, n, i0, q);
     bool keep[4];
     unsigned int c = 0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int64_t i = i0 + e;
-      keep[e] = false;
-      if (i < n) {
-        p[e][0] = __ldg(xyz + 3 * i); p[e][1] = __ldg(xyz + 3 * i + 1); p[e][2] = __ldg(xyz + 3 * i + 2);
-        keep[e] = (axis == 0 ? p[e][0] : (axis == 1 ? p[e][1] : p[e][2])) <= limit;
-      }
-      c += keep[e];
-    }
-    int64_t pos = static_cast<int64_t>(tile_off[t]) + block_exclusive_prefix(c, wsum);
+    for (int e = 0; e < 4; ++e) { keep[e] = (e < m) && ((axis == 0 ? p.x[e] : (axis == 1 ? p.y[e] : p.z[e])) <= limit); c += keep[e]; }
+    const int64_t dst0 = 3 * static_cast<int64_t>(tile_off[t]);
+    const int a = static_cast<int>(dst0 & 3);
+    const unsigned int pos = block_exclusive_prefix(c, wsum);
+    unsigned int total = 0;
+#pragma unroll
+    for (int w = 0; w < HS_TPB / 32; ++w) total += wsum[w];
+    int sp = a + 3 * static_cast<int>(pos);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       if (keep[e]) {
-        out[3 * pos] = p[e][0]; out[3 * pos + 1] = p[e][1]; out[3 * pos + 2] = p[e][2];
-        if (extra_in) {
-          const int64_t i = i0 + e;
-          extra_out[3 * pos] = __ldg(extra_in + 3 * i); extra_out[3 * pos + 1] = __ldg(extra_in + 3 * i + 1); extra_out[3 * pos + 2] = __ldg(extra_in + 3 * i + 2);
-        }
-        ++pos;
+        stage[sp] = p.x[e]; stage[sp + 1] = p.y[e]; stage[sp + 2] = p.z[e];
+        if (extra_in) { stage2[sp] = q.x[e]; stage2[sp + 1] = q.y[e]; stage2[sp + 2] = q.z[e]; }
+        sp += 3;
       }
+    __syncthreads();
+    store_run(stage, a, 3 * static_cast<int>(total), out, dst0);
+    if (extra_in) store_run(stage2, a, 3 * static_cast<int>(total), extra_out, dst0);
     __syncthreads();
   }
 }

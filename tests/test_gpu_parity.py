@@ -476,7 +476,7 @@ def _ne_scale(rec):
     return np.maximum(sc, 1e-300)
 
 
-# mode key 6: 0 = throughput form (Float chains of 16 pixels, then Double; frames cut into row bands), 1 = all-Double form
+# mode key 9: 0 = throughput form (Float chains of 16 pixels, then Double; frames cut into row bands), 1 = all-Double form
 @pytest.mark.parametrize("ne_mode", [0, 1], ids=["f32chains", "double"])
 @pytest.mark.parametrize("use_intr,use_pose", [(False, False), (True, True), (True, False), (False, True)])
 def test_backproject_reduce6x6(ctx, use_intr, use_pose, ne_mode):
@@ -485,11 +485,11 @@ def test_backproject_reduce6x6(ctx, use_intr, use_pose, ne_mode):
     planes = O.planes_from_cuboid(synth.C1_PARAMS) if use_intr else np.stack(
         [O.mk_plane_eq([0, 0, 1], 40.0), O.mk_plane_eq([1, 0, 0], 3.0), O.mk_plane_eq([0, 1, 0], 2.0), O.mk_plane_eq([0.6, 0, 0.8], 60.0)])
     ps = poses if use_pose else None
-    ctx.set_mode(6, ne_mode)
+    ctx.set_mode(9, ne_mode)
     try:
         out_g = ctx.backproject_reduce6x6(frames, 160, 120, planes, intr, ps)
     finally:
-        ctx.set_mode(6, 0)
+        ctx.set_mode(9, 0)
     out_o = O.backproject_reduce6x6(frames, 160, 120, planes, intr, ps)
     assert np.array_equal(out_g[:, 28], out_o[:, 28])
     if ne_mode == 1:

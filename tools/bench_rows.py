@@ -194,7 +194,7 @@ if want("A1"):
     poses = np.ascontiguousarray(np.tile(poses8, ((nf + 7) // 8, 1))[:nf])
     fn_pose = lambda: ctx._chk(lib.hs_backproject_reduce6x6_dev(ctx.h, C.c_void_p(frames.data_ptr()), nf, w, h, ptr(intr), ptr(poses), ptr(planes), 6, C.c_void_p(d_out.data_ptr())))
     for mode, tag in ((1, "all-Double"), (0, "Float chains")):
-        ctx.set_mode(6, mode)
+        ctx.set_mode(9, mode)
         ms = timed(fn, reps=5)
         o = d_out.view(nf, hb.HS_NE).clone()
         cnt_ok = bool(torch.equal(o[:, 28].long(), (frames != 0).view(nf, -1).sum(dim=1)))
