@@ -67,3 +67,17 @@ foreign import ccall safe "hs_peer_mailbox_create"  c_peer_mailbox_create  :: Pt
 foreign import ccall safe "hs_peer_mailbox_connect" c_peer_mailbox_connect :: Ptr HsCtx -> Ptr Word8 -> IO Int32
 foreign import ccall safe "hs_rooms_cuboid_sums_allreduce_async"
   c_rooms_cuboid_sums_allreduce :: Ptr HsCtx -> Ptr HsCloud -> Ptr Int64 -> Int32 -> Ptr CDouble -> Ptr () -> IO Int32
+
+-- room input formats (SURVEY.md 8f rank 1): planeEqsFromFile Main.hs:1379-1389, cloudFromFile :1332-1345, loadRoom :1740-1765
+foreign import ccall unsafe "hs_plane_eqs_from_text"
+  c_plane_eqs_from_text :: CString -> Int64 -> Ptr CFloat -> Int32 -> Ptr Int32 -> IO Int32
+foreign import ccall safe "hs_plane_eqs_from_file"
+  c_plane_eqs_from_file :: CString -> Ptr CFloat -> Int32 -> Ptr Int32 -> IO Int32
+foreign import ccall safe "hs_cloud_from_pcd"
+  c_cloud_from_pcd :: Ptr HsCtx -> CString -> Ptr (Ptr HsCloud) -> Ptr (Ptr HsCloud) -> IO Int32
+foreign import ccall safe "hs_pcd_info"
+  c_pcd_info :: CString -> Ptr Int64 -> Ptr Int32 -> Ptr Int32 -> IO Int32
+foreign import ccall unsafe "hs_make_inward_facing"
+  c_make_inward_facing :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Int32 -> IO Int32
+foreign import ccall safe "hs_load_room"
+  c_load_room :: Ptr HsCtx -> CString -> Ptr (Ptr HsCloud) -> Ptr (Ptr HsCloud) -> Ptr CFloat -> Int32 -> Ptr Int32 -> IO Int32

@@ -239,6 +239,7 @@ static int32_t fill_plane_table(hs_ctx* ctx, const float* planes, int32_t K, int
   t.K = K;
   std::memset(t.pl, 0, sizeof t.pl);
   std::memcpy(t.pl, planes, sizeof(float) * 4 * K);
+  plane_table_mark_pairs(t);
   return HS_OK;
 }
 

@@ -72,8 +72,17 @@ struct RoomTable {
 
 struct PlaneTable {
   int32_t K;
+  int32_t paired;  // K == 6 and planes 2j+1 have exactly the negated normal of 2j (set by plane_table_mark_pairs)
   float pl[16][4];
 };
+inline void plane_table_mark_pairs(PlaneTable& t) {
+  t.paired = 0;
+  if (t.K != 6) return;
+  for (int j = 0; j < 3; ++j)
+    for (int c = 0; c < 3; ++c)
+      if (!(t.pl[2 * j][c] == -t.pl[2 * j + 1][c])) return;  // NaN never pairs
+  t.paired = 1;
+}
 
 #define HS_CUDA_TRY(ctx, call)                                                                                  \
   do {                                                                                                          \

@@ -10,6 +10,46 @@ __device__ __forceinline__ float plane_dist(float nx, float ny, float nz, float 
   return __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, x), __fmul_rn(ny, y)), __fmul_rn(nz, z)), d);
 }
 
+// First minimum of |distance| over the planes of a table (strict <: ties keep the lower index = minimumBy semantics); returns
+// the index and leaves min |distance| in ab.  Only the index is carried through the chain (FSETP + SEL) and the running minimum
+// is an FMNMX; callers that need the signed residual recompute it from the winner's plane.
+//   KT > 0: plane count known at compile time (unrolled, constants straight from the constant bank); KT == 0: tbl.K at run time.
+//   PAIRED (KT == 6 only): planes 2j and 2j+1 have exactly negated normals (a cuboid room's walls, Main.hs:1855-1874), so one dot
+//   product t_j serves both: fl(-a x) == -fl(a x) and round-to-nearest is symmetric, hence the dot product of the negated normal
+//   is exactly -t_j and its distance -t_j - d is the same Float the generic path computes.  15 of the 36 operations go away.
+template <int KT, bool PAIRED>
+__device__ __forceinline__ int nearest_plane(const PlaneTable& t, float x, float y, float z, float& ab) {
+  int kb = 0;
+  if (KT == 6 && PAIRED) {
+    float a[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float tj = __fadd_rn(__fadd_rn(__fmul_rn(t.pl[2 * j][0], x), __fmul_rn(t.pl[2 * j][1], y)), __fmul_rn(t.pl[2 * j][2], z));
+      a[2 * j] = fabsf(__fsub_rn(tj, t.pl[2 * j][3]));
+      a[2 * j + 1] = fabsf(__fsub_rn(-tj, t.pl[2 * j + 1][3]));
+    }
+    ab = a[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) { kb = (a[k] < ab) ? k : kb; ab = fminf(ab, a[k]); }
+  } else if (KT > 0) {
+    ab = fabsf(plane_dist(t.pl[0][0], t.pl[0][1], t.pl[0][2], t.pl[0][3], x, y, z));
+#pragma unroll
+    for (int k = 1; k < KT; ++k) {
+      const float ak = fabsf(plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z));
+      kb = (ak < ab) ? k : kb;
+      ab = fminf(ab, ak);
+    }
+  } else {
+    ab = fabsf(plane_dist(t.pl[0][0], t.pl[0][1], t.pl[0][2], t.pl[0][3], x, y, z));
+    for (int k = 1; k < t.K; ++k) {
+      const float ak = fabsf(plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z));
+      kb = (ak < ab) ? k : kb;
+      ab = fminf(ab, ak);
+    }
+  }
+  return kb;
+}
+
 // Correctly rounded Float division by a divisor that is the same for every point, without the MUFU.RCP + range-check sequence
 // that `/` compiles to (~12 instructions and a slow-path branch per quotient).  y must be RN(1/b) (computed once on the host with
 // an IEEE division).  q0 = RN(a y) is within 2 ulp of a/b; one residual step makes it faithful; by Markstein's theorem

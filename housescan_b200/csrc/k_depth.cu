@@ -40,47 +40,64 @@ __device__ __forceinline__ unsigned int nz16x2(unsigned int w) {
 __device__ __forceinline__ float u16_lo_f(unsigned int w) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), 8388608.0f); }
 __device__ __forceinline__ float u16_hi_f(unsigned int w) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)), 8388608.0f); }
 
-// pass 1: valid-pixel count per tile (+ optional byte mask); the last block turns counts into exclusive offsets
+// pass 1: valid-pixel count per tile (+ optional byte mask); the last block turns counts into exclusive offsets.
+// A block takes BP_CT consecutive tiles per iteration: their loads are all in flight before the first count is reduced, and the
+// counts of two tiles share one shuffle tree (each fits 16 bits), so a round costs one barrier pair for BP_CT * 2048 pixels.
+#define BP_CT 4
+__device__ __forceinline__ unsigned int count_group(const uint16_t* __restrict__ depth, int64_t npx, uint8_t* __restrict__ mask, int64_t i0,
+                                                    bool aligned, bool swar) {
+  if (i0 >= npx) return 0u;
+  if (swar && i0 + 8 <= npx) {  // whole 16-byte group: two pixels per logic op, no per-pixel compare
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(depth + i0));
+    const unsigned int n0 = nz16x2(v.x), n1 = nz16x2(v.y), n2 = nz16x2(v.z), n3 = nz16x2(v.w);
+    if (mask) {
+      uint2 m;  // byte e = (pixel e != 0)
+      m.x = __byte_perm(n0 >> 15, n1 >> 15, 0x6420);
+      m.y = __byte_perm(n2 >> 15, n3 >> 15, 0x6420);
+      __stcs(reinterpret_cast<uint2*>(mask + i0), m);
+    }
+    return __popc(n0 | (n1 >> 1) | (n2 >> 2) | (n3 >> 3));
+  }
+  unsigned int d[8], c = 0;
+  load_px8(depth, npx, i0, aligned, d);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) c += d[e] != 0;
+  if (mask) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (i0 + e < npx) mask[i0 + e] = static_cast<uint8_t>(d[e] != 0);
+  }
+  return c;
+}
+
 __global__ void __launch_bounds__(HS_TPB)
 k_bp_count(const uint16_t* __restrict__ depth, int64_t npx, uint8_t* __restrict__ mask, unsigned int* __restrict__ tile_off,
            unsigned int* ticket, int64_t* __restrict__ n_valid) {
-  __shared__ unsigned int wsum[HS_TPB / 32];
+  __shared__ unsigned int wsum[BP_CT / 2][HS_TPB / 32];
   const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
+  const int64_t nrounds = (ntiles + BP_CT - 1) / BP_CT;
   const bool aligned = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   const bool mask_aligned = mask && (reinterpret_cast<uintptr_t>(mask) & 7) == 0;
   const bool swar = aligned && (!mask || mask_aligned);
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t i0 = t * BP_TILE + 8 * threadIdx.x;
-    unsigned int c = 0;
-    if (swar && i0 + 8 <= npx) {  // whole 16-byte group: two pixels per logic op, no per-pixel compare
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(depth + i0));
-      const unsigned int n0 = nz16x2(v.x), n1 = nz16x2(v.y), n2 = nz16x2(v.z), n3 = nz16x2(v.w);
-      c = __popc(n0 | (n1 >> 1) | (n2 >> 2) | (n3 >> 3));
-      if (mask) {
-        uint2 m;  // byte e = (pixel e != 0)
-        m.x = __byte_perm(n0 >> 15, n1 >> 15, 0x6420);
-        m.y = __byte_perm(n2 >> 15, n3 >> 15, 0x6420);
-        __stcs(reinterpret_cast<uint2*>(mask + i0), m);
-      }
-    } else {
-      unsigned int d[8];
-      load_px8(depth, npx, i0, aligned, d);
+  for (int64_t rd = blockIdx.x; rd < nrounds; rd += gridDim.x) {
+    const int64_t t0 = rd * BP_CT;
+    unsigned int c[BP_CT];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) c += d[e] != 0;
-      if (mask) {
+    for (int q = 0; q < BP_CT; ++q) c[q] = count_group(depth, npx, mask, (t0 + q) * BP_TILE + 8 * threadIdx.x, aligned, swar);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (i0 + e < npx) mask[i0 + e] = static_cast<uint8_t>(d[e] != 0);
-      }
+    for (int q = 0; q < BP_CT / 2; ++q) {
+      unsigned int cc = c[2 * q] | (c[2 * q + 1] << 16);  // a tile holds 2048 pixels: both counts fit 16 bits all the way up
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
+      if ((threadIdx.x & 31) == 0) wsum[q][threadIdx.x >> 5] = cc;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int s = 0;
-      for (int w = 0; w < HS_TPB / 32; ++w) s += wsum[w];
-      tile_off[t] = s;
+    if (threadIdx.x < BP_CT / 2) {
+      unsigned int sum = 0;
+      for (int w = 0; w < HS_TPB / 32; ++w) sum += wsum[threadIdx.x][w];
+      const int64_t t = t0 + 2 * threadIdx.x;
+      if (t < ntiles) tile_off[t] = sum & 0xffffu;
+      if (t + 1 < ntiles) tile_off[t + 1] = sum >> 16;
     }
     __syncthreads();
   }
@@ -117,7 +134,9 @@ k_bp_scatter(const uint16_t* __restrict__ depth, int64_t npx, int w, const unsig
     unsigned int total = 0;
 #pragma unroll
     for (int q = 0; q < HS_TPB / 32; ++q) total += wsum[q];
-    int y = static_cast<int>(i0 / w), x = static_cast<int>(i0 - static_cast<int64_t>(y) * w);
+    int y, x;  // row / column of this thread's first pixel; a 64-bit division costs more than the rest of the iteration
+    if (npx <= 0xffffffffll) { const unsigned int q = static_cast<unsigned int>(i0) / static_cast<unsigned int>(w); y = static_cast<int>(q); x = static_cast<int>(static_cast<unsigned int>(i0) - q * static_cast<unsigned int>(w)); }
+    else { y = static_cast<int>(i0 / w); x = static_cast<int>(i0 - static_cast<int64_t>(y) * w); }
     float xf = static_cast<float>(x);
     float Y = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
     float* sp = stage + a + 3 * pos;
@@ -305,7 +324,7 @@ k_reduce6x6(const uint16_t* __restrict__ frames, int64_t nframes, int w, int h, 
 //     evenly; the band that finishes a frame last adds the bands in band order (deterministic).
 // Requires w % 8 == 0 (a thread's 8 pixels share a row) and 16-byte aligned frames; the launcher falls back otherwise.
 // ------------------------------------------------------------------------------------------------------------------
-template <bool INTR, bool POSE, int KT>
+template <bool INTR, bool POSE, int KT, bool PAIRED>
 __device__ __forceinline__ PixelJ ne_geometry_fast(const FrameGeom& geo, float rfx, float rfy, const float (&M)[12], const PlaneTable& tbl,
                                                    const float4* __restrict__ spl, float xf, float yc /* INTR: y - cy; else y/10 */, unsigned int d) {
   float X, Y, Z;
@@ -325,22 +344,8 @@ __device__ __forceinline__ PixelJ ne_geometry_fast(const FrameGeom& geo, float r
     py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[1]), __fmul_rn(Y, M[4])), __fmul_rn(Z, M[7])), M[10]);
     pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(X, M[2]), __fmul_rn(Y, M[5])), __fmul_rn(Z, M[8])), M[11]);
   }
-  float ab = fabsf(plane_dist(tbl.pl[0][0], tbl.pl[0][1], tbl.pl[0][2], tbl.pl[0][3], px, py, pz));
-  int kb = 0;
-  if (KT > 0) {
-#pragma unroll
-    for (int k = 1; k < KT; ++k) {
-      const float ak = fabsf(plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], px, py, pz));
-      kb = (ak < ab) ? k : kb;  // strict: ties keep the lower index
-      ab = fminf(ab, ak);
-    }
-  } else {
-    for (int k = 1; k < tbl.K; ++k) {
-      const float ak = fabsf(plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], px, py, pz));
-      kb = (ak < ab) ? k : kb;
-      ab = fminf(ab, ak);
-    }
-  }
+  float ab;
+  const int kb = nearest_plane<KT, PAIRED>(tbl, px, py, pz, ab);
   const float4 nn = spl[kb];
   PixelJ o;
   o.j[0] = __fsub_rn(__fmul_rn(py, nn.z), __fmul_rn(pz, nn.y));
@@ -391,7 +396,7 @@ __device__ __forceinline__ void ne_accumulate_f32(float (&acc)[HS_NE], const Pix
 #ifndef NE_ILP
 #define NE_ILP 4
 #endif
-template <bool INTR, bool POSE, int KT>
+template <bool INTR, bool POSE, int KT, bool PAIRED>
 __global__ void __launch_bounds__(HS_TPB, 2)
 k_reduce6x6_f32(const uint16_t* __restrict__ frames, int64_t nframes, int w, int h, const FrameGeom geo, float rfx, float rfy,
                 const float* __restrict__ poses, const __grid_constant__ PlaneTable tbl, int parts, double* __restrict__ partials,
@@ -442,7 +447,7 @@ k_reduce6x6_f32(const uint16_t* __restrict__ frames, int64_t nframes, int w, int
         for (int e = 0; e < NE_ILP; ++e) {
           const int px = NE_ILP * q + e;
           dd[e] = (wv[px >> 1] >> (16 * (px & 1))) & 0xffffu;
-          pj[e] = ne_geometry_fast<INTR, POSE, KT>(geo, rfx, rfy, M, tbl, spl, __fadd_rn(x0f, static_cast<float>(px)), yc, dd[e]);
+          pj[e] = ne_geometry_fast<INTR, POSE, KT, PAIRED>(geo, rfx, rfy, M, tbl, spl, __fadd_rn(x0f, static_cast<float>(px)), yc, dd[e]);
         }
 #pragma unroll
         for (int e = 0; e < NE_ILP; ++e) ne_accumulate_f32(acc, pj[e], dd[e]);
@@ -494,9 +499,10 @@ int32_t launch_backproject(hs_ctx* ctx, const uint16_t* d_depth, int32_t w, int3
   const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
   int64_t nb = std::min<int64_t>(ntiles, static_cast<int64_t>(ctx->sm_count) * 8);
   if (nb < 1) nb = 1;
+  const int64_t nbc = std::max<int64_t>(1, std::min<int64_t>((ntiles + BP_CT - 1) / BP_CT, static_cast<int64_t>(ctx->sm_count) * 8));
   if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(ntiles + 1) * sizeof(unsigned int))) return rc;
   unsigned int* tile_off = reinterpret_cast<unsigned int*>(ctx->d_scratch);
-  k_bp_count<<<static_cast<int>(nb), HS_TPB, 0, ctx->stream>>>(d_depth, npx, d_mask, tile_off, ctx->d_ticket, d_nvalid);
+  k_bp_count<<<static_cast<int>(nbc), HS_TPB, 0, ctx->stream>>>(d_depth, npx, d_mask, tile_off, ctx->d_ticket, d_nvalid);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   if (d_xyz) {
@@ -534,18 +540,19 @@ int32_t launch_reduce6x6(hs_ctx* ctx, const uint16_t* d_frames, int64_t nframes,
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nframes * parts, static_cast<int64_t>(ctx->sm_count) * 2)));
     const float rfx = intr ? 1.0f / geo.fx : 0.f, rfy = intr ? 1.0f / geo.fy : 0.f;  // RN(1/f): IEEE division on the host
     const int dsm = HS_NE * HS_TPB * static_cast<int>(sizeof(double));
-#define HS_NEF_LAUNCH(I, P, KT_)                                                                                       \
-  cudaFuncSetAttribute(k_reduce6x6_f32<I, P, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm);                  \
-  k_reduce6x6_f32<I, P, KT_><<<grid, HS_TPB, dsm, ctx->stream>>>(d_frames, nframes, w, h, geo, rfx, rfy, d_poses, tbl, parts, partials, part_done, d_out, counters)
-#define HS_NEF_PICK(KT_)                                  \
-  do {                                                    \
-    if (intr && d_poses) { HS_NEF_LAUNCH(true, true, KT_); }  \
-    else if (intr) { HS_NEF_LAUNCH(true, false, KT_); }       \
-    else if (d_poses) { HS_NEF_LAUNCH(false, true, KT_); }    \
-    else { HS_NEF_LAUNCH(false, false, KT_); }                \
+#define HS_NEF_LAUNCH(I, P, KT_, PR_)                                                                                      \
+  cudaFuncSetAttribute(k_reduce6x6_f32<I, P, KT_, PR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm);                 \
+  k_reduce6x6_f32<I, P, KT_, PR_><<<grid, HS_TPB, dsm, ctx->stream>>>(d_frames, nframes, w, h, geo, rfx, rfy, d_poses, tbl, parts, partials, part_done, d_out, counters)
+#define HS_NEF_PICK(KT_, PR_)                                   \
+  do {                                                          \
+    if (intr && d_poses) { HS_NEF_LAUNCH(true, true, KT_, PR_); }  \
+    else if (intr) { HS_NEF_LAUNCH(true, false, KT_, PR_); }       \
+    else if (d_poses) { HS_NEF_LAUNCH(false, true, KT_, PR_); }    \
+    else { HS_NEF_LAUNCH(false, false, KT_, PR_); }                \
   } while (0)
-    if (tbl.K == 6) HS_NEF_PICK(6);
-    else HS_NEF_PICK(0);
+    if (tbl.K == 6 && tbl.paired) HS_NEF_PICK(6, true);  // a cuboid room's walls
+    else if (tbl.K == 6) HS_NEF_PICK(6, false);
+    else HS_NEF_PICK(0, false);
 #undef HS_NEF_PICK
 #undef HS_NEF_LAUNCH
     ctx->launches++;

@@ -153,34 +153,19 @@ __device__ __forceinline__ int nearestK(const PlaneTable& t, float x, float y, f
   return kb;
 }
 
-// same choice with a cheaper selection chain: only the index is carried (FSETP + SEL) and the running minimum is an FMNMX;
-// the winner's residual is recomputed from its plane (one LDS.128 + the same six operations => the same bits).
-// KT > 0: the number of planes is known at compile time (unrolled, plane constants straight from the constant bank).
-template <int KT>
+// nearest plane (k_common.cuh nearest_plane) + the winner's residual recomputed from its plane: one LDS.128 and the same six
+// operations as in the chain, hence the same bits
+template <int KT, bool PAIRED>
 __device__ __forceinline__ int nearestK_lds(const PlaneTable& t, const float4* __restrict__ spl, float x, float y, float z, float& r) {
-  float ab = fabsf(plane_dist(t.pl[0][0], t.pl[0][1], t.pl[0][2], t.pl[0][3], x, y, z));
-  int kb = 0;
-  if (KT > 0) {
-#pragma unroll
-    for (int k = 1; k < KT; ++k) {
-      const float ak = fabsf(plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z));
-      kb = (ak < ab) ? k : kb;
-      ab = fminf(ab, ak);
-    }
-  } else {
-    for (int k = 1; k < t.K; ++k) {
-      const float ak = fabsf(plane_dist(t.pl[k][0], t.pl[k][1], t.pl[k][2], t.pl[k][3], x, y, z));
-      kb = (ak < ab) ? k : kb;
-      ab = fminf(ab, ak);
-    }
-  }
+  float ab;
+  const int kb = nearest_plane<KT, PAIRED>(t, x, y, z, ab);
   const float4 nn = spl[kb];
   r = plane_dist(nn.x, nn.y, nn.z, nn.w, x, y, z);
   return kb;
 }
-#define nearestK(tbl, x, y, z, r) nearestK_lds<KT>(tbl, spl, x, y, z, r)
+#define nearestK(tbl, x, y, z, r) nearestK_lds<KT, PAIRED>(tbl, spl, x, y, z, r)
 
-template <int KT>
+template <int KT, bool PAIRED>
 __global__ void __launch_bounds__(HS_TPB)
 k_plane_assign(const float* __restrict__ xyz, int64_t n, const __grid_constant__ PlaneTable tbl, uint8_t* __restrict__ assign,
                float* __restrict__ resid) {
@@ -291,16 +276,10 @@ k_plane_sums(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid
 // FMA is exact, only the short partial sums are rounded to Float), and are then added into per-thread Doubles that live in shared
 // memory, so the registers hold the 10 K chains and four points in flight instead of 9 K Doubles.  Points are read as 4-point
 // groups (3 x LDG.128); the ragged head and tail of the range (room offsets are arbitrary) are taken one point per thread.
-template <int K>
+template <int K, bool PAIRED>
 __device__ __forceinline__ void ps_add(float (&a)[K][9], float (&mx)[K], const PlaneTable& tbl, const float4* __restrict__ spl, float x, float y, float z) {
-  float ab = fabsf(plane_dist(tbl.pl[0][0], tbl.pl[0][1], tbl.pl[0][2], tbl.pl[0][3], x, y, z));
-  int kb = 0;
-#pragma unroll
-  for (int k = 1; k < K; ++k) {
-    const float ak = fabsf(plane_dist(tbl.pl[k][0], tbl.pl[k][1], tbl.pl[k][2], tbl.pl[k][3], x, y, z));
-    kb = (ak < ab) ? k : kb;  // strict: ties keep the lower index
-    ab = fminf(ab, ak);
-  }
+  float ab;
+  const int kb = nearest_plane<K, PAIRED>(tbl, x, y, z, ab);
   const float4 nn = spl[kb];
   const float r = plane_dist(nn.x, nn.y, nn.z, nn.w, x, y, z);  // the winner's residual: same operations, same bits
   // predicated FP instructions, no branches and no selects: the four points a thread holds stay independent streams
@@ -315,7 +294,7 @@ __device__ __forceinline__ void ps_add(float (&a)[K][9], float (&mx)[K], const P
         : "f"(r), "f"(x), "f"(y), "f"(z), "r"(kb), "r"(k), "f"(ab));
 }
 
-template <int K>
+template <int K, bool PAIRED>
 __global__ void __launch_bounds__(HS_TPB, 2)
 k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid_constant__ PlaneTable tbl,
                  double* __restrict__ partials, unsigned int* ticket, double* __restrict__ out) {
@@ -336,8 +315,8 @@ k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __
   if (gl <= gh) {
     if (blockIdx.x == 0) {  // ragged head / tail points (at most 3 each)
       const int64_t nh = gl * 4 - i0, nt = i1 - gh * 4;
-      if (threadIdx.x < nh) { const int64_t i = i0 + threadIdx.x; ps_add<K>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
-      else if (threadIdx.x >= 32 && threadIdx.x - 32 < nt) { const int64_t i = gh * 4 + threadIdx.x - 32; ps_add<K>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+      if (threadIdx.x < nh) { const int64_t i = i0 + threadIdx.x; ps_add<K, PAIRED>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+      else if (threadIdx.x >= 32 && threadIdx.x - 32 < nt) { const int64_t i = gh * 4 + threadIdx.x - 32; ps_add<K, PAIRED>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
     }
     const int64_t stride = static_cast<int64_t>(gridDim.x) * HS_TPB;
     int it = 0;
@@ -348,7 +327,7 @@ k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __
       p = nx;
       if (g + stride < gh) nx = load_group(xyz, g + stride);  // the next group is in flight while this one is evaluated
 #pragma unroll
-      for (int e = 0; e < 4; ++e) ps_add<K>(a, mx, tbl, spl, p.x[e], p.y[e], p.z[e]);
+      for (int e = 0; e < 4; ++e) ps_add<K, PAIRED>(a, mx, tbl, spl, p.x[e], p.y[e], p.z[e]);
       if ((++it & 7) == 0) {  // 32 points per chain
 #pragma unroll
         for (int k = 0; k < K; ++k)
@@ -358,7 +337,7 @@ k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __
     }
   } else if (blockIdx.x == 0) {  // the whole range lies inside one group
     const int64_t i = i0 + threadIdx.x;
-    if (i < i1) ps_add<K>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    if (i < i1) ps_add<K, PAIRED>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -431,8 +410,9 @@ int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const
 
 int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const PlaneTable& tbl, uint8_t* d_assign, float* d_resid) {
   const int nb = pick_blocks(ctx, (n + 3) >> 2, HS_TPB, 8);
-  if (tbl.K == 6) k_plane_assign<6><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);  // a cuboid room's walls
-  else k_plane_assign<0><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);
+  if (tbl.K == 6 && tbl.paired) k_plane_assign<6, true><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);  // a cuboid room's walls
+  else if (tbl.K == 6) k_plane_assign<6, false><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);
+  else k_plane_assign<0, false><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, n, tbl, d_assign, d_resid);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;
@@ -445,8 +425,14 @@ static int32_t launch_plane_sums_k(hs_ctx* ctx, const float* xyz, int64_t i0, in
   if constexpr (K <= 6) {
     if (ctx->modes[HS_MODE_PS_KERNEL] != 1 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
       const int dsm = K * 9 * HS_TPB * static_cast<int>(sizeof(double));
-      HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_f32<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
-      k_plane_sums_f32<K><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, reinterpret_cast<double*>(ctx->d_scratch), ctx->d_ticket, d_out);
+      double* part = reinterpret_cast<double*>(ctx->d_scratch);
+      if (K == 6 && tbl.paired) {
+        HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_f32<K, (K == 6)>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
+        k_plane_sums_f32<K, (K == 6)><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, part, ctx->d_ticket, d_out);
+      } else {
+        HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_f32<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
+        k_plane_sums_f32<K, false><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, part, ctx->d_ticket, d_out);
+      }
       ctx->launches++;
       HS_CUDA_TRY(ctx, cudaGetLastError());
       return HS_OK;

@@ -70,3 +70,13 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_haskell_ffi_binds_only_declared_symbols():
+    """haskell/HouseScanB200/FFI.hs is the reference-side binding a maintainer adds (no GHC here to compile it): every
+    `foreign import ccall` in it must name an entry point that the header declares and the library exports."""
+    src = open(os.path.join(ROOT, "haskell", "HouseScanB200", "FFI.hs")).read()
+    bound = re.findall(r'foreign import ccall (?:safe|unsafe) "(\w+)"', src)
+    assert len(bound) >= 30
+    declared = set(declared_symbols())
+    assert not [b for b in bound if b not in declared]

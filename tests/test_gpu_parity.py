@@ -528,3 +528,31 @@ def test_bfgs_on_cloud_recovers_cuboid(ctx):
     assert np.allclose(p[:6], true[:6], atol=2e-3)
     qa, qb = p[6:] / np.linalg.norm(p[6:]), true[6:] / np.linalg.norm(true[6:])
     assert min(np.linalg.norm(qa - qb), np.linalg.norm(qa + qb)) < 2e-3
+
+
+# ------------------------------------------------------------------ six planes that are NOT a cuboid's antiparallel pairs
+def test_six_unpaired_planes_take_the_generic_path(ctx, room_small):
+    """K == 6 picks the unrolled kernels; the shared-dot-product shortcut applies only when planes 2j / 2j+1 have exactly negated
+    normals.  Break the pairing (one normal perturbed by an ulp, one pair re-ordered) and check every K == 6 kernel again."""
+    xyz, params = room_small
+    xyz = xyz[:60_001]
+    cl = ctx.upload(xyz)
+    base = O.planes_from_cuboid(params)
+    ulp = base.copy()
+    ulp[1, 0] = np.nextafter(ulp[1, 0], np.float32(2.0))
+    swapped = base[[0, 2, 1, 3, 4, 5]]
+    frames, poses = synth.depth_stream(2, 160, 120)
+    intr = (synth.KINFU_INTR * 0.25).astype(np.float32)
+    for planes in (ulp, swapped):
+        a_g, r_g = ctx.plane_assign(cl, planes)
+        a_o, r_o = O.plane_assign(xyz, planes)
+        assert np.array_equal(a_g, a_o) and np.array_equal(r_g.view(np.uint32), r_o.view(np.uint32))
+        offs = np.array([0, 30_002, len(xyz)])
+        out_g = ctx.plane_sums(cl, offs, np.stack([planes] * 2), 6)
+        out_o = O.plane_sums(xyz, offs, np.stack([planes] * 2), 6)
+        assert np.array_equal(out_g[..., 0], out_o[..., 0]) and np.array_equal(out_g[..., 9], out_o[..., 9])
+        assert np.allclose(out_g, out_o, rtol=1e-6, atol=1e-6 * np.abs(out_o).max())
+        ne_g = ctx.backproject_reduce6x6(frames, 160, 120, planes, intr, poses)
+        ne_o = O.backproject_reduce6x6(frames, 160, 120, planes, intr, poses)
+        assert np.array_equal(ne_g[:, 28], ne_o[:, 28])
+        assert _rel(ne_g[:, :28], ne_o[:, :28], _ne_scale(ne_o)[:, :28]) < 1e-6
