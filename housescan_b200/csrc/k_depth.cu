@@ -12,8 +12,10 @@ namespace hsk {
 #define BP_TILE 2048  // pixels per block-tile: 8 consecutive pixels (one 16-byte load) per thread
 
 // x, y < 2^24 (checked by the API) and d is a uint16, so the quotients come from div_rn_small: bit-identical to `/`.
-#define HS_RCP10 __fdiv_rn(1.0f, 10.0f)
-#define HS_RCP20 __fdiv_rn(1.0f, 20.0f)
+// RN(1/10) and RN(1/20) as literals: 1/10 and 0.1 are the same real number, so the decimal literal rounds to the same Float
+// (an __fdiv_rn(1.0f, 10.0f) here is NOT folded by the compiler and costs a full division per use)
+#define HS_RCP10 0.1f
+#define HS_RCP20 0.05f
 __device__ __forceinline__ void scale_point(int x, int y, unsigned int d, float& X, float& Y, float& Z) {
   X = div_rn_small(static_cast<float>(x), 10.0f, HS_RCP10);
   Y = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
