@@ -81,3 +81,9 @@ foreign import ccall unsafe "hs_make_inward_facing"
   c_make_inward_facing :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Int32 -> IO Int32
 foreign import ccall safe "hs_load_room"
   c_load_room :: Ptr HsCtx -> CString -> Ptr (Ptr HsCloud) -> Ptr (Ptr HsCloud) -> Ptr CFloat -> Int32 -> Ptr Int32 -> IO Int32
+
+-- transform export compatibility (SURVEY.md 8f rank 2): replaces the external plyxform / pcl_transform_point_cloud step (Main.hs:2305-2325)
+foreign import ccall unsafe "hs_transform_from_text" c_transform_from_text :: CString -> Int64 -> Ptr CFloat -> IO Int32
+foreign import ccall safe "hs_cloud_from_ply"
+  c_cloud_from_ply :: Ptr HsCtx -> CString -> Ptr (Ptr HsCloud) -> Ptr (Ptr HsCloud) -> IO Int32
+foreign import ccall safe "hs_write_pcd" c_write_pcd :: Ptr HsCtx -> Ptr HsCloud -> Ptr Word8 -> CString -> IO Int32

@@ -71,3 +71,40 @@ def loadRoom(ctx: Context, directory: str):
     k = C.c_int32()
     ctx._chk(ctx.lib.hs_load_room(ctx.h, os.fsencode(directory), C.byref(cl), C.byref(col), ptr(planes), MAX_PLANES, C.byref(k)))
     return Cloud(ctx, cl), (Cloud(ctx, col) if col.value else None), planes[: k.value].copy()
+
+
+# ---- transform export compatibility (Main.hs:2271-2325) -------------------------------------------------------
+def cloudFromPly(ctx: Context, path: str):
+    """-> (Cloud, colours Cloud or None) from a PLY vertex cloud (ascii / binary_little_endian, float x y z [+ uchar red green blue])"""
+    cl, col = C.c_void_p(), C.c_void_p()
+    ctx._chk(ctx.lib.hs_cloud_from_ply(ctx.h, os.fsencode(path), C.byref(cl), C.byref(col)))
+    return Cloud(ctx, cl), (Cloud(ctx, col) if col.value else None)
+
+
+def transformFromText(text: bytes | str) -> np.ndarray:
+    """Inverse of roomProjectionToXfFormat / roomProjectionToString (Main.hs:2271-2302): the file holds the left-multiplicative
+    matrix; the result is roomProj (row vectors, right-multiplied, translation in row 3)."""
+    if isinstance(text, str):
+        text = text.encode()
+    m = np.empty(16, np.float32)
+    rc = L.load().hs_transform_from_text(text, len(text), ptr(m))
+    if rc != L.HS_OK:
+        raise HsError(rc, "not a 4x4 transform (16 numbers expected)")
+    return m.reshape(4, 4)
+
+
+def transformCloudFile(ctx: Context, src: str, matrix, dst: str):
+    """What `plyxform` / `pcl_transform_point_cloud -matrix` do with the reference's exports (Main.hs:2305-2325), at full resolution
+    on the GPU: read src (.ply or .pcd), apply roomProj, write dst (.ply or .pcd).  `matrix` is a 4x4 roomProj array, the text of an
+    .xf file / -matrix string, or the path of an .xf file.  Returns the number of points."""
+    if isinstance(matrix, (str, bytes)) and os.path.exists(matrix):
+        with open(matrix, "rb") as fh:
+            matrix = fh.read()
+    m = transformFromText(matrix) if isinstance(matrix, (str, bytes)) else np.asarray(matrix, np.float32).reshape(4, 4)
+    cl, col = (cloudFromPly if src.lower().endswith(".ply") else cloudFromFile)(ctx, src)
+    out = ctx.transform(cl, m)
+    rgb = None
+    if col is not None:  # colours are u8 / 255 in Float: * 255 and rounding gives the bytes back exactly
+        rgb = np.rint(col.download() * np.float32(255.0)).astype(np.uint8)
+    (ctx.write_ply if dst.lower().endswith(".ply") else ctx.write_pcd)(out, dst, rgb)
+    return len(out)

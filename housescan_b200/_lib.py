@@ -80,6 +80,9 @@ SIGNATURES = {
     "hs_pcd_info": (i32, [C.c_char_p, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
     "hs_make_inward_facing": (i32, [vp, vp, vp, i32]),
     "hs_load_room": (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(vp), vp, i32, C.POINTER(i32)]),
+    "hs_transform_from_text": (i32, [C.c_char_p, i64, vp]),
+    "hs_cloud_from_ply": (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(vp)]),
+    "hs_write_pcd": (i32, [vp, vp, vp, C.c_char_p]),
     "hs_version": (C.c_char_p, []),
 }
 

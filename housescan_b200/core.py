@@ -211,6 +211,12 @@ class Context:
             raise ValueError("rgb must have one row per point")
         self._chk(self.lib.hs_write_ply(self.h, cloud.h, ptr(rgb_a), path.encode()))
 
+    def write_pcd(self, cloud: Cloud, path: str, rgb=None):
+        rgb_a = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3) if rgb is not None else None
+        if rgb_a is not None and rgb_a.shape[0] != len(cloud):
+            raise ValueError("rgb must have one row per point")
+        self._chk(self.lib.hs_write_pcd(self.h, cloud.h, ptr(rgb_a), path.encode()))
+
     # -- (4) connected components
     def cc_label(self, src, dst, n_nodes: int):
         src = np.ascontiguousarray(src, dtype=np.uint32)

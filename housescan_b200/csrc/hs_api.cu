@@ -673,7 +673,8 @@ struct PcdStaged {
   std::vector<uint32_t> rec;    // ascii records
   const uint8_t* raw = nullptr;
   size_t raw_bytes = 0;
-  int64_t off[4] = {0, 0, 0, -1}, stride[4] = {0, 0, 0, 0};
+  int64_t off[6] = {0, 0, 0, -1, -1, -1}, stride[6] = {0, 0, 0, 0, 0, 0};
+  int rgb_bytes = 0;  // colours as three separate bytes (PLY) instead of one packed word (PCD)
   bool has_rgb = false;
 };
 static bool pcd_stage(const char* path, PcdStaged* st, std::string* err) {
@@ -726,15 +727,8 @@ int32_t hs_pcd_info(const char* path, int64_t* n_points, int32_t* has_rgb, int32
   return HS_OK;
 }
 
-int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out) {
-  if (!ctx) return HS_EINVAL;
-  if (!path || !cloud_out) { ctx->err = "hs_cloud_from_pcd: bad arguments"; return HS_EINVAL; }
-  *cloud_out = nullptr;
-  if (colors_out) *colors_out = nullptr;
-  PcdStaged st;
-  std::string err;
-  if (!pcd_stage(path, &st, &err)) { ctx->err = err; return HS_EIO; }
-  const int64_t n = st.h.points;
+// staged file -> device clouds: the DATA section goes up as it is and is unpacked on the GPU
+static int32_t staged_to_device(hs_ctx* ctx, const PcdStaged& st, int64_t n, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out) {
   if (n == 0) { ctx->err = std::string("File ") + path + " contains no points!"; return HS_EIO; }  // Main.hs:1344
   hs_cloud *cl = nullptr, *col = nullptr;
   int32_t rc = hs_cloud_alloc(ctx, n, &cl);
@@ -746,7 +740,7 @@ int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, h
     cudaError_t e = cudaMalloc(&d_raw, st.raw_bytes + 16);
     if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); rc = HS_ENOMEM; }
     if (rc == HS_OK) rc = copy_h2d(ctx, d_raw, st.raw, st.raw_bytes);
-    if (rc == HS_OK) rc = launch_pcd_unpack(ctx, d_raw, n, st.off, st.stride, cl->d, want_rgb ? col->d : nullptr);
+    if (rc == HS_OK) rc = launch_pcd_unpack(ctx, d_raw, n, st.off, st.stride, st.rgb_bytes, cl->d, want_rgb ? col->d : nullptr);
     cudaStreamSynchronize(ctx->stream);  // the staged host buffers die with this call
     if (d_raw) cudaFree(d_raw);
   }
@@ -754,6 +748,61 @@ int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, h
   *cloud_out = cl;
   if (colors_out) *colors_out = col;
   return HS_OK;
+}
+
+int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out) {
+  if (!ctx) return HS_EINVAL;
+  if (!path || !cloud_out) { ctx->err = "hs_cloud_from_pcd: bad arguments"; return HS_EINVAL; }
+  *cloud_out = nullptr;
+  if (colors_out) *colors_out = nullptr;
+  PcdStaged st;
+  std::string err;
+  if (!pcd_stage(path, &st, &err)) { ctx->err = err; return HS_EIO; }
+  return staged_to_device(ctx, st, st.h.points, path, cloud_out, colors_out);
+}
+
+int32_t hs_cloud_from_ply(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out) {
+  if (!ctx) return HS_EINVAL;
+  if (!path || !cloud_out) { ctx->err = "hs_cloud_from_ply: bad arguments"; return HS_EINVAL; }
+  *cloud_out = nullptr;
+  if (colors_out) *colors_out = nullptr;
+  PcdStaged st;
+  hs::PlyHeader h;
+  std::string err;
+  if (!hs::read_file(path, &st.file, &err) || !hs::ply_parse_header(st.file.data(), st.file.size(), &h, &err)) { ctx->err = err; return HS_EIO; }
+  const int f[6] = {h.find("x"), h.find("y"), h.find("z"), h.find("red"), h.find("green"), h.find("blue")};
+  for (int c = 0; c < 3; ++c)
+    if (f[c] < 0 || h.sizes[f[c]] != 4 || (h.types[f[c]] != "float" && h.types[f[c]] != "float32")) { ctx->err = "PLY: x y z must be float properties"; return HS_EIO; }
+  st.has_rgb = f[3] >= 0 && f[4] >= 0 && f[5] >= 0 && h.sizes[f[3]] == 1 && h.sizes[f[4]] == 1 && h.sizes[f[5]] == 1;
+  if (h.ascii) {
+    if (!hs::ply_ascii_records(st.file.data(), st.file.size(), h, st.has_rgb, &st.rec, &err)) { ctx->err = err; return HS_EIO; }
+    const int W = st.has_rgb ? 4 : 3;
+    st.raw = reinterpret_cast<const uint8_t*>(st.rec.data());
+    st.raw_bytes = st.rec.size() * 4;
+    for (int c = 0; c < 4; ++c) { st.off[c] = 4 * c; st.stride[c] = 4 * W; }
+  } else {
+    st.raw = reinterpret_cast<const uint8_t*>(st.file.data()) + h.data_offset;
+    st.raw_bytes = static_cast<size_t>(h.n) * h.step;
+    if (h.data_offset + st.raw_bytes > st.file.size()) { ctx->err = "PLY: binary data ends early"; return HS_EIO; }
+    for (int c = 0; c < 6; ++c) { st.off[c] = f[c] >= 0 ? h.offsets[f[c]] : -1; st.stride[c] = h.step; }
+    st.rgb_bytes = 1;
+  }
+  return staged_to_device(ctx, st, h.n, path, cloud_out, colors_out);
+}
+
+int32_t hs_write_pcd(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb, const char* path) {
+  if (!ctx) return HS_EINVAL;
+  if (!cloud || !path) { ctx->err = "hs_write_pcd: bad arguments"; return HS_EINVAL; }
+  std::vector<float> host(static_cast<size_t>(cloud->n) * 3);
+  if (int32_t rc = hs_cloud_download(ctx, cloud, host.data())) return rc;
+  std::string err;
+  if (!hs::write_pcd(path, host.data(), rgb, cloud->n, &err)) { ctx->err = err; return HS_EIO; }
+  return HS_OK;
+}
+
+int32_t hs_transform_from_text(const char* text, int64_t len, float m_rowmajor[16]) {
+  if (!text || len < 0 || !m_rowmajor) return HS_EINVAL;
+  return hs::parse_transform_text(text, static_cast<size_t>(len), m_rowmajor) ? HS_OK : HS_EIO;
 }
 
 // the plane hulls are a few dozen points each: read on the host, mean as the reference's Float fold (planeMean, Main.hs:1608)

@@ -114,7 +114,7 @@ size_t reduce6x6_work_bytes(const hs_ctx* ctx, int64_t nframes, int32_t w, int32
 int32_t launch_reduce6x6(hs_ctx* ctx, const uint16_t* d_frames, int64_t nframes, int32_t w, int32_t h, const float* intr,
                          const float* d_poses, const PlaneTable& tbl, double* d_out, char* d_work);
 
-int32_t launch_pcd_unpack(hs_ctx* ctx, const uint8_t* d_raw, int64_t n, const int64_t off[4], const int64_t stride[4], float* d_xyz, float* d_rgbf);
+int32_t launch_pcd_unpack(hs_ctx* ctx, const uint8_t* d_raw, int64_t n, const int64_t off[6], const int64_t stride[6], int rgb_bytes, float* d_xyz, float* d_rgbf);
 
 int32_t launch_cc(hs_ctx* ctx, const uint32_t* d_src, const uint32_t* d_dst, int64_t E, uint32_t N, uint32_t* d_label);
 

@@ -108,51 +108,61 @@ k_bp_count(const uint16_t* __restrict__ depth, int64_t npx, uint8_t* __restrict_
   if (threadIdx.x == 0) *n_valid = total;
 }
 
-// pass 2: order-preserving scatter of the scaled points.  The tile's points are compacted in shared memory first, shifted so
-// that a shared-memory float index and its global float index agree modulo 4; the run then leaves as 16-byte stores
-// (fully coalesced STG.128) with at most three scalar floats at either end, instead of 12-byte scattered stores.
+// pass 2: order-preserving scatter of the scaled points.
+//   * a warp owns 256 consecutive pixels of the tile.  Each lane loads 16 bytes (8 pixels) and parks them in the warp's slice
+//     of shared memory; the warp then walks its pixels in 8 steps of 32 CONSECUTIVE pixels (lane l takes pixel 32 e + l), so
+//     the position of a valid pixel is a ballot + popcount and neighbouring lanes write neighbouring points of the staging
+//     buffer (stride 3 words: conflict-free; 8 pixels per lane would put the lanes 24 words apart, an 8-way bank conflict);
+//   * the tile's points are staged shifted so that a shared-memory float index and its global float index agree modulo 4, and
+//     the run leaves as 16-byte stores (coalesced STG.128) with at most three scalar floats at either end.
 __global__ void __launch_bounds__(HS_TPB)
 k_bp_scatter(const uint16_t* __restrict__ depth, int64_t npx, int w, const unsigned int* __restrict__ tile_off, float* __restrict__ xyz) {
   __shared__ unsigned int wsum[HS_TPB / 32];
+  __shared__ __align__(16) uint16_t sraw[BP_TILE];
   __shared__ __align__(16) float stage[BP_TILE * 3 + 4];
   const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
   const bool aligned = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int lt = (1u << lane) - 1u;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t i0 = t * BP_TILE + 8 * threadIdx.x;
-    unsigned int wv[4];
     if (aligned && i0 + 8 <= npx) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(depth + i0));
-      wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
+      reinterpret_cast<uint4*>(sraw)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(depth + i0));
     } else {
-      unsigned int d[8];
-      load_px8(depth, npx, i0, aligned, d);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) wv[q] = d[2 * q] | (d[2 * q + 1] << 16);
+      for (int e = 0; e < 8; ++e) sraw[8 * threadIdx.x + e] = (i0 + e < npx) ? depth[i0 + e] : static_cast<uint16_t>(0);
     }
-    const unsigned int c = __popc(nz16x2(wv[0]) | (nz16x2(wv[1]) >> 1) | (nz16x2(wv[2]) >> 2) | (nz16x2(wv[3]) >> 3));
     const int64_t dst0 = 3 * static_cast<int64_t>(tile_off[t]);  // first float of the tile's run in xyz
     const int a = static_cast<int>(dst0 & 3);
-    unsigned int pos = block_exclusive_prefix(c, wsum);  // position inside the tile
-    unsigned int total = 0;
-#pragma unroll
-    for (int q = 0; q < HS_TPB / 32; ++q) total += wsum[q];
-    int y, x;  // row / column of this thread's first pixel; a 64-bit division costs more than the rest of the iteration
-    if (npx <= 0xffffffffll) { const unsigned int q = static_cast<unsigned int>(i0) / static_cast<unsigned int>(w); y = static_cast<int>(q); x = static_cast<int>(static_cast<unsigned int>(i0) - q * static_cast<unsigned int>(w)); }
-    else { y = static_cast<int>(i0 / w); x = static_cast<int>(i0 - static_cast<int64_t>(y) * w); }
-    float xf = static_cast<float>(x);
-    float Y = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
-    float* sp = stage + a + 3 * pos;
+    __syncwarp();
+    unsigned int d[8], bal[8], cw = 0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float df = (e & 1) ? u16_hi_f(wv[e >> 1]) : u16_lo_f(wv[e >> 1]);
-      if (df != 0.0f) {
-        sp[0] = div_rn_small(xf, 10.0f, HS_RCP10);
-        sp[1] = Y;
-        sp[2] = __fsub_rn(div_rn_small(df, 20.0f, HS_RCP20), 30.0f);
-        sp += 3;
+      d[e] = sraw[256 * warp + 32 * e + lane];
+      bal[e] = __ballot_sync(0xffffffffu, d[e] != 0);
+      cw += __popc(bal[e]);
+    }
+    if (lane == 0) wsum[warp] = cw;
+    __syncthreads();
+    unsigned int run = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < HS_TPB / 32; ++q) { run += (q < warp) ? wsum[q] : 0u; total += wsum[q]; }
+    // row / column of this lane's first pixel (a 64-bit division costs more than the rest of the iteration)
+    const int64_t p0 = t * BP_TILE + 256 * warp + lane;
+    int y, x;
+    if (npx <= 0xffffffffll) { const unsigned int q = static_cast<unsigned int>(p0) / static_cast<unsigned int>(w); y = static_cast<int>(q); x = static_cast<int>(static_cast<unsigned int>(p0) - q * static_cast<unsigned int>(w)); }
+    else { y = static_cast<int>(p0 / w); x = static_cast<int>(p0 - static_cast<int64_t>(y) * w); }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (d[e] != 0) {
+        float* sp = stage + a + 3 * (run + __popc(bal[e] & lt));
+        sp[0] = div_rn_small(static_cast<float>(x), 10.0f, HS_RCP10);
+        sp[1] = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
+        sp[2] = __fsub_rn(div_rn_small(static_cast<float>(d[e]), 20.0f, HS_RCP20), 30.0f);
       }
-      xf = __fadd_rn(xf, 1.0f);
-      if (++x == w) { x = 0; xf = 0.0f; ++y; Y = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10); }
+      run += __popc(bal[e]);
+      x += 32;
+      while (x >= w) { x -= w; ++y; }
     }
     __syncthreads();
     const int lo = a, hi = a + 3 * static_cast<int>(total);  // the run in shared-memory float indices; global index = dst0 - a + s

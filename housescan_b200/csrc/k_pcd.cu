@@ -9,9 +9,10 @@
 namespace hsk {
 
 struct PcdLayout {
-  int64_t off[4];     // x, y, z, rgb (rgb < 0: none)
-  int64_t stride[4];
-  int aligned;        // every address is a multiple of 4
+  int64_t off[6];     // x, y, z, then either the packed rgb word (rgb_bytes == 0) or the red, green, blue bytes (PLY)
+  int64_t stride[6];
+  int aligned;        // every 4-byte address is a multiple of 4
+  int rgb_bytes;      // 1: colours are three separate uint8 properties
 };
 
 __device__ __forceinline__ uint32_t load_u32(const uint8_t* p, bool aligned) {
@@ -30,10 +31,16 @@ k_pcd_unpack(const uint8_t* __restrict__ raw, int64_t n, const PcdLayout L, floa
       sx[3 * threadIdx.x + 1] = __uint_as_float(load_u32(raw + L.off[1] + i * L.stride[1], al));
       sx[3 * threadIdx.x + 2] = __uint_as_float(load_u32(raw + L.off[2] + i * L.stride[2], al));
       if (rgbf) {
-        const uint32_t c = load_u32(raw + L.off[3] + i * L.stride[3], al);  // 0x00RRGGBB
-        sc[3 * threadIdx.x + 0] = __fdiv_rn(static_cast<float>((c >> 16) & 255u), 255.0f);
-        sc[3 * threadIdx.x + 1] = __fdiv_rn(static_cast<float>((c >> 8) & 255u), 255.0f);
-        sc[3 * threadIdx.x + 2] = __fdiv_rn(static_cast<float>(c & 255u), 255.0f);
+        uint32_t r, g, b;
+        if (L.rgb_bytes) {
+          r = raw[L.off[3] + i * L.stride[3]]; g = raw[L.off[4] + i * L.stride[4]]; b = raw[L.off[5] + i * L.stride[5]];
+        } else {
+          const uint32_t c = load_u32(raw + L.off[3] + i * L.stride[3], al);  // 0x00RRGGBB
+          r = (c >> 16) & 255u; g = (c >> 8) & 255u; b = c & 255u;
+        }
+        sc[3 * threadIdx.x + 0] = __fdiv_rn(static_cast<float>(r), 255.0f);
+        sc[3 * threadIdx.x + 1] = __fdiv_rn(static_cast<float>(g), 255.0f);
+        sc[3 * threadIdx.x + 2] = __fdiv_rn(static_cast<float>(b), 255.0f);
       }
     }
     __syncthreads();
@@ -50,15 +57,16 @@ k_pcd_unpack(const uint8_t* __restrict__ raw, int64_t n, const PcdLayout L, floa
 
 using namespace hsk;
 
-int32_t launch_pcd_unpack(hs_ctx* ctx, const uint8_t* d_raw, int64_t n, const int64_t off[4], const int64_t stride[4], float* d_xyz, float* d_rgbf) {
+int32_t launch_pcd_unpack(hs_ctx* ctx, const uint8_t* d_raw, int64_t n, const int64_t off[6], const int64_t stride[6], int rgb_bytes, float* d_xyz, float* d_rgbf) {
   if (n == 0) return HS_OK;
   PcdLayout L;
   bool al = (reinterpret_cast<uintptr_t>(d_raw) & 3) == 0;
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 6; ++c) {
     L.off[c] = off[c]; L.stride[c] = stride[c];
-    if (c < 3 || d_rgbf) al = al && (off[c] % 4 == 0) && (stride[c] % 4 == 0);
+    if (c < 3 || (c == 3 && d_rgbf && !rgb_bytes)) al = al && (off[c] % 4 == 0) && (stride[c] % 4 == 0);
   }
   L.aligned = al ? 1 : 0;
+  L.rgb_bytes = rgb_bytes;
   int64_t nb = (n + HS_TPB - 1) / HS_TPB;
   const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
   if (nb > cap) nb = cap;

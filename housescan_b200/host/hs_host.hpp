@@ -74,4 +74,18 @@ bool pcd_ascii_records(const char* buf, size_t len, const PcdHeader& h, std::vec
 bool lzf_decompress(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len);
 bool read_file(const char* path, std::vector<char>* out, std::string* err);
 
+bool parse_transform_text(const char* text, size_t len, float m_rowmajor[16]);  // .xf or comma-separated, transposed back to roomProj
+struct PlyHeader {
+  bool ascii = false;
+  int64_t n = -1;
+  std::vector<std::string> names, types;
+  std::vector<int> sizes, offsets;
+  int step = 0;            // bytes per vertex record (binary)
+  size_t data_offset = 0;  // first byte after end_header
+  int find(const std::string& name) const;
+};
+bool ply_parse_header(const char* buf, size_t len, PlyHeader* h, std::string* err);
+bool ply_ascii_records(const char* buf, size_t len, const PlyHeader& h, bool want_rgb, std::vector<uint32_t>* rec, std::string* err);
+bool write_pcd(const char* path, const float* xyz, const uint8_t* rgb, int64_t n, std::string* err);
+
 }  // namespace hs

@@ -4,6 +4,7 @@
 //   makeInwardFacing  (Main.hs:1746-1751)
 // The reference reads PCD through the `pcd-loader` package and parses numbers with attoparsec; neither is mounted, so this file
 // follows the published PCD v0.7 layout and attoparsec's documented `double` grammar (see parse_double below).
+#include <algorithm>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -223,6 +224,142 @@ bool lzf_decompress(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_l
     }
   }
   return op == out_len;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Transform files written by the reference: roomProjectionToXfFormat (Main.hs:2287-2302, four lines of
+// four numbers) and roomProjectionToString (Main.hs:2271-2284, sixteen numbers separated by commas).  Both hold the
+// LEFT-multiplicative matrix, i.e. the transpose of roomProj; the result here is roomProj again (row vectors, p' = p .* M).
+// ---------------------------------------------------------------------------------------------------------------------------
+bool parse_transform_text(const char* text, size_t len, float m_rowmajor[16]) {
+  float L[16];
+  size_t i = 0;
+  for (int k = 0; k < 16; ++k) {
+    while (i < len && (text[i] == ' ' || text[i] == ',' || (text[i] >= 9 && text[i] <= 13))) ++i;
+    if (i >= len) return false;
+    const std::string rest(text + i, std::min<size_t>(len - i, 64));
+    char* end = nullptr;
+    const float v = std::strtof(rest.c_str(), &end);  // Haskell `show` of a Float: decimal or d.ddde-n, both strtof syntax
+    if (end == rest.c_str()) return false;
+    L[k] = v;
+    i += static_cast<size_t>(end - rest.c_str());
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) m_rowmajor[4 * r + c] = L[4 * c + r];
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// PLY (the format of the full-resolution KinFu meshes / clouds the external `plyxform` tool transforms, Main.hs:2287-2325)
+// ---------------------------------------------------------------------------------------------------------------------------
+static int ply_type_size(const std::string& t) {
+  if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+  if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+  if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+  if (t == "double" || t == "float64") return 8;
+  return 0;
+}
+int PlyHeader::find(const std::string& name) const {
+  for (size_t f = 0; f < names.size(); ++f)
+    if (names[f] == name) return static_cast<int>(f);
+  return -1;
+}
+bool ply_parse_header(const char* buf, size_t len, PlyHeader* h, std::string* err) {
+  *h = PlyHeader();
+  size_t i = 0;
+  int element = -1;  // 0: inside the vertex element, 1: a later element
+  bool first = true, done = false;
+  while (i < len && !done) {
+    size_t e = i;
+    while (e < len && buf[e] != '\n') ++e;
+    std::string line(buf + i, e - i);
+    i = e < len ? e + 1 : e;
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (first) { if (line != "ply") { *err = "PLY: missing magic"; return false; } first = false; continue; }
+    std::istringstream ss(line);
+    std::string key, a, b;
+    ss >> key;
+    if (key == "format") {
+      ss >> a;
+      if (a == "ascii") h->ascii = true;
+      else if (a == "binary_little_endian") h->ascii = false;
+      else { *err = "PLY: unsupported format '" + a + "'"; return false; }
+    } else if (key == "element") {
+      ss >> a >> b;
+      if (element < 0) {
+        if (a != "vertex") { *err = "PLY: the first element must be `vertex`"; return false; }
+        h->n = std::atoll(b.c_str());
+        element = 0;
+      } else element = 1;
+    } else if (key == "property" && element == 0) {
+      ss >> a;
+      if (a == "list") { *err = "PLY: list property in the vertex element"; return false; }
+      ss >> b;
+      const int sz = ply_type_size(a);
+      if (!sz) { *err = "PLY: unknown property type '" + a + "'"; return false; }
+      h->names.push_back(b); h->types.push_back(a); h->sizes.push_back(sz); h->offsets.push_back(h->step);
+      h->step += sz;
+    } else if (key == "end_header") done = true;
+  }
+  if (!done || element < 0 || h->n < 0) { *err = "PLY: incomplete header"; return false; }
+  h->data_offset = i;
+  return true;
+}
+// vertex records of an ascii PLY as packed 4-byte records [x y z (0x00RRGGBB)]
+bool ply_ascii_records(const char* buf, size_t len, const PlyHeader& h, bool want_rgb, std::vector<uint32_t>* rec, std::string* err) {
+  const int fx = h.find("x"), fy = h.find("y"), fz = h.find("z"), fr = h.find("red"), fg = h.find("green"), fb = h.find("blue");
+  const int W = want_rgb ? 4 : 3;
+  rec->assign(static_cast<size_t>(h.n) * W, 0u);
+  const char* p = buf + h.data_offset;
+  const char* end = buf + len;
+  const int nprop = static_cast<int>(h.names.size());
+  for (int64_t i = 0; i < h.n; ++i) {
+    uint32_t rgb = 0;
+    for (int c = 0; c < nprop; ++c) {
+      while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+      if (p >= end) { *err = "PLY: ascii data ends early"; return false; }
+      const char* t0 = p;
+      while (p < end && !(*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+      const std::string tok(t0, p - t0);
+      if (c == fx || c == fy || c == fz) {
+        const float v = std::strtof(tok.c_str(), nullptr);
+        std::memcpy(&(*rec)[static_cast<size_t>(i) * W + (c == fx ? 0 : (c == fy ? 1 : 2))], &v, 4);
+      } else if (want_rgb && (c == fr || c == fg || c == fb)) {
+        const uint32_t v = static_cast<uint32_t>(std::strtoul(tok.c_str(), nullptr, 10)) & 255u;
+        rgb |= v << (c == fr ? 16 : (c == fg ? 8 : 0));
+      }
+    }
+    if (want_rgb) (*rec)[static_cast<size_t>(i) * W + 3] = rgb;
+  }
+  return true;
+}
+
+// binary PCD v0.7 with FIELDS x y z [rgb] (what pcl_transform_point_cloud would have written, Main.hs:2305-2313)
+bool write_pcd(const char* path, const float* xyz, const uint8_t* rgb, int64_t n, std::string* err) {
+  FILE* fp = std::fopen(path, "wb");
+  if (!fp) { *err = std::string("cannot open ") + path; return false; }
+  std::fprintf(fp, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z%s\nSIZE 4 4 4%s\nTYPE F F F%s\nCOUNT 1 1 1%s\n"
+                   "WIDTH %lld\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %lld\nDATA binary\n",
+               rgb ? " rgb" : "", rgb ? " 4" : "", rgb ? " F" : "", rgb ? " 1" : "", static_cast<long long>(n), static_cast<long long>(n));
+  bool ok = true;
+  if (!rgb) ok = std::fwrite(xyz, 12, static_cast<size_t>(n), fp) == static_cast<size_t>(n);
+  else {
+    const size_t chunk = 1 << 16;
+    std::vector<uint8_t> buf(chunk * 16);
+    for (int64_t i0 = 0; i0 < n && ok; i0 += chunk) {
+      const size_t m = static_cast<size_t>(std::min<int64_t>(chunk, n - i0));
+      for (size_t i = 0; i < m; ++i) {
+        std::memcpy(&buf[i * 16], xyz + 3 * (i0 + i), 12);
+        const uint8_t* c = rgb + 3 * (i0 + i);
+        const uint32_t packed = (static_cast<uint32_t>(c[0]) << 16) | (static_cast<uint32_t>(c[1]) << 8) | c[2];
+        std::memcpy(&buf[i * 16 + 12], &packed, 4);
+      }
+      ok = std::fwrite(buf.data(), 16, m, fp) == m;
+    }
+  }
+  if (std::fclose(fp) != 0) ok = false;
+  if (!ok) *err = std::string("short write to ") + path;
+  return ok;
 }
 
 bool read_file(const char* path, std::vector<char>* out, std::string* err) {

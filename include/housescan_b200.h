@@ -145,6 +145,18 @@ HS_API int32_t hs_plane_eqs_from_file(const char* path, float* planes_out, int32
  * else NULL (`OneColor`).  A file without points is HS_EIO with the reference's message. */
 HS_API int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out);
 HS_API int32_t hs_pcd_info(const char* path, int64_t* n_points, int32_t* has_rgb, int32_t* data_kind /* 0 ascii 1 binary 2 compressed */);
+/* ---- transform export compatibility: the step after the hot path --------------------------------
+ * The reference writes .xf files / -matrix strings (Main.hs:2271-2325) for the external plyxform and pcl_transform_point_cloud
+ * tools to transform the full-resolution .ply / .pcd of a room.  These entry points close that loop on the GPU: read the file,
+ * hs_transform with the parsed matrix, hs_write_ply / hs_write_pcd. */
+/* inverse of hs_proj_to_xf / hs_proj_to_string: 16 numbers (blank- or comma-separated) holding the LEFT-multiplicative matrix
+ * (Main.hs:2278-2284); the result is roomProj again (row-major, right-multiplied) */
+HS_API int32_t hs_transform_from_text(const char* text, int64_t len, float m_rowmajor_out[16]);
+/* PLY vertex clouds: format ascii or binary_little_endian, `element vertex` first, float x y z [+ uchar red green blue] */
+HS_API int32_t hs_cloud_from_ply(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out);
+/* binary PCD v0.7, FIELDS x y z [rgb] (what pcl_transform_point_cloud ... -matrix would have written, Main.hs:2305-2313) */
+HS_API int32_t hs_write_pcd(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb_or_null, const char* path);
+
 /* makeInwardFacing (Main.hs:1746-1751): flip (n, d) of every plane unless (roomCenter - planeMean) . n > 0 */
 HS_API int32_t hs_make_inward_facing(const float room_center[3], const float* plane_means /* K x 3 */, float* planes_inout /* K x 4 */, int32_t K);
 /* loadRoom (Main.hs:1740-1765): dir/cloud_downsampled.pcd, dir/planes.txt, dir/cloud_plane_hull<i>.pcd; planes inward facing */

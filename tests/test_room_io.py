@@ -164,3 +164,76 @@ def test_load_room_matches_oracle(ctx, tmp_path):
     os.remove(os.path.join(d, "cloud_plane_hull3.pcd"))
     with pytest.raises(hb.HsError):
         RoomIO.loadRoom(ctx, d)
+
+
+# ------------------------------------------------------------------ transform export compatibility
+def test_transform_text_round_trips_the_reference_formats(built_lib):
+    """roomProjectionToXfFormat / roomProjectionToString (Main.hs:2271-2302) write the transposed matrix with `show`; reading it
+    back gives roomProj bit for bit (Haskell's show prints the shortest digits that identify the Float)."""
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        m = np.eye(4, dtype=np.float32)
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        m[:3, :3] = q.astype(np.float32)
+        m[3, :3] = (rng.normal(size=3) * 7).astype(np.float32)
+        for text in (hb.proj_to_xf(m), hb.proj_to_string(m)):
+            back = RoomIO.transformFromText(text)
+            assert np.array_equal(back.view(np.uint32), m.view(np.uint32)), text
+    # the .xf layout is the LEFT-multiplicative matrix: translation in the last column
+    xf = "1.0 0.0 0.0 5.0\n0.0 1.0 0.0 6.0\n0.0 0.0 1.0 7.0\n0.0 0.0 0.0 1.0\n"
+    assert np.array_equal(RoomIO.transformFromText(xf)[3], [5, 6, 7, 1])
+    with pytest.raises(hb.HsError):
+        RoomIO.transformFromText("1 2 3")
+
+
+def _write_ply_ascii(path, xyz, rgb=None, extra=False):
+    with open(path, "w") as fh:
+        fh.write("ply\nformat ascii 1.0\ncomment test\nelement vertex %d\n" % len(xyz))
+        if extra:
+            fh.write("property float confidence\n")
+        fh.write("property float x\nproperty float y\nproperty float z\n")
+        if rgb is not None:
+            fh.write("property uchar red\nproperty uchar green\nproperty uchar blue\n")
+        fh.write("element face 0\nproperty list uchar int vertex_indices\nend_header\n")
+        for i in range(len(xyz)):
+            row = (["0.5"] if extra else []) + [repr(float(v)) for v in xyz[i]] + ([str(int(v)) for v in rgb[i]] if rgb is not None else [])
+            fh.write(" ".join(row) + "\n")
+
+
+@pytest.mark.gpu
+def test_ply_reader_and_file_transformer(ctx, tmp_path):
+    rng = np.random.default_rng(41)
+    n = 20_003
+    xyz = (rng.normal(size=(n, 3)) * 3).astype(np.float32)
+    rgb = rng.integers(0, 256, (n, 3)).astype(np.uint8)
+    m = np.eye(4, dtype=np.float32)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    m[:3, :3] = q.astype(np.float32)
+    m[3, :3] = [1.5, -2.0, 0.25]
+    exp = O.project_cloud(xyz, m)  # projectRoom's cloud part (Main.hs:1716-1730)
+    src_bin, src_asc = str(tmp_path / "in.ply"), str(tmp_path / "in_ascii.ply")
+    ctx.write_ply(ctx.upload(xyz), src_bin, rgb)  # binary_little_endian with uchar colours
+    _write_ply_ascii(src_asc, xyz, rgb, extra=True)
+    for src in (src_bin, src_asc):
+        cl, col = RoomIO.cloudFromPly(ctx, src)
+        assert np.array_equal(cl.download().view(np.uint32), xyz.view(np.uint32))
+        assert np.array_equal(col.download(), rgb.astype(np.float32) / np.float32(255))
+    cl, col = RoomIO.cloudFromPly(ctx, str(tmp_path / "in.ply"))
+    xf = tmp_path / "room.xf"
+    xf.write_text(hb.proj_to_xf(m))
+    want = ctx.transform(ctx.upload(xyz), m).download()
+    assert np.array_equal(want.view(np.uint32), exp.view(np.uint32))
+    for dst in ("out.ply", "out.pcd"):
+        npts = RoomIO.transformCloudFile(ctx, src_bin, str(xf), str(tmp_path / dst))
+        assert npts == n
+        back, bcol = (RoomIO.cloudFromPly if dst.endswith("ply") else RoomIO.cloudFromFile)(ctx, str(tmp_path / dst))
+        assert np.array_equal(back.download().view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(np.rint(bcol.download() * 255).astype(np.uint8), rgb)
+    # the -matrix string form and a colourless PCD source
+    p = str(tmp_path / "plain.pcd")
+    write_pcd(p, xyz, kind="binary")
+    RoomIO.transformCloudFile(ctx, p, hb.proj_to_string(m), str(tmp_path / "plain_out.pcd"))
+    back, bcol = RoomIO.cloudFromFile(ctx, str(tmp_path / "plain_out.pcd"))
+    assert bcol is None and np.array_equal(back.download().view(np.uint32), want.view(np.uint32))
+    xo, _ = O.pcd_load(str(tmp_path / "plain_out.pcd"))  # the files we write are readable by the independent loader
+    assert np.array_equal(xo.view(np.uint32), want.view(np.uint32))
