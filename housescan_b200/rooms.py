@@ -28,6 +28,40 @@ def local_room_offsets(room_offsets, lo: int, hi: int) -> np.ndarray:
     return (np.clip(ro, lo, hi) - lo).astype(np.int64)
 
 
+def shard_frames(nframes: int, rank: int, world: int):
+    """Frame range [lo, hi) of `rank` for a replayed depth stream (BASELINE configs[4]): frames are independent, so the stream
+    is cut into contiguous, near-equal ranges (the first nframes % world ranks take one frame more)."""
+    base, extra = divmod(nframes, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def depth_stream_records_sharded(reduce_fn, frames, poses, rank: int, world: int, group=None):
+    """Per-frame 6x6 records of a depth stream sharded by frame range.  `reduce_fn(frames, poses)` evaluates
+    a block of frames (on the GPU: Context.backproject_reduce6x6) and returns [n, HS_NE] doubles.  No collective on the data path:
+    every rank reduces its own frames; the 232-byte records are gathered in frame order at the end (all_gather of ragged blocks).
+    Returns the full [nframes, HS_NE] array on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    nframes = len(frames)
+    lo, hi = shard_frames(nframes, rank, world)
+    local = np.asarray(reduce_fn(frames[lo:hi], None if poses is None else poses[lo:hi]), np.float64).reshape(hi - lo, -1)
+    if world == 1:
+        return local
+    width = local.shape[1]
+    per = -(-nframes // world)  # pad every block to the largest range so the gather is one fixed-size collective
+    buf = torch.zeros(per, width, dtype=torch.float64)
+    buf[: hi - lo] = torch.from_numpy(local)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    out = np.empty((nframes, width), np.float64)
+    for r in range(world):
+        a, b = shard_frames(nframes, r, world)
+        out[a:b] = parts[r][: b - a].numpy()
+    return out
+
+
 X, Y, Z = 0, 1, 2
 SAME = ("Same",)
 

@@ -79,3 +79,32 @@ def test_two_rank_vertex_range_cc_equals_unsharded(tmp_path, built_lib, oracle_l
     world = 2
     mp.spawn(_cc_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert [open(tmp_path / f"cc{r}").read() for r in range(world)] == ["1", "1"]
+
+
+def _frames_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from housescan_b200 import synth
+    from housescan_b200.rooms import depth_stream_records_sharded, shard_frames
+
+    nf, w, h = 7, 64, 48  # 7 frames over 2 ranks: ragged ranges (4 + 3)
+    frames, poses = synth.depth_stream(nf, w, h)
+    planes = O.planes_from_cuboid(synth.C1_PARAMS)
+    intr = (synth.KINFU_INTR * 0.1).astype(np.float32)
+    fn = lambda fr, ps: O.backproject_reduce6x6(fr, w, h, planes, intr, ps)
+    got = depth_stream_records_sharded(fn, frames, poses, rank, world)
+    whole = fn(frames, poses)
+    ranges = [shard_frames(nf, r, world) for r in range(world)]
+    ok = np.array_equal(got, whole) and ranges == [(0, 4), (4, 7)]
+    ok = ok and [shard_frames(10_000, r, 8) for r in (0, 7)] == [(0, 1250), (8750, 10_000)]  # BASELINE configs[4]
+    ok = ok and sum(b - a for a, b in (shard_frames(5, r, 8) for r in range(8))) == 5  # more ranks than frames: empty ranges
+    open(os.path.join(tmp, f"fr{rank}"), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_frame_range_stream_equals_unsharded(tmp_path, built_lib, oracle_lib):
+    world = 2
+    mp.spawn(_frames_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / f"fr{r}").read() for r in range(world)] == ["1", "1"]
