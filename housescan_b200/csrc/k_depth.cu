@@ -446,8 +446,11 @@ k_reduce6x6_f32(const uint16_t* __restrict__ frames, int64_t nframes, int w, int
     int g = g_lo + threadIdx.x;
     int y = (g << 3) / w, x = (g << 3) - y * w;
     int it = 0;
+    uint4 vn = make_uint4(0u, 0u, 0u, 0u);
+    if (g < g_hi) vn = __ldcs(dep8 + g);
     for (; g < g_hi; g += HS_TPB, ++it) {
-      const uint4 v = __ldcs(dep8 + g);
+      const uint4 v = vn;
+      if (g + HS_TPB < g_hi) vn = __ldcs(dep8 + g + HS_TPB);  // the next 8 pixels are in flight while these are evaluated
       const unsigned int wv[4] = {v.x, v.y, v.z, v.w};
       const float x0f = static_cast<float>(x), yf = static_cast<float>(y);
       const float yc = INTR ? __fsub_rn(yf, geo.cy) : div_rn_small(yf, 10.0f, HS_RCP10);

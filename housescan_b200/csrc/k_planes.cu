@@ -3,6 +3,7 @@
 // (minimumBy, FitCuboidBFGS.hs:74); cuboid planes from makePlanesFromCuboid Main.hs:1852-1874 (built on the host).
 // All per-point geometry is Float without FMA contraction (bit-exact assignment); all sums are Double.
 #include "k_common.cuh"
+#include "k_ring.cuh"
 
 namespace hsk {
 
@@ -380,6 +381,148 @@ k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Ring form of the per-plane sums (default for K <= 6).  Same per-point block as k_plane_sums_f32 (ps_add), but
+//   * the points arrive through warp-private rings of 1-D bulk async copies (the TMA engine): lane 0 of a warp keeps D - 1 tiles
+//     of 32 groups (1536 B) in flight for ITS warp, so ~70 KB per SM are always on their way instead of one 48-byte group per
+//     thread, and nothing couples the warps of a block inside the streaming loop;
+//   * the Float chains are summed across the warp with shuffles every 64 points per lane and only the 9 K warp totals are
+//     added in Double (a [warps][9 K] table): no per-thread Doubles, so the 110 KB they took are the rings' now.
+// Block b owns a contiguous range of groups; its warps take the tiles of that range round-robin.
+// ------------------------------------------------------------------------------------------------------------------
+#define PSR_D 4                 // ring slots per warp
+#define PSR_TILE_BYTES 1536u    // 32 groups x 48 B
+#define PSR_FLUSH_TILES 16      // 64 points per lane between flushes
+
+template <int K, bool PAIRED>
+__global__ void __launch_bounds__(HS_TPB, 2)
+k_plane_sums_ring(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid_constant__ PlaneTable tbl, int64_t gpb,
+                  double* __restrict__ partials, unsigned int* ticket, double* __restrict__ out) {
+  constexpr int NW = HS_TPB / 32, NV = K * 9;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* rings = smem_raw;                                                                        // [NW][D][TILE]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(NW) * PSR_D * PSR_TILE_BYTES);  // [NW][D]
+  double* wacc = reinterpret_cast<double*>(full + NW * PSR_D);                                            // [NW][NV]
+  float* wtmp = reinterpret_cast<float*>(wacc + NW * NV);                                                  // [NW][64]
+  float* wmax = wtmp + NW * 64;                                                                            // [NW][8]
+  __shared__ float4 spl[HS_MAX_PLANES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < K) spl[threadIdx.x] = make_float4(tbl.pl[threadIdx.x][0], tbl.pl[threadIdx.x][1], tbl.pl[threadIdx.x][2], tbl.pl[threadIdx.x][3]);
+  uint64_t* my_full = full + warp * PSR_D;
+  if (lane == 0) {
+    for (int sl = 0; sl < PSR_D; ++sl) mbar_init(my_full + sl, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  double* my_wacc = wacc + warp * NV;
+  float* my_wtmp = wtmp + warp * 64;
+  for (int q = lane; q < NV; q += 32) my_wacc[q] = 0.0;
+  __syncthreads();
+
+  float a[K][9], mx[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    mx[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) a[k][c] = 0.f;
+  }
+  auto flush = [&]() {  // chains of the whole warp -> the warp's Double table
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        float v = a[k][c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) my_wtmp[k * 9 + c] = v;
+        a[k][c] = 0.f;
+      }
+    __syncwarp();
+    for (int q = lane; q < NV; q += 32) my_wacc[q] += static_cast<double>(my_wtmp[q]);
+    __syncwarp();
+  };
+
+  const int64_t gl = (i0 + 3) >> 2, gh = i1 >> 2;  // whole groups inside [i0, i1)
+  if (gl <= gh) {
+    if (blockIdx.x == 0) {  // ragged head / tail points (at most 3 each)
+      const int64_t nh = gl * 4 - i0, nt = i1 - gh * 4;
+      if (threadIdx.x < nh) { const int64_t i = i0 + threadIdx.x; ps_add<K, PAIRED>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+      else if (threadIdx.x >= 32 && threadIdx.x - 32 < nt) { const int64_t i = gh * 4 + threadIdx.x - 32; ps_add<K, PAIRED>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+    }
+    const int64_t b0 = gl + static_cast<int64_t>(blockIdx.x) * gpb, b1 = min(b0 + gpb, gh);  // this block's groups
+    const int64_t ngroups = b1 > b0 ? b1 - b0 : 0;
+    const int64_t ntiles = (ngroups + 31) / 32;
+    const int64_t mine = ntiles > warp ? (ntiles - warp + NW - 1) / NW : 0;  // tiles warp, warp + NW, ...
+    const float4* src = reinterpret_cast<const float4*>(xyz) + 3 * b0;
+    const uint32_t ring_s = smem_u32(rings) + warp * (PSR_D * PSR_TILE_BYTES), full_s = smem_u32(my_full);
+    auto issue = [&](int64_t i) {  // lane 0: bulk copy of my i-th tile into slot i % D
+      const int64_t tg = (warp + i * NW) * 32;
+      const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(32), ngroups - tg) * 48);
+      const uint32_t slot = static_cast<uint32_t>(i % PSR_D);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_s + 8 * slot), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(ring_s + slot * PSR_TILE_BYTES), "l"(src + 3 * tg), "r"(bytes), "r"(full_s + 8 * slot) : "memory");
+    };
+    if (lane == 0)
+      for (int64_t i = 0; i < PSR_D - 1 && i < mine; ++i) issue(i);
+    int since_flush = 0;
+    for (int64_t i = 0; i < mine; ++i) {
+      __syncwarp();  // every lane has read the slot that tile i + D - 1 overwrites (it held tile i - 1)
+      if (lane == 0 && i + PSR_D - 1 < mine) issue(i + PSR_D - 1);
+      const uint32_t slot = static_cast<uint32_t>(i % PSR_D);
+      mbar_wait_s_spin(full_s + 8 * slot, static_cast<uint32_t>((i / PSR_D) & 1));
+      const int64_t left = ngroups - (warp + i * NW) * 32;  // groups in this tile (>= 1)
+      const uint32_t base = ring_s + slot * PSR_TILE_BYTES + lane * 48;
+      const float4 q0 = lds_v4(base), q1 = lds_v4(base + 16), q2 = lds_v4(base + 32);  // lanes past a partial tile read stale (valid) smem
+      if (lane < left) {
+        ps_add<K, PAIRED>(a, mx, tbl, spl, q0.x, q0.y, q0.z);
+        ps_add<K, PAIRED>(a, mx, tbl, spl, q0.w, q1.x, q1.y);
+        ps_add<K, PAIRED>(a, mx, tbl, spl, q1.z, q1.w, q2.x);
+        ps_add<K, PAIRED>(a, mx, tbl, spl, q2.y, q2.z, q2.w);
+      }
+      if (++since_flush == PSR_FLUSH_TILES) { flush(); since_flush = 0; }
+    }
+  } else if (blockIdx.x == 0) {  // the whole range lies inside one group
+    const int64_t i = i0 + threadIdx.x;
+    if (i < i1) ps_add<K, PAIRED>(a, mx, tbl, spl, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  }
+  flush();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float m = mx[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) wmax[warp * 8 + k] = m;
+  }
+  __syncthreads();
+  // the block's K records (HS_PS layout: 9 sums + max |r|), warp tables combined in warp order
+  if (threadIdx.x < K * HS_PS) {
+    const int k = threadIdx.x / HS_PS, c = threadIdx.x % HS_PS;
+    double v = 0.0;
+    if (c < 9) { for (int w = 0; w < NW; ++w) v += wacc[w * NV + k * 9 + c]; }
+    else { float m = 0.f; for (int w = 0; w < NW; ++w) m = fmaxf(m, wmax[w * 8 + k]); v = m; }
+    partials[static_cast<int64_t>(blockIdx.x) * (K * HS_PS) + threadIdx.x] = v;
+  }
+  if (!last_block_arrives(ticket, gridDim.x)) return;
+  __shared__ double fin[HS_TPB];
+  constexpr int NVO = K * HS_PS, S = HS_TPB / NVO;
+  const int idx = threadIdx.x % NVO, sl = threadIdx.x / NVO;
+  const bool is_max = (idx % HS_PS) == 9;
+  double acc = 0.0;
+  if (sl < S)
+    for (unsigned int b = sl; b < gridDim.x; b += S) {
+      const double v = __ldcg(partials + static_cast<int64_t>(b) * NVO + idx);
+      acc = is_max ? fmax(acc, v) : acc + v;
+    }
+  fin[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < NVO) {
+    double t = 0.0;
+    for (int q = 0; q < S; ++q) { const double v = fin[q * NVO + threadIdx.x]; t = is_max ? fmax(t, v) : t + v; }
+    out[threadIdx.x] = t;
+  }
+}
+
 }  // namespace hsk
 
 // ======================================================== launchers ==================================================
@@ -423,6 +566,23 @@ static int32_t launch_plane_sums_k(hs_ctx* ctx, const float* xyz, int64_t i0, in
   const int nb = pick_blocks(ctx, i1 - i0, 4 * HS_TPB, 2);
   if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(nb) * K * HS_PS * sizeof(double))) return rc;
   if constexpr (K <= 6) {
+    if (ctx->modes[HS_MODE_PS_KERNEL] == 0 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {  // ring form
+      constexpr int NW = HS_TPB / 32;
+      const int dsm = NW * PSR_D * static_cast<int>(PSR_TILE_BYTES) + NW * PSR_D * 8 + NW * K * 9 * 8 + NW * 64 * 4 + NW * 8 * 4;
+      const int64_t ngroups = (i1 >> 2) - ((i0 + 3) >> 2);
+      const int64_t gpb = ngroups > 0 ? (ngroups + nb - 1) / nb : 1;
+      double* part = reinterpret_cast<double*>(ctx->d_scratch);
+      if (K == 6 && tbl.paired) {
+        HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_ring<K, (K == 6)>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
+        k_plane_sums_ring<K, (K == 6)><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, gpb, part, ctx->d_ticket, d_out);
+      } else {
+        HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_ring<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
+        k_plane_sums_ring<K, false><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, gpb, part, ctx->d_ticket, d_out);
+      }
+      ctx->launches++;
+      HS_CUDA_TRY(ctx, cudaGetLastError());
+      return HS_OK;
+    }
     if (ctx->modes[HS_MODE_PS_KERNEL] != 1 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
       const int dsm = K * 9 * HS_TPB * static_cast<int>(sizeof(double));
       double* part = reinterpret_cast<double*>(ctx->d_scratch);

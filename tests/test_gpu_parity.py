@@ -235,8 +235,9 @@ def test_rooms_sums_additive_over_point_shards(ctx, room_small, eval_mode):
         assert _rel(acc[r, :16], whole[r, :16], _record_scale(xyz[offs[r] : offs[r + 1]], pp[r])[:16]) < 2 * eval_mode
 
 
-# mode key 7: 0 = throughput form (Float chains of 32 points, then Double), 1 = all-Double form
-@pytest.mark.parametrize("ps_mode,tol", [(0, 1e-6), (1, 1e-11)])
+# mode key 7: 0 = ring form (bulk-async tiles, Float chains of 64 points summed across the warp, then Double),
+# 1 = all-Double form, 2 = direct loads with Float chains of 32 points and per-thread Doubles
+@pytest.mark.parametrize("ps_mode,tol", [(0, 1e-6), (1, 1e-11), (2, 1e-6)])
 def test_plane_sums_generic(ctx, room_small, ps_mode, tol):
     xyz, params = room_small
     offs = np.array([0, 100_000, 100_000, len(xyz)])
@@ -249,10 +250,10 @@ def test_plane_sums_generic(ctx, room_small, ps_mode, tol):
     out_o = O.plane_sums(xyz, offs, planes, 6)
     assert np.array_equal(out_g[..., 0], out_o[..., 0])
     assert np.array_equal(out_g[..., 9], out_o[..., 9])  # max |r| exact
-    assert np.allclose(out_g, out_o, rtol=tol, atol=1e-9 if ps_mode else 1e-6 * np.abs(out_o).max())
+    assert np.allclose(out_g, out_o, rtol=tol, atol=1e-9 if ps_mode == 1 else 1e-6 * np.abs(out_o).max())
 
 
-@pytest.mark.parametrize("ps_mode", [0, 1])
+@pytest.mark.parametrize("ps_mode", [0, 1, 2])
 def test_plane_sums_ragged_offsets_and_small_k(ctx, room_small, ps_mode):
     """room offsets that are not multiples of 4 (head / tail points), rooms shorter than a group, K from 1 to 8"""
     xyz, params = room_small

@@ -130,7 +130,7 @@ if want("A5"):
 if want("A13"):
     offs = np.arange(13, dtype=np.int64) * per
     allp = np.stack([hb.planes_from_cuboid(params[r]) for r in range(12)])
-    for mode, tag in ((1, "all-Double"), (0, "Float chains")):
+    for mode, tag in ((1, "all-Double"), (2, "Float chains, direct loads"), (0, "Float chains, bulk-async rings")):
         ctx.set_mode(7, mode)
         ps = ctx.plane_sums(cloud, offs, allp, 6)
         ms = timed(lambda: ctx.plane_sums(cloud, offs, allp, 6), reps=3, warm=1)
