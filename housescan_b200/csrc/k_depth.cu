@@ -182,6 +182,138 @@ k_bp_scatter(const uint16_t* __restrict__ depth, int64_t npx, int w, const unsig
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Single-pass form (default when points are wanted): count, mask, order-preserving offsets and scatter in ONE sweep over the
+// depth data.  Tiles are claimed in order through a counter; a tile publishes its valid-pixel count as soon as it knows it
+// (status AGGREGATE), then warp 0 looks back over its predecessors 32 at a time — adding aggregates until it meets a tile that
+// has already published its INCLUSIVE prefix — and publishes its own inclusive prefix (decoupled look-back).  A predecessor was
+// claimed earlier, is therefore running, and publishes its aggregate before it waits for anything: no deadlock for any grid.
+// Status and value share one 64-bit word (one store, one load: nothing else to order).  The depth data is read once
+// (2 B/px instead of 4) and one launch goes away; the scatter half is the same code as k_bp_scatter.
+// ------------------------------------------------------------------------------------------------------------------
+#define BP_ST_AGG (1ull << 62)
+#define BP_ST_INC (2ull << 62)
+#define BP_ST_MASK (3ull << 62)
+
+__global__ void __launch_bounds__(HS_TPB)
+k_bp_onepass(const uint16_t* __restrict__ depth, int64_t npx, int w, uint8_t* __restrict__ mask, unsigned long long* state /* [ntiles], zeroed */,
+             unsigned int* counters /* [0] next tile, [1] blocks done; zero between launches */, float* __restrict__ xyz, int64_t* __restrict__ n_valid) {
+  __shared__ unsigned int wsum[HS_TPB / 32];
+  __shared__ __align__(16) uint16_t sraw[BP_TILE];
+  __shared__ __align__(16) float stage[BP_TILE * 3 + 4];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_prefix;
+  const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
+  const bool aligned = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
+  const bool mask_aligned = mask && (reinterpret_cast<uintptr_t>(mask) & 7) == 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int lt = (1u << lane) - 1u;
+  volatile unsigned long long* vstate = state;
+  for (;;) {
+    __syncthreads();  // the previous tile's staging buffer and s_tile / s_prefix are free again
+    if (threadIdx.x == 0) s_tile = atomicAdd(counters, 1u);
+    __syncthreads();
+    const int64_t t = s_tile;
+    if (t >= ntiles) break;
+    const int64_t i0 = t * BP_TILE + 8 * threadIdx.x;
+    if (aligned && i0 + 8 <= npx) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(depth + i0));
+      reinterpret_cast<uint4*>(sraw)[threadIdx.x] = v;
+      if (mask_aligned) {
+        uint2 m;
+        m.x = __byte_perm(nz16x2(v.x) >> 15, nz16x2(v.y) >> 15, 0x6420);
+        m.y = __byte_perm(nz16x2(v.z) >> 15, nz16x2(v.w) >> 15, 0x6420);
+        __stcs(reinterpret_cast<uint2*>(mask + i0), m);
+      } else if (mask) {
+        const unsigned int wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mask[i0 + e] = static_cast<uint8_t>(((wv[e >> 1] >> (16 * (e & 1))) & 0xffffu) != 0);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint16_t dv = (i0 + e < npx) ? depth[i0 + e] : static_cast<uint16_t>(0);
+        sraw[8 * threadIdx.x + e] = dv;
+        if (mask && i0 + e < npx) mask[i0 + e] = static_cast<uint8_t>(dv != 0);
+      }
+    }
+    __syncwarp();
+    unsigned int d[8], bal[8], cw = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      d[e] = sraw[256 * warp + 32 * e + lane];
+      bal[e] = __ballot_sync(0xffffffffu, d[e] != 0);
+      cw += __popc(bal[e]);
+    }
+    if (lane == 0) wsum[warp] = cw;
+    __syncthreads();
+    unsigned int run = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < HS_TPB / 32; ++q) { run += (q < warp) ? wsum[q] : 0u; total += wsum[q]; }
+    if (warp == 0) {  // decoupled look-back
+      unsigned long long prefix = 0;
+      if (t > 0) {
+        if (lane == 0) vstate[t] = BP_ST_AGG | total;
+        int64_t look = t - 1;
+        for (;;) {
+          const int64_t idx = look - lane;
+          unsigned long long sv = BP_ST_INC;  // before tile 0: "inclusive prefix 0"
+          if (idx >= 0) { do { sv = vstate[idx]; } while ((sv & BP_ST_MASK) == 0); }
+          const unsigned int inc = __ballot_sync(0xffffffffu, (sv & BP_ST_MASK) == BP_ST_INC);
+          const int first = inc ? __ffs(inc) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
+          unsigned long long v = (lane <= first) ? (sv & ~BP_ST_MASK) : 0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          prefix += v;
+          if (inc) break;
+          look -= 32;
+        }
+      }
+      if (lane == 0) {
+        vstate[t] = BP_ST_INC | (prefix + total);
+        s_prefix = prefix;
+        if (t == ntiles - 1) *n_valid = static_cast<int64_t>(prefix + total);
+      }
+    }
+    __syncthreads();
+    const int64_t dst0 = 3 * static_cast<int64_t>(s_prefix);  // first float of the tile's run in xyz
+    const int a = static_cast<int>(dst0 & 3);
+    const int64_t p0 = t * BP_TILE + 256 * warp + lane;
+    int y, x;
+    if (npx <= 0xffffffffll) { const unsigned int q = static_cast<unsigned int>(p0) / static_cast<unsigned int>(w); y = static_cast<int>(q); x = static_cast<int>(static_cast<unsigned int>(p0) - q * static_cast<unsigned int>(w)); }
+    else { y = static_cast<int>(p0 / w); x = static_cast<int>(p0 - static_cast<int64_t>(y) * w); }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (d[e] != 0) {
+        float* sp = stage + a + 3 * (run + __popc(bal[e] & lt));
+        sp[0] = div_rn_small(static_cast<float>(x), 10.0f, HS_RCP10);
+        sp[1] = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
+        sp[2] = __fsub_rn(div_rn_small(static_cast<float>(d[e]), 20.0f, HS_RCP20), 30.0f);
+      }
+      run += __popc(bal[e]);
+      x += 32;
+      while (x >= w) { x -= w; ++y; }
+    }
+    __syncthreads();
+    const int lo = a, hi = a + 3 * static_cast<int>(total);
+    float* gbase = xyz + (dst0 - a);
+    const int lo4 = (lo + 3) & ~3, hi4 = hi & ~3;
+    if (lo4 < hi4) {
+      if (static_cast<int>(threadIdx.x) < lo4 - lo) gbase[lo + threadIdx.x] = stage[lo + threadIdx.x];
+      const float4* s4 = reinterpret_cast<const float4*>(stage);
+      float4* g4 = reinterpret_cast<float4*>(gbase);
+      for (int v = (lo4 >> 2) + threadIdx.x; v < (hi4 >> 2); v += HS_TPB) __stcs(g4 + v, s4[v]);
+      if (static_cast<int>(threadIdx.x) < hi - hi4) gbase[hi4 + threadIdx.x] = stage[hi4 + threadIdx.x];
+    } else {
+      for (int q = lo + threadIdx.x; q < hi; q += HS_TPB) gbase[q] = stage[q];
+    }
+  }
+  if (threadIdx.x == 0) {  // the last block to run out of tiles re-arms the counters for the next launch on this stream
+    __threadfence();
+    if (atomicAdd(counters + 1, 1u) == gridDim.x - 1) { counters[0] = 0u; counters[1] = 0u; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // fused per-frame: back-project -> (pose) -> nearest plane -> J = [p x n, n], accumulate J^T J (21), J^T r (6), r^2, count.
 // One block per frame (grid-stride over frames); Float geometry, Double accumulation, deterministic per-frame order.
 // ------------------------------------------------------------------------------------------------------------------
@@ -515,7 +647,15 @@ int32_t launch_backproject(hs_ctx* ctx, const uint16_t* d_depth, int32_t w, int3
   int64_t nb = std::min<int64_t>(ntiles, static_cast<int64_t>(ctx->sm_count) * 8);
   if (nb < 1) nb = 1;
   const int64_t nbc = std::max<int64_t>(1, std::min<int64_t>((ntiles + BP_CT - 1) / BP_CT, static_cast<int64_t>(ctx->sm_count) * 8));
-  if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(ntiles + 1) * sizeof(unsigned int))) return rc;
+  if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(ntiles + 1) * sizeof(unsigned long long))) return rc;
+  if (d_xyz && ctx->modes[HS_MODE_BP_KERNEL] != 1 && npx > 0) {  // single pass with decoupled look-back
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+    HS_CUDA_TRY(ctx, cudaMemsetAsync(state, 0, static_cast<size_t>(ntiles) * sizeof(unsigned long long), ctx->stream));
+    k_bp_onepass<<<static_cast<int>(nb), HS_TPB, 0, ctx->stream>>>(d_depth, npx, w, d_mask, state, ctx->d_ticket + 16, d_xyz, d_nvalid);
+    ctx->launches++;
+    HS_CUDA_TRY(ctx, cudaGetLastError());
+    return HS_OK;
+  }
   unsigned int* tile_off = reinterpret_cast<unsigned int*>(ctx->d_scratch);
   k_bp_count<<<static_cast<int>(nbc), HS_TPB, 0, ctx->stream>>>(d_depth, npx, d_mask, tile_off, ctx->d_ticket, d_nvalid);
   ctx->launches++;

@@ -33,8 +33,31 @@ def room_small():
 
 
 # ------------------------------------------------------------------ (1) back-projection
-@pytest.mark.parametrize("w,h", [(640, 480), (64, 48), (37, 5), (1, 1)])
-def test_backproject_mask_and_points_bit_exact(ctx, w, h):
+# mode key 10: 0 = single pass (decoupled look-back), 1 = count pass + scatter pass
+@pytest.fixture(params=[0, 1], ids=["onepass", "twopass"])
+def bp_mode(ctx, request):
+    ctx.set_mode(10, request.param)
+    yield request.param
+    ctx.set_mode(10, 0)
+
+
+def test_backproject_long_raster_many_tiles(ctx, bp_mode):
+    """40 frames as one tall raster (6000 tiles: several look-back windows deep), runs of invalid tiles, repeated launches"""
+    rng = np.random.default_rng(77)
+    w, h = 640, 480 * 40
+    depth = rng.integers(1, 65536, size=(h, w), dtype=np.uint16)
+    depth[rng.random((h, w)) < 0.1] = 0
+    depth[1000:1500] = 0      # ~150 consecutive tiles without a valid pixel
+    depth[9000:9001, :7] = 0
+    xyz_o, mask_o = O.backproject_ref(depth, w, h)
+    for _ in range(3):
+        xyz_g, mask_g = ctx.backproject_ref(depth, w, h)
+        assert np.array_equal(mask_g, mask_o)
+        assert xyz_g.shape == xyz_o.shape and np.array_equal(xyz_g.view(np.uint32), xyz_o.view(np.uint32))
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (64, 48), (37, 5), (1, 1), (2048, 3), (2047, 2)])
+def test_backproject_mask_and_points_bit_exact(ctx, w, h, bp_mode):
     rng = np.random.default_rng(w * 1000 + h)
     depth = rng.integers(0, 65536, size=(h, w), dtype=np.uint16)
     depth[rng.random((h, w)) < 0.3] = 0
@@ -45,7 +68,7 @@ def test_backproject_mask_and_points_bit_exact(ctx, w, h):
     assert np.array_equal(xyz_g.view(np.uint32), xyz_o.view(np.uint32))
 
 
-def test_backproject_all_invalid_and_all_valid(ctx):
+def test_backproject_all_invalid_and_all_valid(ctx, bp_mode):
     z = np.zeros((48, 64), np.uint16)
     xyz, mask = ctx.backproject_ref(z, 64, 48)
     assert xyz.shape == (0, 3) and mask.sum() == 0

@@ -172,6 +172,9 @@ if want("A1"):
     d_mask = torch.empty(npx, dtype=torch.uint8, device=dev)
     nv = C.c_int64()
     fn = lambda: ctx._chk(lib.hs_backproject_ref_dev(ctx.h, C.c_void_p(frames.data_ptr()), w, h * nf, bp_cloud.h, C.c_void_p(d_mask.data_ptr()), C.byref(nv)))
+    ctx.set_mode(10, 1)
+    ms2 = timed(fn, reps=5)
+    ctx.set_mode(10, 0)
     ms = timed(fn, reps=5)
     valid = frames.view(-1) != 0
     ok = nv.value == int(valid.sum().item()) and bool(torch.equal(d_mask.bool(), valid))
@@ -183,7 +186,8 @@ if want("A1"):
     exp = torch.stack([torch.div((idx % w).float(), ten), torch.div((idx // w).float(), ten), torch.div(d, twenty) - 30.0], dim=1)
     got = bp_out[: 3 * nv.value].view(-1, 3)[-1000:]
     ok = ok and bool(torch.equal(exp, got))
-    report("A1-3", "hs_backproject_ref_dev (stream)", npx, "px", 2.0 + 1.0 + 12.0 * fr, ms, bool(ok), note=f"{nf} frames as one raster, valid fraction {fr:.3f}, mask written")
+    report("A1-3", "hs_backproject_ref_dev (two passes)", npx, "px", 2.0 + 1.0 + 12.0 * fr, ms2, True, note="count pass + scatter pass")
+    report("A1-3", "hs_backproject_ref_dev (single pass)", npx, "px", 2.0 + 1.0 + 12.0 * fr, ms, bool(ok), note=f"decoupled look-back; {nf} frames as one raster, valid fraction {fr:.3f}, mask written")
     del bp_out, d_mask
     # A4 fused back-project + nearest plane + 6x6 normal equations per frame
     planes = hb.planes_from_cuboid(synth.C1_PARAMS)
