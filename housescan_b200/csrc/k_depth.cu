@@ -194,65 +194,81 @@ k_bp_scatter(const uint16_t* __restrict__ depth, int64_t npx, int w, const unsig
 #define BP_ST_INC (2ull << 62)
 #define BP_ST_MASK (3ull << 62)
 
+#define BP_SUPER 4  // tiles per claim: one counter increment and one look-back per 8192 pixels
+
 __global__ void __launch_bounds__(HS_TPB)
-k_bp_onepass(const uint16_t* __restrict__ depth, int64_t npx, int w, uint8_t* __restrict__ mask, unsigned long long* state /* [ntiles], zeroed */,
-             unsigned int* counters /* [0] next tile, [1] blocks done; zero between launches */, float* __restrict__ xyz, int64_t* __restrict__ n_valid) {
-  __shared__ unsigned int wsum[HS_TPB / 32];
-  __shared__ __align__(16) uint16_t sraw[BP_TILE];
+k_bp_onepass(const uint16_t* __restrict__ depth, int64_t npx, int w, uint8_t* __restrict__ mask, unsigned long long* state /* [nsuper], zeroed */,
+             unsigned int* counters /* [0] next super-tile, [1] blocks done; zero between launches */, float* __restrict__ xyz, int64_t* __restrict__ n_valid) {
+  __shared__ unsigned int wsum[BP_SUPER][HS_TPB / 32];
+  __shared__ __align__(16) uint16_t sraw[BP_SUPER * BP_TILE];
   __shared__ __align__(16) float stage[BP_TILE * 3 + 4];
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_prefix;
-  const int64_t ntiles = (npx + BP_TILE - 1) / BP_TILE;
+  const int64_t nsuper = (npx + BP_SUPER * BP_TILE - 1) / (BP_SUPER * BP_TILE);
   const bool aligned = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   const bool mask_aligned = mask && (reinterpret_cast<uintptr_t>(mask) & 7) == 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int lt = (1u << lane) - 1u;
   volatile unsigned long long* vstate = state;
   for (;;) {
-    __syncthreads();  // the previous tile's staging buffer and s_tile / s_prefix are free again
+    __syncthreads();  // the previous claim's buffers and s_tile / s_prefix are free again
     if (threadIdx.x == 0) s_tile = atomicAdd(counters, 1u);
     __syncthreads();
     const int64_t t = s_tile;
-    if (t >= ntiles) break;
-    const int64_t i0 = t * BP_TILE + 8 * threadIdx.x;
-    if (aligned && i0 + 8 <= npx) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(depth + i0));
-      reinterpret_cast<uint4*>(sraw)[threadIdx.x] = v;
-      if (mask_aligned) {
-        uint2 m;
-        m.x = __byte_perm(nz16x2(v.x) >> 15, nz16x2(v.y) >> 15, 0x6420);
-        m.y = __byte_perm(nz16x2(v.z) >> 15, nz16x2(v.w) >> 15, 0x6420);
-        __stcs(reinterpret_cast<uint2*>(mask + i0), m);
-      } else if (mask) {
-        const unsigned int wv[4] = {v.x, v.y, v.z, v.w};
+    if (t >= nsuper) break;
+    // ---- all BP_SUPER tiles of the claim: loads first (independent, all in flight), then mask + parking in shared memory
+    uint4 v[BP_SUPER];
+    bool fast[BP_SUPER];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) mask[i0 + e] = static_cast<uint8_t>(((wv[e >> 1] >> (16 * (e & 1))) & 0xffffu) != 0);
+    for (int q = 0; q < BP_SUPER; ++q) {
+      const int64_t i0 = (t * BP_SUPER + q) * BP_TILE + 8 * threadIdx.x;
+      fast[q] = aligned && i0 + 8 <= npx;
+      v[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (fast[q]) v[q] = __ldg(reinterpret_cast<const uint4*>(depth + i0));
+    }
+#pragma unroll
+    for (int q = 0; q < BP_SUPER; ++q) {
+      const int64_t i0 = (t * BP_SUPER + q) * BP_TILE + 8 * threadIdx.x;
+      if (!fast[q]) {  // ragged end of the raster or an unaligned frame
+        unsigned int dd[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dd[e] = (i0 + e < npx) ? depth[i0 + e] : 0u;
+        v[q] = make_uint4(dd[0] | (dd[1] << 16), dd[2] | (dd[3] << 16), dd[4] | (dd[5] << 16), dd[6] | (dd[7] << 16));
       }
-    } else {
+      reinterpret_cast<uint4*>(sraw)[q * HS_TPB + threadIdx.x] = v[q];
+      if (mask) {
+        uint2 m;  // byte e = (pixel e != 0)
+        m.x = __byte_perm(nz16x2(v[q].x) >> 15, nz16x2(v[q].y) >> 15, 0x6420);
+        m.y = __byte_perm(nz16x2(v[q].z) >> 15, nz16x2(v[q].w) >> 15, 0x6420);
+        if (mask_aligned && i0 + 8 <= npx) __stcs(reinterpret_cast<uint2*>(mask + i0), m);
+        else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint16_t dv = (i0 + e < npx) ? depth[i0 + e] : static_cast<uint16_t>(0);
-        sraw[8 * threadIdx.x + e] = dv;
-        if (mask && i0 + e < npx) mask[i0 + e] = static_cast<uint8_t>(dv != 0);
+          for (int e = 0; e < 8; ++e)
+            if (i0 + e < npx) mask[i0 + e] = static_cast<uint8_t>(((e < 4 ? m.x : m.y) >> (8 * (e & 3))) & 1u);
+        }
       }
     }
     __syncwarp();
-    unsigned int d[8], bal[8], cw = 0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      d[e] = sraw[256 * warp + 32 * e + lane];
-      bal[e] = __ballot_sync(0xffffffffu, d[e] != 0);
-      cw += __popc(bal[e]);
+    for (int q = 0; q < BP_SUPER; ++q) {
+      unsigned int cw = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cw += __popc(__ballot_sync(0xffffffffu, sraw[q * BP_TILE + 256 * warp + 32 * e + lane] != 0));
+      if (lane == 0) wsum[q][warp] = cw;
     }
-    if (lane == 0) wsum[warp] = cw;
     __syncthreads();
-    unsigned int run = 0, total = 0;
+    unsigned int total[BP_SUPER], all = 0;
 #pragma unroll
-    for (int q = 0; q < HS_TPB / 32; ++q) { run += (q < warp) ? wsum[q] : 0u; total += wsum[q]; }
+    for (int q = 0; q < BP_SUPER; ++q) {
+      total[q] = 0;
+#pragma unroll
+      for (int u = 0; u < HS_TPB / 32; ++u) total[q] += wsum[q][u];
+      all += total[q];
+    }
     if (warp == 0) {  // decoupled look-back
       unsigned long long prefix = 0;
       if (t > 0) {
-        if (lane == 0) vstate[t] = BP_ST_AGG | total;
+        if (lane == 0) vstate[t] = BP_ST_AGG | all;
         int64_t look = t - 1;
         for (;;) {
           const int64_t idx = look - lane;
@@ -260,51 +276,63 @@ k_bp_onepass(const uint16_t* __restrict__ depth, int64_t npx, int w, uint8_t* __
           if (idx >= 0) { do { sv = vstate[idx]; } while ((sv & BP_ST_MASK) == 0); }
           const unsigned int inc = __ballot_sync(0xffffffffu, (sv & BP_ST_MASK) == BP_ST_INC);
           const int first = inc ? __ffs(inc) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
-          unsigned long long v = (lane <= first) ? (sv & ~BP_ST_MASK) : 0ull;
+          unsigned long long pv = (lane <= first) ? (sv & ~BP_ST_MASK) : 0ull;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          prefix += v;
+          for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+          prefix += pv;
           if (inc) break;
           look -= 32;
         }
       }
       if (lane == 0) {
-        vstate[t] = BP_ST_INC | (prefix + total);
+        vstate[t] = BP_ST_INC | (prefix + all);
         s_prefix = prefix;
-        if (t == ntiles - 1) *n_valid = static_cast<int64_t>(prefix + total);
+        if (t == nsuper - 1) *n_valid = static_cast<int64_t>(prefix + all);
       }
     }
     __syncthreads();
-    const int64_t dst0 = 3 * static_cast<int64_t>(s_prefix);  // first float of the tile's run in xyz
-    const int a = static_cast<int>(dst0 & 3);
-    const int64_t p0 = t * BP_TILE + 256 * warp + lane;
-    int y, x;
-    if (npx <= 0xffffffffll) { const unsigned int q = static_cast<unsigned int>(p0) / static_cast<unsigned int>(w); y = static_cast<int>(q); x = static_cast<int>(static_cast<unsigned int>(p0) - q * static_cast<unsigned int>(w)); }
-    else { y = static_cast<int>(p0 / w); x = static_cast<int>(p0 - static_cast<int64_t>(y) * w); }
+    int64_t pts0 = static_cast<int64_t>(s_prefix);  // points before the current tile
+#pragma unroll 1
+    for (int q = 0; q < BP_SUPER; ++q) {
+      unsigned int run = 0;
+      for (int u = 0; u < warp; ++u) run += wsum[q][u];
+      const int64_t dst0 = 3 * pts0;  // first float of the tile's run in xyz
+      const int a = static_cast<int>(dst0 & 3);
+      const int64_t p0 = (t * BP_SUPER + q) * BP_TILE + 256 * warp + lane;
+      int y, x;
+      if (npx <= 0xffffffffll) { const unsigned int qq = static_cast<unsigned int>(p0) / static_cast<unsigned int>(w); y = static_cast<int>(qq); x = static_cast<int>(static_cast<unsigned int>(p0) - qq * static_cast<unsigned int>(w)); }
+      else { y = static_cast<int>(p0 / w); x = static_cast<int>(p0 - static_cast<int64_t>(y) * w); }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (d[e] != 0) {
-        float* sp = stage + a + 3 * (run + __popc(bal[e] & lt));
-        sp[0] = div_rn_small(static_cast<float>(x), 10.0f, HS_RCP10);
-        sp[1] = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
-        sp[2] = __fsub_rn(div_rn_small(static_cast<float>(d[e]), 20.0f, HS_RCP20), 30.0f);
+      for (int e = 0; e < 8; ++e) {
+        const unsigned int d = sraw[q * BP_TILE + 256 * warp + 32 * e + lane];
+        const unsigned int bal = __ballot_sync(0xffffffffu, d != 0);
+        if (d != 0) {
+          float* sp = stage + a + 3 * (run + __popc(bal & lt));
+          sp[0] = div_rn_small(static_cast<float>(x), 10.0f, HS_RCP10);
+          sp[1] = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
+          sp[2] = __fsub_rn(div_rn_small(static_cast<float>(d), 20.0f, HS_RCP20), 30.0f);
+        }
+        run += __popc(bal);
+        x += 32;
+        while (x >= w) { x -= w; ++y; }
       }
-      run += __popc(bal[e]);
-      x += 32;
-      while (x >= w) { x -= w; ++y; }
-    }
-    __syncthreads();
-    const int lo = a, hi = a + 3 * static_cast<int>(total);
-    float* gbase = xyz + (dst0 - a);
-    const int lo4 = (lo + 3) & ~3, hi4 = hi & ~3;
-    if (lo4 < hi4) {
-      if (static_cast<int>(threadIdx.x) < lo4 - lo) gbase[lo + threadIdx.x] = stage[lo + threadIdx.x];
-      const float4* s4 = reinterpret_cast<const float4*>(stage);
-      float4* g4 = reinterpret_cast<float4*>(gbase);
-      for (int v = (lo4 >> 2) + threadIdx.x; v < (hi4 >> 2); v += HS_TPB) __stcs(g4 + v, s4[v]);
-      if (static_cast<int>(threadIdx.x) < hi - hi4) gbase[hi4 + threadIdx.x] = stage[hi4 + threadIdx.x];
-    } else {
-      for (int q = lo + threadIdx.x; q < hi; q += HS_TPB) gbase[q] = stage[q];
+      __syncthreads();
+      unsigned int tq = 0;
+      for (int u = 0; u < HS_TPB / 32; ++u) tq += wsum[q][u];
+      const int lo = a, hi = a + 3 * static_cast<int>(tq);
+      float* gbase = xyz + (dst0 - a);
+      const int lo4 = (lo + 3) & ~3, hi4 = hi & ~3;
+      if (lo4 < hi4) {
+        if (static_cast<int>(threadIdx.x) < lo4 - lo) gbase[lo + threadIdx.x] = stage[lo + threadIdx.x];
+        const float4* s4 = reinterpret_cast<const float4*>(stage);
+        float4* g4 = reinterpret_cast<float4*>(gbase);
+        for (int vv = (lo4 >> 2) + threadIdx.x; vv < (hi4 >> 2); vv += HS_TPB) __stcs(g4 + vv, s4[vv]);
+        if (static_cast<int>(threadIdx.x) < hi - hi4) gbase[hi4 + threadIdx.x] = stage[hi4 + threadIdx.x];
+      } else {
+        for (int qq = lo + threadIdx.x; qq < hi; qq += HS_TPB) gbase[qq] = stage[qq];
+      }
+      pts0 += tq;
+      __syncthreads();  // the staging buffer is reused by the next tile of the claim
     }
   }
   if (threadIdx.x == 0) {  // the last block to run out of tiles re-arms the counters for the next launch on this stream
@@ -650,7 +678,9 @@ int32_t launch_backproject(hs_ctx* ctx, const uint16_t* d_depth, int32_t w, int3
   if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(ntiles + 1) * sizeof(unsigned long long))) return rc;
   if (d_xyz && ctx->modes[HS_MODE_BP_KERNEL] != 1 && npx > 0) {  // single pass with decoupled look-back
     unsigned long long* state = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
-    HS_CUDA_TRY(ctx, cudaMemsetAsync(state, 0, static_cast<size_t>(ntiles) * sizeof(unsigned long long), ctx->stream));
+    const int64_t nsuper = (ntiles + BP_SUPER - 1) / BP_SUPER;
+    HS_CUDA_TRY(ctx, cudaMemsetAsync(state, 0, static_cast<size_t>(nsuper) * sizeof(unsigned long long), ctx->stream));
+    nb = std::max<int64_t>(1, std::min<int64_t>(nsuper, static_cast<int64_t>(ctx->sm_count) * 5));
     k_bp_onepass<<<static_cast<int>(nb), HS_TPB, 0, ctx->stream>>>(d_depth, npx, w, d_mask, state, ctx->d_ticket + 16, d_xyz, d_nvalid);
     ctx->launches++;
     HS_CUDA_TRY(ctx, cudaGetLastError());
