@@ -3,7 +3,10 @@
 // Data.Graph.components of the undirected graph; the canonical label of a vertex is the minimum vertex id of its
 // component (components are listed in ascending order of that minimum).  Implemented as a lock-free union-find:
 // every link hangs the larger root under the smaller one (atomicCAS), so each root is its set's minimum.
+#include <algorithm>
+
 #include "k_common.cuh"
+#define HS_CC_DEFAULT_CHUNKS 1
 
 namespace hsk {
 
@@ -61,8 +64,19 @@ int32_t launch_cc(hs_ctx* ctx, const uint32_t* d_src, const uint32_t* d_dst, int
   k_cc_init<<<blocks(N), HS_TPB, 0, ctx->stream>>>(d_label, N);
   ctx->launches++;
   if (E > 0) {
-    k_cc_link<<<blocks(E), HS_TPB, 0, ctx->stream>>>(d_src, d_dst, E, d_label);
-    ctx->launches++;
+    // The edge list is linked in `chunks` slices with a flatten in between: a flatten costs one sweep over the vertices (8 B each)
+    // and leaves every tree one level deep, so the finds of the next slice are one or two loads instead of pointer chases
+    // through whatever chains the previous slice built (mode key 11; 0 = default).
+    int chunks = ctx->modes[HS_MODE_CC_CHUNKS] > 0 ? ctx->modes[HS_MODE_CC_CHUNKS] : HS_CC_DEFAULT_CHUNKS;
+    if (E < (1 << 20)) chunks = 1;
+    const int64_t per = (E + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
+      const int64_t e0 = c * per, e1 = std::min<int64_t>(E, e0 + per);
+      if (e0 >= e1) break;
+      if (c > 0) { k_cc_flatten<<<blocks(N), HS_TPB, 0, ctx->stream>>>(d_label, N); ctx->launches++; }
+      k_cc_link<<<blocks(e1 - e0), HS_TPB, 0, ctx->stream>>>(d_src + e0, d_dst + e0, e1 - e0, d_label);
+      ctx->launches++;
+    }
   }
   k_cc_flatten<<<blocks(N), HS_TPB, 0, ctx->stream>>>(d_label, N);
   ctx->launches++;
