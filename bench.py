@@ -159,6 +159,21 @@ def run_reference(args, rank, world):
     import oracle as O
     from housescan_b200 import synth
 
+    if os.environ.get("TORCHELASTIC_RUN_ID") and os.environ.get("OMP_NUM_THREADS") == "1" and not os.environ.get("HS_REF_CHILD"):
+        # torchrun exports OMP_NUM_THREADS=1 to its workers (and libgomp sizes its pool and wait policy from it at load time): run
+        # this arm in a child with the launcher's settings removed, so that it uses all host threads exactly as at N = 1
+        import subprocess
+        env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS" and not k.startswith("TORCHELASTIC")}
+        env["HS_REF_CHILD"] = "1"
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", str(args.gpus), "--steps", str(args.steps),
+               "--warmup", str(args.warmup), "--scaling", args.scaling, "--ref-pts-per-room", str(args.ref_pts_per_room)]
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        sys.stderr.write(out.stderr)
+        sys.stdout.write(out.stdout)
+        sys.stdout.flush()
+        return
     O.build()
     per_room = args.ref_pts_per_room
     params = room_params()

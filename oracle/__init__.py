@@ -69,6 +69,10 @@ def num_threads() -> int:
     return lib().orc_num_threads()
 
 
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
+
+
 # ---------------------------------------------------------------- A1-A3
 def backproject_ref(depth: np.ndarray, w: int, h: int):
     """Main.hs:1296-1313.  Returns (xyz[n_valid,3] f32, mask[w*h] u8)."""

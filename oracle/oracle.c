@@ -39,6 +39,15 @@ ORC_API int orc_num_threads(void) {
   return 1;
 #endif
 }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline arm asks for all host threads explicitly */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 
 /* ------------------------------------------------------------------------------------
  * A1-A3  depth frame -> points.   Main.hs:1296-1313
