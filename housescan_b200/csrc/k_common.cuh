@@ -184,6 +184,39 @@ __device__ __forceinline__ void last_block_sum(const double* __restrict__ partia
   __syncthreads();
 }
 
+// Decoupled look-back for single-pass order-preserving compactions.  Claims (tiles) are handed out in order through a counter;
+// claim t publishes its element count as soon as it knows it (status AGGREGATE), then one warp looks back over the predecessors
+// 32 at a time, adding aggregates until it meets one that already published its INCLUSIVE prefix, and publishes its own.
+// A predecessor was claimed earlier, is therefore running, and publishes its aggregate before it waits for anything: no
+// deadlock for any grid size.  Status and value share one 64-bit word (one store, one load: nothing else to order); the state
+// array must be zero before the launch.  Call with all 32 lanes of ONE warp; returns the exclusive prefix of claim t.
+#define HS_LB_AGG (1ull << 62)
+#define HS_LB_INC (2ull << 62)
+#define HS_LB_MASK (3ull << 62)
+__device__ __forceinline__ unsigned long long tile_lookback(volatile unsigned long long* vstate, int64_t t, unsigned long long count) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long prefix = 0;
+  if (t > 0) {
+    if (lane == 0) vstate[t] = HS_LB_AGG | count;
+    int64_t look = t - 1;
+    for (;;) {
+      const int64_t idx = look - lane;
+      unsigned long long sv = HS_LB_INC;  // before claim 0: "inclusive prefix 0"
+      if (idx >= 0) { do { sv = vstate[idx]; } while ((sv & HS_LB_MASK) == 0); }
+      const unsigned int inc = __ballot_sync(0xffffffffu, (sv & HS_LB_MASK) == HS_LB_INC);
+      const int first = inc ? __ffs(inc) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
+      unsigned long long pv = (lane <= first) ? (sv & ~HS_LB_MASK) : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+      prefix += pv;
+      if (inc) break;
+      look -= 32;
+    }
+  }
+  if (lane == 0) vstate[t] = HS_LB_INC | (prefix + count);
+  return prefix;
+}
+
 // exclusive prefix of a per-thread count inside the block (raster order of threads); smem wsum[HS_TPB/32]
 __device__ __forceinline__ unsigned int block_exclusive_prefix(unsigned int c, unsigned int* wsum) {
   unsigned int incl = c;

@@ -183,17 +183,9 @@ k_bp_scatter(const uint16_t* __restrict__ depth, int64_t npx, int w, const unsig
 
 // ------------------------------------------------------------------------------------------------------------------
 // Single-pass form (default when points are wanted): count, mask, order-preserving offsets and scatter in ONE sweep over the
-// depth data.  Tiles are claimed in order through a counter; a tile publishes its valid-pixel count as soon as it knows it
-// (status AGGREGATE), then warp 0 looks back over its predecessors 32 at a time — adding aggregates until it meets a tile that
-// has already published its INCLUSIVE prefix — and publishes its own inclusive prefix (decoupled look-back).  A predecessor was
-// claimed earlier, is therefore running, and publishes its aggregate before it waits for anything: no deadlock for any grid.
-// Status and value share one 64-bit word (one store, one load: nothing else to order).  The depth data is read once
-// (2 B/px instead of 4) and one launch goes away; the scatter half is the same code as k_bp_scatter.
+// depth data, the offsets coming from a decoupled look-back (tile_lookback, k_common.cuh) over claims of BP_SUPER tiles.
+// The depth data is read once (2 B/px instead of 4) and one launch goes away; the scatter half is the code of k_bp_scatter.
 // ------------------------------------------------------------------------------------------------------------------
-#define BP_ST_AGG (1ull << 62)
-#define BP_ST_INC (2ull << 62)
-#define BP_ST_MASK (3ull << 62)
-
 #define BP_SUPER 4  // tiles per claim: one counter increment and one look-back per 8192 pixels
 
 __global__ void __launch_bounds__(HS_TPB)
@@ -265,27 +257,9 @@ k_bp_onepass(const uint16_t* __restrict__ depth, int64_t npx, int w, uint8_t* __
       for (int u = 0; u < HS_TPB / 32; ++u) total[q] += wsum[q][u];
       all += total[q];
     }
-    if (warp == 0) {  // decoupled look-back
-      unsigned long long prefix = 0;
-      if (t > 0) {
-        if (lane == 0) vstate[t] = BP_ST_AGG | all;
-        int64_t look = t - 1;
-        for (;;) {
-          const int64_t idx = look - lane;
-          unsigned long long sv = BP_ST_INC;  // before tile 0: "inclusive prefix 0"
-          if (idx >= 0) { do { sv = vstate[idx]; } while ((sv & BP_ST_MASK) == 0); }
-          const unsigned int inc = __ballot_sync(0xffffffffu, (sv & BP_ST_MASK) == BP_ST_INC);
-          const int first = inc ? __ffs(inc) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
-          unsigned long long pv = (lane <= first) ? (sv & ~BP_ST_MASK) : 0ull;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
-          prefix += pv;
-          if (inc) break;
-          look -= 32;
-        }
-      }
+    if (warp == 0) {
+      const unsigned long long prefix = tile_lookback(vstate, t, all);
       if (lane == 0) {
-        vstate[t] = BP_ST_INC | (prefix + all);
         s_prefix = prefix;
         if (t == nsuper - 1) *n_valid = static_cast<int64_t>(prefix + all);
       }

@@ -3,6 +3,8 @@
 //   removeCeiling (Main.hs:2643-2664): yLimit = k-th largest y with k = n `quot` 5; keep y <= yLimit in input order.
 // The order statistic is found by a 4-pass MSB radix select over order-preserving uint images of the Float keys
 // (no sort, no copy of the cloud); the filter is a two-pass block-scan compaction.
+#include <algorithm>
+
 #include "k_common.cuh"
 
 namespace hsk {
@@ -268,6 +270,101 @@ k_filter_scatter(const float* __restrict__ xyz, int64_t n, int axis, float limit
   }
 }
 
+// Single-pass filter (default): the same compaction with the offsets from a decoupled look-back over claims of FL_SUPER tiles
+// (tile_lookback, k_common.cuh).  A claim's points are read once from HBM; the second read, for the scatter, comes from L2
+// (48 KB per claim).  12 + 12 kept bytes per point instead of 24 + 12 kept, and one launch less.
+#define FL_SUPER 4
+__global__ void __launch_bounds__(HS_TPB)
+k_filter_onepass(const float* __restrict__ xyz, int64_t n, int axis, float limit, unsigned long long* state /* [nsuper], zeroed */,
+                 unsigned int* counters /* [0] next claim, [1] blocks done */, const float* __restrict__ extra_in, float* __restrict__ out,
+                 float* __restrict__ extra_out, int64_t* __restrict__ n_out) {
+  __shared__ unsigned int wsum[FL_SUPER][HS_TPB / 32];
+  __shared__ __align__(16) float stage[FL_TILE * 3 + 4];
+  __shared__ __align__(16) float stage2[FL_TILE * 3 + 4];
+  __shared__ unsigned int s_claim;
+  __shared__ unsigned long long s_prefix;
+  const int64_t nsuper = (n + FL_SUPER * FL_TILE - 1) / (FL_SUPER * FL_TILE);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  volatile unsigned long long* vstate = state;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_claim = atomicAdd(counters, 1u);
+    __syncthreads();
+    const int64_t t = s_claim;
+    if (t >= nsuper) break;
+    unsigned int keepbits = 0;  // bit 4 q + e: point e of this thread's group in tile q is kept
+#pragma unroll
+    for (int q = 0; q < FL_SUPER; ++q) {
+      const int64_t i0 = (t * FL_SUPER + q) * FL_TILE + 4 * threadIdx.x;
+      Pts4 p;
+      const int m = load_tile_group(xyz, n, i0, p);
+      unsigned int c = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool k = (e < m) && ((axis == 0 ? p.x[e] : (axis == 1 ? p.y[e] : p.z[e])) <= limit);
+        keepbits |= static_cast<unsigned int>(k) << (4 * q + e);
+        c += k;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) wsum[q][warp] = c;
+    }
+    __syncthreads();
+    unsigned int all = 0;
+#pragma unroll
+    for (int q = 0; q < FL_SUPER; ++q)
+#pragma unroll
+      for (int u = 0; u < HS_TPB / 32; ++u) all += wsum[q][u];
+    if (warp == 0) {
+      const unsigned long long prefix = tile_lookback(vstate, t, all);
+      if (lane == 0) {
+        s_prefix = prefix;
+        if (t == nsuper - 1) *n_out = static_cast<int64_t>(prefix + all);
+      }
+    }
+    __syncthreads();
+    int64_t pts0 = static_cast<int64_t>(s_prefix);
+#pragma unroll 1
+    for (int q = 0; q < FL_SUPER; ++q) {
+      const int64_t i0 = (t * FL_SUPER + q) * FL_TILE + 4 * threadIdx.x;
+      const unsigned int kb = (keepbits >> (4 * q)) & 15u;
+      // position of this thread's first kept point inside the tile: kept points of the lower lanes + of the lower warps
+      unsigned int incl = __popc(kb);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      unsigned int pos = incl - __popc(kb), tq = 0;
+      for (int u = 0; u < HS_TPB / 32; ++u) { pos += (u < warp) ? wsum[q][u] : 0u; tq += wsum[q][u]; }
+      const int64_t dst0 = 3 * pts0;
+      const int a = static_cast<int>(dst0 & 3);
+      if (kb) {
+        Pts4 p, c;
+        load_tile_group(xyz, n, i0, p);
+        if (extra_in) load_tile_group(extra_in, n, i0, c);
+        int sp = a + 3 * static_cast<int>(pos);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if ((kb >> e) & 1u) {
+            stage[sp] = p.x[e]; stage[sp + 1] = p.y[e]; stage[sp + 2] = p.z[e];
+            if (extra_in) { stage2[sp] = c.x[e]; stage2[sp + 1] = c.y[e]; stage2[sp + 2] = c.z[e]; }
+            sp += 3;
+          }
+      }
+      __syncthreads();
+      store_run(stage, a, 3 * static_cast<int>(tq), out, dst0);
+      if (extra_in) store_run(stage2, a, 3 * static_cast<int>(tq), extra_out, dst0);
+      pts0 += tq;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(counters + 1, 1u) == gridDim.x - 1) { counters[0] = 0u; counters[1] = 0u; }
+  }
+}
+
 }  // namespace hsk
 
 using namespace hsk;
@@ -319,7 +416,17 @@ int32_t launch_filter_le(hs_ctx* ctx, const float* xyz, int64_t n, int axis, flo
   const int64_t ntiles = (n + FL_TILE - 1) / FL_TILE;
   int64_t nb = ntiles < static_cast<int64_t>(ctx->sm_count) * 8 ? ntiles : static_cast<int64_t>(ctx->sm_count) * 8;
   if (nb < 1) nb = 1;
-  if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(ntiles + 1) * sizeof(unsigned int))) return rc;
+  if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(ntiles + 1) * sizeof(unsigned long long))) return rc;
+  if (ctx->modes[HS_MODE_FILTER_KERNEL] != 1 && n > 0 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {  // single pass
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+    const int64_t nsuper = (ntiles + FL_SUPER - 1) / FL_SUPER;
+    HS_CUDA_TRY(ctx, cudaMemsetAsync(state, 0, static_cast<size_t>(nsuper) * sizeof(unsigned long long), ctx->stream));
+    const int64_t nb1 = std::max<int64_t>(1, std::min<int64_t>(nsuper, static_cast<int64_t>(ctx->sm_count) * 6));
+    k_filter_onepass<<<static_cast<int>(nb1), HS_TPB, 0, ctx->stream>>>(xyz, n, axis, limit, state, ctx->d_ticket + 24, extra_in, out, extra_out, d_nout);
+    ctx->launches++;
+    HS_CUDA_TRY(ctx, cudaGetLastError());
+    return HS_OK;
+  }
   unsigned int* tile_off = reinterpret_cast<unsigned int*>(ctx->d_scratch);
   k_filter_count<<<static_cast<int>(nb), HS_TPB, 0, ctx->stream>>>(xyz, n, axis, limit, tile_off, ctx->d_ticket, d_nout);
   ctx->launches++;

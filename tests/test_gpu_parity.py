@@ -450,7 +450,7 @@ def test_kth_small_and_degenerate(ctx, sel_mode):
     assert ctx.kth_largest(cl, 2, 5000) == np.float32(-2.5) and ctx.kth_smallest(cl, 2, 1) == np.float32(-2.5)
 
 
-def test_kth_and_remove_ceiling(ctx, sel_mode):
+def test_kth_and_remove_ceiling(ctx, sel_mode, flt_mode):
     rng = np.random.default_rng(13)
     n = 250_007
     xyz = rng.normal(size=(n, 3)).astype(np.float32) * 2
@@ -477,9 +477,33 @@ def test_kth_and_remove_ceiling(ctx, sel_mode):
         ctx.remove_ceiling(ctx.upload(xyz[:4]))
 
 
-def test_filter_le_order_preserving(ctx):
+# mode key 12: 0 = single pass (decoupled look-back), 1 = count pass + scatter pass
+@pytest.fixture(params=[0, 1], ids=["onepass", "twopass"])
+def flt_mode(ctx, request):
+    ctx.set_mode(12, request.param)
+    yield request.param
+    ctx.set_mode(12, 0)
+
+
+def test_filter_le_large_with_colours(ctx, flt_mode):
+    """1.5 M points = 367 claims of 4 tiles: look-back windows several deep; long runs where nothing / everything is kept"""
+    rng = np.random.default_rng(15)
+    n = 1_500_003
+    xyz = rng.normal(size=(n, 3)).astype(np.float32)
+    xyz[200_000:330_000, 1] = 9.0   # nothing kept
+    xyz[700_000:900_000, 1] = -9.0  # everything kept
+    col = rng.random((n, 3)).astype(np.float32)
+    cl, cc = ctx.upload(xyz), ctx.upload(col)
+    for _ in range(2):
+        out, cout = ctx.filter_le(cl, 1, 0.25, cc)
+        keep = xyz[:, 1] <= np.float32(0.25)
+        assert np.array_equal(out.download().view(np.uint32), xyz[keep].view(np.uint32))
+        assert np.array_equal(cout.download(), col[keep])
+
+
+def test_filter_le_order_preserving(ctx, flt_mode):
     rng = np.random.default_rng(14)
-    for n in (1, 5, 1024, 1025, 70_001):
+    for n in (1, 5, 1024, 1025, 4096, 4097, 70_001):
         xyz = rng.normal(size=(n, 3)).astype(np.float32)
         for axis, lim in ((0, 0.0), (2, -5.0), (1, 5.0)):
             out, _ = ctx.filter_le(ctx.upload(xyz), axis, lim)
