@@ -58,7 +58,7 @@ enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1, HS_MODE_EVAL_CONSUMER
        HS_MODE_PRODUCER_SLEEP = 6,  // packed-form evaluation kernel only: ns the producer sleeps between polls (tools)
        HS_MODE_PS_KERNEL = 7,   // per-plane sums: 0 = ring form (bulk-async tiles, warp-level flushes), 1 = all-Double form, 2 = direct-load Float chains
        HS_MODE_SEL_KERNEL = 8,  // k-th: 0 = 11/11/10-bit passes over compacted keys, 1 = four 8-bit passes over the cloud
-       HS_MODE_FILTER_KERNEL = 12,  // order-preserving filter: 0 = single pass (decoupled look-back), 1 = count pass + scatter pass
+       HS_MODE_FILTER_KERNEL = 12,  // order-preserving filter: 0 = count pass + scatter pass, 1 = single pass (decoupled look-back)
        HS_MODE_CC_CHUNKS = 11,  // connected components: slices of the edge list with a flatten in between (0 = default)
        HS_MODE_BP_KERNEL = 10,  // back-projection: 0 = single pass (decoupled look-back), 1 = count pass + scatter pass
        HS_MODE_NE_KERNEL = 9    // 6x6 record: 0 = throughput form (Float chains), 1 = all-Double form

@@ -270,7 +270,7 @@ k_filter_scatter(const float* __restrict__ xyz, int64_t n, int axis, float limit
   }
 }
 
-// Single-pass filter (default): the same compaction with the offsets from a decoupled look-back over claims of FL_SUPER tiles
+// Single-pass filter (mode key 12 = 1; measured no faster than the two passes at 100 M points, so not the default): the same compaction with the offsets from a decoupled look-back over claims of FL_SUPER tiles
 // (tile_lookback, k_common.cuh).  A claim's points are read once from HBM; the second read, for the scatter, comes from L2
 // (48 KB per claim).  12 + 12 kept bytes per point instead of 24 + 12 kept, and one launch less.
 #define FL_SUPER 4
@@ -417,7 +417,7 @@ int32_t launch_filter_le(hs_ctx* ctx, const float* xyz, int64_t n, int axis, flo
   int64_t nb = ntiles < static_cast<int64_t>(ctx->sm_count) * 8 ? ntiles : static_cast<int64_t>(ctx->sm_count) * 8;
   if (nb < 1) nb = 1;
   if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(ntiles + 1) * sizeof(unsigned long long))) return rc;
-  if (ctx->modes[HS_MODE_FILTER_KERNEL] != 1 && n > 0 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {  // single pass
+  if (ctx->modes[HS_MODE_FILTER_KERNEL] == 1 && n > 0 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {  // single pass (opt-in: measured no faster)
     unsigned long long* state = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
     const int64_t nsuper = (ntiles + FL_SUPER - 1) / FL_SUPER;
     HS_CUDA_TRY(ctx, cudaMemsetAsync(state, 0, static_cast<size_t>(nsuper) * sizeof(unsigned long long), ctx->stream));

@@ -477,8 +477,8 @@ def test_kth_and_remove_ceiling(ctx, sel_mode, flt_mode):
         ctx.remove_ceiling(ctx.upload(xyz[:4]))
 
 
-# mode key 12: 0 = single pass (decoupled look-back), 1 = count pass + scatter pass
-@pytest.fixture(params=[0, 1], ids=["onepass", "twopass"])
+# mode key 12: 0 = count pass + scatter pass, 1 = single pass (decoupled look-back)
+@pytest.fixture(params=[0, 1], ids=["twopass", "onepass"])
 def flt_mode(ctx, request):
     ctx.set_mode(12, request.param)
     yield request.param

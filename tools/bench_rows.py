@@ -155,13 +155,13 @@ if want("A12"):
     fn = lambda: ctx._chk(lib.hs_remove_ceiling(ctx.h, cloud.h, None, out_cloud.h, None, C.byref(n_out), C.byref(yl)))
     ctx.set_mode(12, 1)
     ms2 = timed(fn, reps=5)
-    report("A12", "hs_remove_ceiling (two-pass filter)", n, "pts", 16.0 + 12.0 + 12.0 * 0.8, ms2, True, note="k-th + count pass + scatter pass")
+    report("A12", "hs_remove_ceiling (single-pass filter)", n, "pts", 16.0 + 12.0 + 12.0 * 0.8, ms2, True, note="k-th + look-back compaction")
     ctx.set_mode(12, 0)
     ms = timed(fn, reps=5)
     kept = int((y <= yl.value).sum().item())
     o = out_buf[: 3 * kept].view(kept, 3)
     ok = n_out.value == kept and bool(torch.equal(o, pts[y <= yl.value]))
-    report("A12", "hs_remove_ceiling (single-pass filter)", n, "pts", 16.0 + 12.0 + 12.0 * kept / n, ms, bool(ok), note="k-th + count pass + scatter; output order preserved (checked bit-exact vs torch mask)")
+    report("A12", "hs_remove_ceiling (two-pass filter)", n, "pts", 16.0 + 12.0 + 12.0 * kept / n, ms, bool(ok), note="k-th + count pass + scatter; output order preserved (checked bit-exact vs torch mask)")
 
 if want("A1"):
     from housescan_b200 import synth
