@@ -604,3 +604,10 @@ def test_six_unpaired_planes_take_the_generic_path(ctx, room_small):
         ne_o = O.backproject_reduce6x6(frames, 160, 120, planes, intr, poses)
         assert np.array_equal(ne_g[:, 28], ne_o[:, 28])
         assert _rel(ne_g[:, :28], ne_o[:, :28], _ne_scale(ne_o)[:, :28]) < 1e-6
+
+
+def test_graft_entry_smoke():
+    """the driver's smoke(): one small invocation of the hot path on cuda:0 checked against the oracle"""
+    import __graft_entry__
+
+    __graft_entry__.smoke()
