@@ -193,7 +193,7 @@ k_bp_onepass(const uint16_t* __restrict__ depth, int64_t npx, int w, uint8_t* __
              unsigned int* counters /* [0] next super-tile, [1] blocks done; zero between launches */, float* __restrict__ xyz, int64_t* __restrict__ n_valid) {
   __shared__ unsigned int wsum[BP_SUPER][HS_TPB / 32];
   __shared__ __align__(16) uint16_t sraw[BP_SUPER * BP_TILE];
-  __shared__ __align__(16) float stage[BP_TILE * 3 + 4];
+  __shared__ __align__(16) float stage[(HS_TPB / 32) * (256 * 3 + 4)];
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_prefix;
   const int64_t nsuper = (npx + BP_SUPER * BP_TILE - 1) / (BP_SUPER * BP_TILE);
@@ -265,23 +265,29 @@ k_bp_onepass(const uint16_t* __restrict__ depth, int64_t npx, int w, uint8_t* __
       }
     }
     __syncthreads();
+    // ---- scatter: every warp stages ITS 256 pixels of a tile in its own slice of shared memory and writes its own run, so the
+    // tiles of the claim need no block-wide barrier at all (the compaction was barrier-bound with block-wide staging)
     int64_t pts0 = static_cast<int64_t>(s_prefix);  // points before the current tile
+    float* ws = stage + warp * (256 * 3 + 4);
 #pragma unroll 1
     for (int q = 0; q < BP_SUPER; ++q) {
-      unsigned int run = 0;
-      for (int u = 0; u < warp; ++u) run += wsum[q][u];
-      const int64_t dst0 = 3 * pts0;  // first float of the tile's run in xyz
+      unsigned int wbase = 0, tq = 0;
+#pragma unroll
+      for (int u = 0; u < HS_TPB / 32; ++u) { wbase += (u < warp) ? wsum[q][u] : 0u; tq += wsum[q][u]; }
+      const unsigned int cwq = wsum[q][warp];
+      const int64_t dst0 = 3 * (pts0 + wbase);  // first float of this warp's run in xyz
       const int a = static_cast<int>(dst0 & 3);
       const int64_t p0 = (t * BP_SUPER + q) * BP_TILE + 256 * warp + lane;
       int y, x;
       if (npx <= 0xffffffffll) { const unsigned int qq = static_cast<unsigned int>(p0) / static_cast<unsigned int>(w); y = static_cast<int>(qq); x = static_cast<int>(static_cast<unsigned int>(p0) - qq * static_cast<unsigned int>(w)); }
       else { y = static_cast<int>(p0 / w); x = static_cast<int>(p0 - static_cast<int64_t>(y) * w); }
+      unsigned int run = 0;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const unsigned int d = sraw[q * BP_TILE + 256 * warp + 32 * e + lane];
         const unsigned int bal = __ballot_sync(0xffffffffu, d != 0);
         if (d != 0) {
-          float* sp = stage + a + 3 * (run + __popc(bal & lt));
+          float* sp = ws + a + 3 * (run + __popc(bal & lt));
           sp[0] = div_rn_small(static_cast<float>(x), 10.0f, HS_RCP10);
           sp[1] = div_rn_small(static_cast<float>(y), 10.0f, HS_RCP10);
           sp[2] = __fsub_rn(div_rn_small(static_cast<float>(d), 20.0f, HS_RCP20), 30.0f);
@@ -290,23 +296,21 @@ k_bp_onepass(const uint16_t* __restrict__ depth, int64_t npx, int w, uint8_t* __
         x += 32;
         while (x >= w) { x -= w; ++y; }
       }
-      __syncthreads();
-      unsigned int tq = 0;
-      for (int u = 0; u < HS_TPB / 32; ++u) tq += wsum[q][u];
-      const int lo = a, hi = a + 3 * static_cast<int>(tq);
-      float* gbase = xyz + (dst0 - a);
+      __syncwarp();
+      const int lo = a, hi = a + 3 * static_cast<int>(cwq);  // the run in this warp's staging indices; global index = dst0 - a + s
+      float* gbase = xyz + (dst0 - a);                        // 16-byte aligned
       const int lo4 = (lo + 3) & ~3, hi4 = hi & ~3;
       if (lo4 < hi4) {
-        if (static_cast<int>(threadIdx.x) < lo4 - lo) gbase[lo + threadIdx.x] = stage[lo + threadIdx.x];
-        const float4* s4 = reinterpret_cast<const float4*>(stage);
+        if (lane < lo4 - lo) gbase[lo + lane] = ws[lo + lane];
+        const float4* s4 = reinterpret_cast<const float4*>(ws);
         float4* g4 = reinterpret_cast<float4*>(gbase);
-        for (int vv = (lo4 >> 2) + threadIdx.x; vv < (hi4 >> 2); vv += HS_TPB) __stcs(g4 + vv, s4[vv]);
-        if (static_cast<int>(threadIdx.x) < hi - hi4) gbase[hi4 + threadIdx.x] = stage[hi4 + threadIdx.x];
+        for (int vv = (lo4 >> 2) + lane; vv < (hi4 >> 2); vv += 32) __stcs(g4 + vv, s4[vv]);
+        if (lane < hi - hi4) gbase[hi4 + lane] = ws[hi4 + lane];
       } else {
-        for (int qq = lo + threadIdx.x; qq < hi; qq += HS_TPB) gbase[qq] = stage[qq];
+        for (int qq = lo + lane; qq < hi; qq += 32) gbase[qq] = ws[qq];
       }
       pts0 += tq;
-      __syncthreads();  // the staging buffer is reused by the next tile of the claim
+      __syncwarp();  // the slice is reused by the warp's next tile
     }
   }
   if (threadIdx.x == 0) {  // the last block to run out of tiles re-arms the counters for the next launch on this stream

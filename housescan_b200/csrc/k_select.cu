@@ -233,14 +233,37 @@ __device__ __forceinline__ void store_run(const float* stage, int a, int nfloats
   }
 }
 
+// warp-private flavour of store_run: the 32 lanes of one warp write the run staged in the warp's own slice
+__device__ __forceinline__ void store_run_warp(const float* ws, int a, int nfloats, float* __restrict__ out, int64_t dst0, int lane) {
+  const int lo = a, hi = a + nfloats;
+  float* gbase = out + (dst0 - a);
+  const int lo4 = (lo + 3) & ~3, hi4 = hi & ~3;
+  if (lo4 < hi4) {
+    if (lane < lo4 - lo) gbase[lo + lane] = ws[lo + lane];
+    const float4* s4 = reinterpret_cast<const float4*>(ws);
+    float4* g4 = reinterpret_cast<float4*>(gbase);
+    for (int v = (lo4 >> 2) + lane; v < (hi4 >> 2); v += 32) __stcs(g4 + v, s4[v]);
+    if (lane < hi - hi4) gbase[hi4 + lane] = ws[hi4 + lane];
+  } else {
+    for (int q = lo + lane; q < hi; q += 32) gbase[q] = ws[q];
+  }
+}
+
+// Every warp stages the kept points of ITS 128 points in its own slice of shared memory and writes its own run: one block-wide
+// barrier per tile (for the warp offsets) instead of three — the compaction was barrier-bound with block-wide staging.
 __global__ void __launch_bounds__(HS_TPB)
 k_filter_scatter(const float* __restrict__ xyz, int64_t n, int axis, float limit, const unsigned int* __restrict__ tile_off,
                  const float* __restrict__ extra_in, float* __restrict__ out, float* __restrict__ extra_out) {
-  __shared__ unsigned int wsum[HS_TPB / 32];
-  __shared__ __align__(16) float stage[FL_TILE * 3 + 4];
-  __shared__ __align__(16) float stage2[FL_TILE * 3 + 4];
+  constexpr int NW = HS_TPB / 32, SLICE = 128 * 3 + 4;  // 388 floats = 97 x 16 B: slices stay 16-byte aligned
+  __shared__ unsigned int wsum[2][NW];
+  __shared__ __align__(16) float stage[NW * SLICE];
+  __shared__ __align__(16) float stage2[NW * SLICE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ws = stage + warp * SLICE;
+  float* ws2 = stage2 + warp * SLICE;
   const int64_t ntiles = (n + FL_TILE - 1) / FL_TILE;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  int par = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, par ^= 1) {
     const int64_t i0 = t * FL_TILE + 4 * threadIdx.x;
     Pts4 p, q;
     const int m = load_tile_group(xyz, n, i0, p);
@@ -249,24 +272,32 @@ k_filter_scatter(const float* __restrict__ xyz, int64_t n, int axis, float limit
     unsigned int c = 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) { keep[e] = (e < m) && ((axis == 0 ? p.x[e] : (axis == 1 ? p.y[e] : p.z[e])) <= limit); c += keep[e]; }
-    const int64_t dst0 = 3 * static_cast<int64_t>(tile_off[t]);
-    const int a = static_cast<int>(dst0 & 3);
-    const unsigned int pos = block_exclusive_prefix(c, wsum);
-    unsigned int total = 0;
+    unsigned int incl = c;
 #pragma unroll
-    for (int w = 0; w < HS_TPB / 32; ++w) total += wsum[w];
-    int sp = a + 3 * static_cast<int>(pos);
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    const unsigned int cw = __shfl_sync(0xffffffffu, incl, 31);  // kept points of this warp
+    if (lane == 0) wsum[par][warp] = cw;
+    __syncthreads();  // the only block-wide barrier of the tile (wsum alternates, so the next tile cannot overwrite it early)
+    unsigned int wbase = 0;
+#pragma unroll
+    for (int u = 0; u < NW; ++u) wbase += (u < warp) ? wsum[par][u] : 0u;
+    const int64_t dst0 = 3 * (static_cast<int64_t>(tile_off[t]) + wbase);
+    const int a = static_cast<int>(dst0 & 3);
+    int sp = a + 3 * static_cast<int>(incl - c);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       if (keep[e]) {
-        stage[sp] = p.x[e]; stage[sp + 1] = p.y[e]; stage[sp + 2] = p.z[e];
-        if (extra_in) { stage2[sp] = q.x[e]; stage2[sp + 1] = q.y[e]; stage2[sp + 2] = q.z[e]; }
+        ws[sp] = p.x[e]; ws[sp + 1] = p.y[e]; ws[sp + 2] = p.z[e];
+        if (extra_in) { ws2[sp] = q.x[e]; ws2[sp + 1] = q.y[e]; ws2[sp + 2] = q.z[e]; }
         sp += 3;
       }
-    __syncthreads();
-    store_run(stage, a, 3 * static_cast<int>(total), out, dst0);
-    if (extra_in) store_run(stage2, a, 3 * static_cast<int>(total), extra_out, dst0);
-    __syncthreads();
+    __syncwarp();
+    store_run_warp(ws, a, 3 * static_cast<int>(cw), out, dst0, lane);
+    if (extra_in) store_run_warp(ws2, a, 3 * static_cast<int>(cw), extra_out, dst0, lane);
+    __syncwarp();  // the slice is reused by the warp's next tile
   }
 }
 
