@@ -188,26 +188,41 @@ __device__ __forceinline__ int load_tile_group(const float* __restrict__ xyz, in
   return m;
 }
 
+// A block takes FL_CT consecutive tiles per round: their loads are all in flight before the first count is reduced, and the
+// counts of two tiles share one shuffle tree (each fits 16 bits), so a round costs one barrier pair for FL_CT * 1024 points.
+#define FL_CT 4
 __global__ void __launch_bounds__(HS_TPB)
 k_filter_count(const float* __restrict__ xyz, int64_t n, int axis, float limit, unsigned int* __restrict__ tile_off,
                unsigned int* ticket, int64_t* __restrict__ n_out) {
-  __shared__ unsigned int wsum[HS_TPB / 32];
+  __shared__ unsigned int wsum[FL_CT / 2][HS_TPB / 32];
   const int64_t ntiles = (n + FL_TILE - 1) / FL_TILE;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t i0 = t * FL_TILE + 4 * threadIdx.x;
-    Pts4 p;
-    const int m = load_tile_group(xyz, n, i0, p);
-    unsigned int c = 0;
+  const int64_t nrounds = (ntiles + FL_CT - 1) / FL_CT;
+  for (int64_t rd = blockIdx.x; rd < nrounds; rd += gridDim.x) {
+    const int64_t t0 = rd * FL_CT;
+    unsigned int c[FL_CT];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) c += (e < m) && ((axis == 0 ? p.x[e] : (axis == 1 ? p.y[e] : p.z[e])) <= limit);
+    for (int q = 0; q < FL_CT; ++q) {
+      const int64_t i0 = (t0 + q) * FL_TILE + 4 * threadIdx.x;
+      Pts4 p;
+      const int m = load_tile_group(xyz, n, i0, p);
+      c[q] = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+      for (int e = 0; e < 4; ++e) c[q] += (e < m) && ((axis == 0 ? p.x[e] : (axis == 1 ? p.y[e] : p.z[e])) <= limit);
+    }
+#pragma unroll
+    for (int q = 0; q < FL_CT / 2; ++q) {
+      unsigned int cc = c[2 * q] | (c[2 * q + 1] << 16);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
+      if ((threadIdx.x & 31) == 0) wsum[q][threadIdx.x >> 5] = cc;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int s = 0;
-      for (int w = 0; w < HS_TPB / 32; ++w) s += wsum[w];
-      tile_off[t] = s;
+    if (threadIdx.x < FL_CT / 2) {
+      unsigned int sum = 0;
+      for (int w = 0; w < HS_TPB / 32; ++w) sum += wsum[threadIdx.x][w];
+      const int64_t t = t0 + 2 * threadIdx.x;
+      if (t < ntiles) tile_off[t] = sum & 0xffffu;
+      if (t + 1 < ntiles) tile_off[t + 1] = sum >> 16;
     }
     __syncthreads();
   }
@@ -459,7 +474,8 @@ int32_t launch_filter_le(hs_ctx* ctx, const float* xyz, int64_t n, int axis, flo
     return HS_OK;
   }
   unsigned int* tile_off = reinterpret_cast<unsigned int*>(ctx->d_scratch);
-  k_filter_count<<<static_cast<int>(nb), HS_TPB, 0, ctx->stream>>>(xyz, n, axis, limit, tile_off, ctx->d_ticket, d_nout);
+  const int64_t nbc = std::max<int64_t>(1, std::min<int64_t>((ntiles + FL_CT - 1) / FL_CT, static_cast<int64_t>(ctx->sm_count) * 8));
+  k_filter_count<<<static_cast<int>(nbc), HS_TPB, 0, ctx->stream>>>(xyz, n, axis, limit, tile_off, ctx->d_ticket, d_nout);
   ctx->launches++;
   k_filter_scatter<<<static_cast<int>(nb), HS_TPB, 0, ctx->stream>>>(xyz, n, axis, limit, tile_off, extra_in, out, extra_out);
   ctx->launches++;
