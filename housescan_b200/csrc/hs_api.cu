@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <vector>
 
 #include "../host/hs_host.hpp"
@@ -720,7 +721,9 @@ int32_t hs_pcd_info(const char* path, int64_t* n_points, int32_t* has_rgb, int32
   std::string err;
   hs::PcdHeader h;
   int f[4];
-  if (!hs::read_file(path, &buf, &err) || !hs::pcd_parse_header(buf.data(), buf.size(), &h, &err) || !hs::pcd_layout(h, &f[0], &f[1], &f[2], &f[3], &err)) return HS_EIO;
+  try {
+    if (!hs::read_file(path, &buf, &err) || !hs::pcd_parse_header(buf.data(), buf.size(), &h, &err) || !hs::pcd_layout(h, &f[0], &f[1], &f[2], &f[3], &err)) return HS_EIO;
+  } catch (const std::exception&) { return HS_ENOMEM; }
   if (n_points) *n_points = h.points;
   if (has_rgb) *has_rgb = f[3] >= 0;
   if (data_kind) *data_kind = h.data_kind;
@@ -755,10 +758,12 @@ int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, h
   if (!path || !cloud_out) { ctx->err = "hs_cloud_from_pcd: bad arguments"; return HS_EINVAL; }
   *cloud_out = nullptr;
   if (colors_out) *colors_out = nullptr;
-  PcdStaged st;
-  std::string err;
-  if (!pcd_stage(path, &st, &err)) { ctx->err = err; return HS_EIO; }
-  return staged_to_device(ctx, st, st.h.points, path, cloud_out, colors_out);
+  try {  // nothing may unwind through the C ABI (a hostile header can ask for any amount of memory)
+    PcdStaged st;
+    std::string err;
+    if (!pcd_stage(path, &st, &err)) { ctx->err = err; return HS_EIO; }
+    return staged_to_device(ctx, st, st.h.points, path, cloud_out, colors_out);
+  } catch (const std::exception& e) { ctx->err = std::string("hs_cloud_from_pcd: ") + e.what(); return HS_ENOMEM; }
 }
 
 int32_t hs_cloud_from_ply(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out) {
@@ -766,6 +771,7 @@ int32_t hs_cloud_from_ply(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, h
   if (!path || !cloud_out) { ctx->err = "hs_cloud_from_ply: bad arguments"; return HS_EINVAL; }
   *cloud_out = nullptr;
   if (colors_out) *colors_out = nullptr;
+  try {
   PcdStaged st;
   hs::PlyHeader h;
   std::string err;
@@ -788,6 +794,7 @@ int32_t hs_cloud_from_ply(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, h
     st.rgb_bytes = 1;
   }
   return staged_to_device(ctx, st, h.n, path, cloud_out, colors_out);
+  } catch (const std::exception& e) { ctx->err = std::string("hs_cloud_from_ply: ") + e.what(); return HS_ENOMEM; }
 }
 
 int32_t hs_write_pcd(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb, const char* path) {
@@ -834,7 +841,10 @@ int32_t hs_load_room(hs_ctx* ctx, const char* dir, hs_cloud** cloud_out, hs_clou
   std::vector<float> means(static_cast<size_t>(K) * 3);
   for (int k = 0; k < K; ++k) {  // planesFromDir, Main.hs:1391-1404
     std::string err;
-    if (!pcd_host_mean((d + "/cloud_plane_hull" + std::to_string(k) + ".pcd").c_str(), &means[3 * k], &err)) return fail(HS_EIO, err);
+    bool ok = false;
+    try { ok = pcd_host_mean((d + "/cloud_plane_hull" + std::to_string(k) + ".pcd").c_str(), &means[3 * k], &err); }
+    catch (const std::exception& e) { err = e.what(); }
+    if (!ok) return fail(HS_EIO, err);
   }
   double m[3];
   float md;

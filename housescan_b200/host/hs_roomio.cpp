@@ -143,14 +143,16 @@ bool pcd_parse_header(const char* buf, size_t len, PcdHeader* h, std::string* er
   if (h->count.size() != nf) { *err = "PCD: COUNT does not match FIELDS"; return false; }
   if (h->points < 0) h->points = h->width * h->height;
   if (h->points < 0) { *err = "PCD: no POINTS / WIDTH x HEIGHT"; return false; }
+  if (static_cast<uint64_t>(h->points) > len) { *err = "PCD: POINTS exceeds the file size"; return false; }  // every point takes >= 1 byte
   h->field_offset.resize(nf);
   int off = 0;
   for (size_t f = 0; f < nf; ++f) {
     if (h->size[f] != 1 && h->size[f] != 2 && h->size[f] != 4 && h->size[f] != 8) { *err = "PCD: bad SIZE"; return false; }
-    if (h->count[f] < 0) { *err = "PCD: bad COUNT"; return false; }
+    if (h->count[f] < 0 || h->count[f] > (1 << 16)) { *err = "PCD: bad COUNT"; return false; }
     h->field_offset[f] = off;
     off += h->size[f] * h->count[f];
   }
+  if (off <= 0 || off > (1 << 24)) { *err = "PCD: bad record size"; return false; }
   h->point_step = off;
   h->data_offset = i;
   return true;
@@ -302,6 +304,7 @@ bool ply_parse_header(const char* buf, size_t len, PlyHeader* h, std::string* er
     } else if (key == "end_header") done = true;
   }
   if (!done || element < 0 || h->n < 0) { *err = "PLY: incomplete header"; return false; }
+  if (static_cast<uint64_t>(h->n) > len) { *err = "PLY: vertex count exceeds the file size"; return false; }
   h->data_offset = i;
   return true;
 }

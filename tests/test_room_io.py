@@ -237,3 +237,34 @@ def test_ply_reader_and_file_transformer(ctx, tmp_path):
     assert bcol is None and np.array_equal(back.download().view(np.uint32), want.view(np.uint32))
     xo, _ = O.pcd_load(str(tmp_path / "plain_out.pcd"))  # the files we write are readable by the independent loader
     assert np.array_equal(xo.view(np.uint32), want.view(np.uint32))
+
+
+def test_pcd_header_fuzz_never_crashes(built_lib, tmp_path):
+    """hostile / damaged headers: the parser answers with a status, whatever the numbers claim (no crash, no giant allocation)"""
+    rng = np.random.default_rng(99)
+    good = tmp_path / "good.pcd"
+    write_pcd(str(good), np.arange(30, dtype=np.float32).reshape(10, 3), rgb=np.zeros((10, 3), int), kind="binary")
+    raw = good.read_bytes()
+    head_end = raw.index(b"DATA binary\n") + len(b"DATA binary\n")
+    cases = [raw[:head_end].replace(b"POINTS 10", b"POINTS 99999999999999") + raw[head_end:],
+             raw[:head_end].replace(b"COUNT 1 1 1 1", b"COUNT 1 1 1 2000000000") + raw[head_end:],
+             raw[:head_end].replace(b"SIZE 4 4 4 4", b"SIZE 4 4 4 3") + raw[head_end:],
+             raw[:head_end].replace(b"POINTS 10", b"POINTS -5") + raw[head_end:],
+             raw[:head_end].replace(b"DATA binary", b"DATA zip") + raw[head_end:],
+             raw[:40], b"", b"\n\n\n", raw[:head_end]]
+    for _ in range(200):
+        b = bytearray(raw)
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(0, head_end))] = int(rng.integers(32, 127))
+        cases.append(bytes(b))
+    ok = bad = 0
+    for i, c in enumerate(cases):
+        p = tmp_path / f"fz{i}.pcd"
+        p.write_bytes(c)
+        try:
+            n, _, _ = RoomIO.pcdInfo(str(p))
+            assert 0 <= n <= len(c)
+            ok += 1
+        except hb.HsError:
+            bad += 1
+    assert bad >= 8 and ok + bad == len(cases)
