@@ -611,3 +611,56 @@ def test_graft_entry_smoke():
     import __graft_entry__
 
     __graft_entry__.smoke()
+
+
+# ------------------------------------------------------------------ config 3 end to end: wall alignment of an apartment
+def test_wall_alignment_pipeline_on_gpu(ctx):
+    """BASELINE configs[2] in small: per-room, per-wall point reductions on the GPU (hs_plane_sums) feed the reference's
+    optimizeRoomPositions (Main.hs:2089-2168: desired offsets -> connected components (GPU) -> lstSqDistances).  The room
+    translations must agree with the same pipeline fed by the oracle's sums to 1e-6, and the aligned rooms end `Opposite 0.1`
+    apart, i.e. the facing walls of neighbouring rooms sit 0.1 m from each other."""
+    from housescan_b200 import FitCuboidBFGS
+    from housescan_b200.rooms import X, Z, Opposite, optimizeRoomPositions
+
+    rng = np.random.default_rng(33)
+    grid = [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1)]  # an L-shaped flat: X neighbours and Z neighbours
+    params = np.zeros((len(grid), 10))
+    clouds, offs = [], [0]
+    for r, (gx, gz) in enumerate(grid):
+        params[r, :3] = np.array([6.0 * gx, 0.0, 6.0 * gz]) + rng.uniform(-0.2, 0.2, size=3)
+        params[r, 3:6] = np.array([5.0, 2.6, 4.0]) + rng.uniform(-0.3, 0.3, size=3)
+        params[r, 6:] = [1.0, 0.0, 0.0, 0.0]
+        pts, _ = synth.cuboid_room_cloud(20_003, params[r], sigma=0.003, rng=rng)
+        clouds.append(pts)
+        offs.append(offs[-1] + len(pts))
+    xyz, offs = np.concatenate(clouds), np.array(offs, np.int64)
+    planes = np.stack([O.planes_from_cuboid(params[r]) for r in range(len(grid))])
+    sums_g = ctx.plane_sums(ctx.upload(xyz), offs, planes, 6)
+    sums_o = O.plane_sums(xyz, offs, planes, 6)
+    assert np.array_equal(sums_g[..., 0], sums_o[..., 0])
+    # the wall of room r on its +axis / -axis side: makePlanesFromCuboid (Main.hs:1855-1874) gives that wall the normal +/- e_axis
+    def wall(r, axis, sign):
+        return int(np.argmax(sign * planes[r][:, axis]))
+    conns = []
+    for a, (ga, za) in enumerate(grid):
+        for b, (gb, zb) in enumerate(grid):
+            if (gb, zb) == (ga + 1, za):
+                conns.append((X, Opposite(0.1), (a, wall(a, 0, +1)), (b, wall(b, 0, -1))))
+            if (gb, zb) == (ga, za + 1):
+                conns.append((Z, Opposite(0.1), (a, wall(a, 2, +1)), (b, wall(b, 2, -1))))
+    conns = conns[::-1]  # connectWalls conses: newest first (Main.hs:2061)
+    corner_mean = lambda r: FitCuboidBFGS.cuboidFromParams(params[r]).mean(axis=0)
+    ids = list(range(len(grid)))
+    res = []
+    for sums in (sums_g, sums_o):
+        pm = lambda r, w, s=sums: s[r, w, 3:6] / s[r, w, 0]
+        moved, log = optimizeRoomPositions(ids, conns, pm, corner_mean, ctx=ctx)
+        res.append(np.stack([moved[r] for r in ids]))
+    assert np.allclose(res[0], res[1], rtol=1e-6, atol=1e-6)
+    assert any("Aligning the X" in l for l in log) and any("Aligning the Z" in l for l in log)
+    # after the move the facing walls are 0.1 m apart (to the noise of the synthetic walls)
+    pm = lambda r, w: sums_g[r, w, 3:6] / sums_g[r, w, 0] + res[0][r]
+    for axis, _, (r1, w1), (r2, w2) in conns:
+        gap = abs(float(pm(r2, w2)[axis] - pm(r1, w1)[axis]))
+        assert abs(gap - 0.1) < 5e-3, (axis, r1, r2, gap)
+    assert np.abs(res[0]).max() < 3.0  # rooms close their 1-2 m gaps; nobody jumps across a neighbour (6 m grid)
