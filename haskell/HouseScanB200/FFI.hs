@@ -87,3 +87,7 @@ foreign import ccall unsafe "hs_transform_from_text" c_transform_from_text :: CS
 foreign import ccall safe "hs_cloud_from_ply"
   c_cloud_from_ply :: Ptr HsCtx -> CString -> Ptr (Ptr HsCloud) -> Ptr (Ptr HsCloud) -> IO Int32
 foreign import ccall safe "hs_write_pcd" c_write_pcd :: Ptr HsCtx -> Ptr HsCloud -> Ptr Word8 -> CString -> IO Int32
+-- sharded k-th (point ranges on several GPUs, SURVEY.md 8e): one radix pass per call, histograms summed by the caller
+foreign import ccall safe "hs_kth_shard_pass"
+  c_kth_shard_pass :: Ptr HsCtx -> Ptr HsCloud -> Int32 -> Int32 -> Word32 -> Word32 -> Ptr Word32 -> IO Int32
+foreign import ccall unsafe "hs_kth_float_of_key" c_kth_float_of_key :: Word32 -> CFloat

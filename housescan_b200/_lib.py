@@ -83,6 +83,9 @@ SIGNATURES = {
     "hs_transform_from_text": (i32, [C.c_char_p, i64, vp]),
     "hs_cloud_from_ply": (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(vp)]),
     "hs_write_pcd": (i32, [vp, vp, vp, C.c_char_p]),
+    "hs_kth_shard_pass": (i32, [vp, vp, i32, i32, u32, u32, vp]),
+    "hs_kth_key_of_float": (u32, [f32]),
+    "hs_kth_float_of_key": (f32, [u32]),
     "hs_version": (C.c_char_p, []),
 }
 

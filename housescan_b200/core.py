@@ -245,6 +245,12 @@ class Context:
         self._chk(self.lib.hs_kth_smallest(self.h, cloud.h, axis, k, C.byref(out)))
         return np.float32(out.value)
 
+    def kth_shard_pass(self, cloud: Cloud, axis: int, pass_no: int, prefix: int, mask: int) -> np.ndarray:
+        """one radix pass of the sharded k-th over this rank's points: local histogram (2048 bins) of the pass's digit"""
+        hist = np.zeros(2048, np.uint32)
+        self._chk(self.lib.hs_kth_shard_pass(self.h, cloud.h, axis, pass_no, prefix, mask, ptr(hist)))
+        return hist
+
     def filter_le(self, cloud: Cloud, axis: int, limit: float, colors: Cloud | None = None):
         out = self.alloc(len(cloud))
         cout = self.alloc(len(cloud)) if colors is not None else None

@@ -612,6 +612,24 @@ static int32_t kth_impl(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_
 int32_t hs_kth_largest(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_t k, float* out) { HS_LOCK(ctx); return kth_impl(ctx, cloud, axis, k, true, out); }
 int32_t hs_kth_smallest(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_t k, float* out) { HS_LOCK(ctx); return kth_impl(ctx, cloud, axis, k, false, out); }
 
+// sharded k-th: one pass = this rank's histogram of the next digit; the caller sums the histograms of all ranks
+// (one all-reduce of 2048 counters per pass), picks the digit and calls the next pass with the extended (prefix, mask)
+int32_t hs_kth_shard_pass(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int32_t pass, uint32_t prefix, uint32_t mask, uint32_t* hist_out) {
+  HS_LOCK(ctx);
+  if (!cloud || !hist_out || axis < 0 || axis > 2 || pass < 0 || pass > 2) HS_FAIL(ctx, HS_EINVAL, "hs_kth_shard_pass: bad arguments");
+  if (cloud->n >= (1ll << 32)) HS_FAIL(ctx, HS_EINVAL, "hs_kth_shard_pass: at most 2^32 - 1 points per shard");
+  if (cloud->n == 0) { std::memset(hist_out, 0, sizeof(uint32_t) * 2048); return HS_OK; }  // an empty shard adds nothing
+  uint32_t* d_buf = nullptr;
+  HS_CUDA_TRY(ctx, cudaMalloc(&d_buf, sizeof(uint32_t) * 2048));
+  int32_t rc = launch_kth_shard_pass(ctx, cloud->d, cloud->n, axis, pass, prefix, mask, d_buf);
+  if (rc == HS_OK) rc = copy_d2h_sync(ctx, hist_out, d_buf, sizeof(uint32_t) * 2048);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_buf);
+  return rc;
+}
+uint32_t hs_kth_key_of_float(float v) { uint32_t b; std::memcpy(&b, &v, 4); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+float hs_kth_float_of_key(uint32_t u) { const uint32_t b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u; float v; std::memcpy(&v, &b, 4); return v; }
+
 static int32_t filter_impl(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, float limit, const hs_cloud* colors, hs_cloud* out, hs_cloud* colors_out, int64_t* n_out) {
   if (!cloud || !out || axis < 0 || axis > 2) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: bad arguments");
   if (out->cap < cloud->n || out->d == cloud->d) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: output cloud too small or aliases the input");

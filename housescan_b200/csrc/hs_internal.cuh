@@ -121,6 +121,7 @@ int32_t launch_pcd_unpack(hs_ctx* ctx, const uint8_t* d_raw, int64_t n, const in
 
 int32_t launch_cc(hs_ctx* ctx, const uint32_t* d_src, const uint32_t* d_dst, int64_t E, uint32_t N, uint32_t* d_label);
 
+int32_t launch_kth_shard_pass(hs_ctx* ctx, const float* xyz, int64_t n, int axis, int pass, uint32_t prefix, uint32_t mask, uint32_t* d_hist_out /* 2048 */);
 int32_t launch_kth(hs_ctx* ctx, const float* xyz, int64_t n, int axis, int64_t k, bool largest, float* d_out);
 int32_t launch_filter_le(hs_ctx* ctx, const float* xyz, int64_t n, int axis, float limit, const float* extra_in, float* out,
                          float* extra_out, int64_t* d_nout);

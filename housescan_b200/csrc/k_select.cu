@@ -87,6 +87,7 @@ __device__ __forceinline__ void sel2_finish(unsigned int* sh, int shift, int bit
   __syncthreads();
   for (int b = threadIdx.x; b < nbins; b += HS_TPB)
     if (sh[b]) atomicAdd(&st->hist[b], sh[b]);
+  if (!out) return;  // sharded mode: the digit is picked on the host after the histograms of all ranks are summed
   if (!last_block_arrives(ticket, gridDim.x)) return;
   // scan order: descending bins for the k-th largest, ascending for the k-th smallest; thread t owns 8 consecutive bins of it
   unsigned int c[SEL_BINS / HS_TPB], mine = 0;
@@ -414,6 +415,32 @@ k_filter_onepass(const float* __restrict__ xyz, int64_t n, int axis, float limit
 }  // namespace hsk
 
 using namespace hsk;
+
+// One radix pass of the sharded k-th: the local histogram of the pass's digit over this rank's points, restricted to
+// the keys that match (prefix, mask).  Pass 0 also builds the dense key array, which stays in the ctx scratch for passes 1 and 2.
+int32_t launch_kth_shard_pass(hs_ctx* ctx, const float* xyz, int64_t n, int axis, int pass, uint32_t prefix, uint32_t mask, uint32_t* d_hist_out) {
+  const size_t keys_off = (sizeof(SelState2) + 255) & ~static_cast<size_t>(255);
+  if (int32_t rc = hs_ensure_scratch(ctx, keys_off + static_cast<size_t>(n) * 4 + 16)) return rc;
+  SelState2* st = reinterpret_cast<SelState2*>(ctx->d_scratch);
+  unsigned int* keys = reinterpret_cast<unsigned int*>(ctx->d_scratch + keys_off);
+  SelState2 head;  // prefix, mask, k_rem: only the first 16 bytes travel; the histogram is zeroed on the device
+  head.prefix = prefix; head.mask = mask; head.k_rem = 0;
+  HS_CUDA_TRY(ctx, cudaMemsetAsync(st, 0, sizeof(SelState2), ctx->stream));
+  HS_CUDA_TRY(ctx, cudaMemcpyAsync(st, &head, 16, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `head` lives on this stack frame
+  int64_t nb = ((n >> 2) + HS_TPB - 1) / HS_TPB;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  const int g = static_cast<int>(nb);
+  if (pass == 0) k_sel2_first<true><<<g, HS_TPB, 0, ctx->stream>>>(xyz, n, axis, keys, st, ctx->d_ticket, nullptr);
+  else if (pass == 1) k_sel2_next<true><<<g, HS_TPB, 0, ctx->stream>>>(keys, n, 10, 11, st, ctx->d_ticket, nullptr);
+  else k_sel2_next<true><<<g, HS_TPB, 0, ctx->stream>>>(keys, n, 0, 10, st, ctx->d_ticket, nullptr);
+  ctx->launches++;
+  HS_CUDA_TRY(ctx, cudaGetLastError());
+  HS_CUDA_TRY(ctx, cudaMemcpyAsync(d_hist_out, st->hist, sizeof(unsigned int) * SEL_BINS, cudaMemcpyDeviceToDevice, ctx->stream));
+  return HS_OK;
+}
 
 int32_t launch_kth(hs_ctx* ctx, const float* xyz, int64_t n, int axis, int64_t k, bool largest, float* d_out) {
   if (ctx->modes[HS_MODE_SEL_KERNEL] != 1 && n < (1ll << 32) && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {

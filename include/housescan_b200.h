@@ -178,6 +178,14 @@ HS_API int32_t hs_kth_largest(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, 
 HS_API int32_t hs_kth_smallest(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_t k, float* out);
 /* order-preserving V.filter ((<= limit) . component axis).  `colors` (the ManyColors Vector Vec3 of Main.hs:112-115, same
  * length as the cloud) is filtered by the same predicate on the POINTS (V.ifilter, Main.hs:2664) when given. */
+/* Sharded k-th (point ranges on several GPUs).  One call = one MSB radix pass over THIS rank's points:
+ * hist_out[2048] is the local histogram of the pass's digit (pass 0: bits 31..21, 1: bits 20..10, 2: bits 9..0 of the order-
+ * preserving key image) over the keys with (key & mask) == prefix.  The caller sums the histograms of all ranks (one all-reduce
+ * of 2048 counters per pass), picks the digit that holds the k-th key, extends (prefix, mask) and calls the next pass; after
+ * pass 2 the prefix is the key of the k-th value.  Same semantics as kthLargestBy / kthSmallestBy (VectorUtil.hs:11-19). */
+HS_API int32_t hs_kth_shard_pass(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int32_t pass, uint32_t prefix, uint32_t mask, uint32_t* hist_out);
+HS_API uint32_t hs_kth_key_of_float(float v);   /* order-preserving uint image of a Float key */
+HS_API float hs_kth_float_of_key(uint32_t key);
 HS_API int32_t hs_filter_le(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, float limit, const hs_cloud* colors_or_null,
                             hs_cloud* cloud_out, hs_cloud* colors_out_or_null, int64_t* n_out);
 HS_API int32_t hs_remove_ceiling(hs_ctx* ctx, const hs_cloud* cloud, const hs_cloud* colors_or_null, hs_cloud* cloud_out,

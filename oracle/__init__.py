@@ -750,3 +750,20 @@ def load_room(directory):
     means = np.stack([point_mean_f32seq(pcd_load(_os.path.join(directory, f"cloud_plane_hull{k}.pcd"))[0]) for k in range(len(planes))])
     center = point_mean_f64(xyz).astype(np.float32)
     return xyz, cols, make_inward_facing(center, means, planes)
+
+
+# ------------------------------------------------------------------ sharded k-th: one radix pass over a shard
+def kth_key_image(keys):
+    """order-preserving uint32 image of float32 keys (negative: all bits flipped; non-negative: sign bit set)"""
+    b = np.ascontiguousarray(keys, np.float32).view(np.uint32)
+    return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+
+def kth_shard_hist(keys, pass_no, prefix, mask):
+    shift, bits = ((21, 11), (10, 11), (0, 10))[pass_no]
+    u = kth_key_image(keys)
+    sel = u[(u & np.uint32(mask)) == np.uint32(prefix)]
+    h = np.zeros(2048, np.uint32)
+    d = (sel >> np.uint32(shift)) & np.uint32((1 << bits) - 1)
+    np.add.at(h, d, 1)
+    return h

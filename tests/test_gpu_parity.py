@@ -664,3 +664,36 @@ def test_wall_alignment_pipeline_on_gpu(ctx):
         gap = abs(float(pm(r2, w2)[axis] - pm(r1, w1)[axis]))
         assert abs(gap - 0.1) < 5e-3, (axis, r1, r2, gap)
     assert np.abs(res[0]).max() < 3.0  # rooms close their 1-2 m gaps; nobody jumps across a neighbour (6 m grid)
+
+
+def test_sharded_kth_passes_on_gpu(ctx):
+    """hs_kth_shard_pass: the three radix passes of the sharded k-th on one rank, and two 'ranks' emulated by two
+    clouds whose histograms are added by hand, against the sorted keys; histograms bit-exact against the oracle's"""
+    from housescan_b200 import VectorUtil
+
+    rng = np.random.default_rng(23)
+    n = 200_005
+    xyz = (rng.normal(size=(n, 3)) * 2).astype(np.float32)
+    xyz[rng.integers(0, n, 3000), 1] = np.float32(-0.75)
+    xyz[:4, 1] = [0.0, -0.0, 2e38, -2e38]
+    cl = ctx.upload(xyz)
+    srt = np.sort(xyz[:, 1])
+    for k in (1, n // 5, n // 2, n):
+        assert VectorUtil.kthLargestBySharded(1, k, cl) == srt[::-1][k - 1] == ctx.kth_largest(cl, 1, k)
+        assert VectorUtil.kthSmallestBySharded(1, k, cl) == srt[k - 1]
+    h = ctx.kth_shard_pass(cl, 1, 0, 0, 0)
+    assert np.array_equal(h, O.kth_shard_hist(xyz[:, 1], 0, 0, 0)) and int(h.sum()) == n
+    # two shards, histograms summed by hand
+    cut = 80_004
+    a, b = ctx.upload(xyz[:cut]), ctx.upload(xyz[cut:])
+    ctx_b = hb.Context(0)  # every rank has its own context (and key scratch)
+    try:
+        b = ctx_b.upload(xyz[cut:])
+        fn = lambda p, pre, m: ctx.kth_shard_pass(a, 1, p, pre, m).astype(np.int64) + ctx_b.kth_shard_pass(b, 1, p, pre, m).astype(np.int64)
+        for k in (1, 777, n // 5, n):
+            assert VectorUtil.kth_sharded(fn, k, True) == srt[::-1][k - 1]
+        with pytest.raises(ValueError, match="k must be >= 1"):
+            VectorUtil.kth_sharded(fn, 0, True)
+    finally:
+        b.free()
+        ctx_b.close()

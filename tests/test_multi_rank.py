@@ -108,3 +108,39 @@ def test_two_rank_frame_range_stream_equals_unsharded(tmp_path, built_lib, oracl
     world = 2
     mp.spawn(_frames_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert [open(tmp_path / f"fr{r}").read() for r in range(world)] == ["1", "1"]
+
+
+def _kth_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from housescan_b200.rooms import shard_range
+    from housescan_b200.VectorUtil import kth_sharded
+
+    rng = np.random.default_rng(17)
+    n = 100_003
+    y = (rng.normal(size=n) * 3).astype(np.float32)
+    y[rng.integers(0, n, 4000)] = np.float32(1.25)  # heavy ties
+    y[:6] = [0.0, -0.0, 1e-30, -1e-30, 3e38, -3e38]
+    lo, hi = shard_range(n, rank, world)
+    mine = y[lo:hi]
+    fn = lambda p, pre, m: O.kth_shard_hist(mine, p, pre, m)  # the oracle stands in for Context.kth_shard_pass on the CPU box
+    srt = np.sort(y)
+    ok = True
+    for k in (1, 2, n // 5, n // 2, n - 1, n):
+        ok = ok and kth_sharded(fn, k, True) == srt[::-1][k - 1] and kth_sharded(fn, k, False) == srt[k - 1]
+    for bad in (0, n + 1):
+        try:
+            kth_sharded(fn, bad, True)
+            ok = False
+        except ValueError:
+            pass
+    open(os.path.join(tmp, f"kth{rank}"), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_kth_equals_unsharded(tmp_path, built_lib, oracle_lib):
+    world = 2
+    mp.spawn(_kth_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / f"kth{r}").read() for r in range(world)] == ["1", "1"]
