@@ -64,3 +64,44 @@ def kthLargestBySharded(axis: int, k: int, cloud, group=None):
 
 def kthSmallestBySharded(axis: int, k: int, cloud, group=None):
     return kth_sharded(lambda p, pre, m: cloud.ctx.kth_shard_pass(cloud, axis, p, pre, m), k, False, group)
+
+
+def remove_ceiling_sharded(n_local: int, hist_fn, filter_fn, group=None):
+    """removeCeiling (Main.hs:2643-2664) over a cloud sharded by point range: k = n `quot` 5 of the GLOBAL point count, yLimit = the
+    k-th largest y over all ranks (kth_sharded), then every rank keeps its own points with y <= yLimit in input order
+    (`filter_fn(y_limit)` -> whatever the rank keeps, e.g. Context.filter_le).  Returns (kept, y_limit, first_index): first_index is the
+    position of this rank's first kept point in the concatenated output (exclusive scan of the kept counts over the ranks), so the
+    ranks can write one file / one buffer without another pass.  An empty global cloud returns (None, None, 0) like the V.null guard."""
+    import torch
+    import torch.distributed as dist
+
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    n = torch.tensor([int(n_local)], dtype=torch.int64)
+    if multi:
+        dist.all_reduce(n, group=group)
+    n_global = int(n.item())
+    if n_global == 0:
+        return None, None, 0
+    y_limit = kth_sharded(hist_fn, n_global // 5, True, group)  # n < 5 => k = 0 => raises like the reference
+    kept = filter_fn(float(y_limit))
+    first = 0
+    if multi:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([len(kept)], dtype=torch.int64), group=group)
+        first = int(sum(int(c.item()) for c in counts[:rank]))
+    return kept, y_limit, first
+
+
+def removeCeilingSharded(cloud, colors=None, group=None):
+    """this rank's shard of the cloud in, this rank's kept points out: (Cloud, colours or None, y_limit, first_index)"""
+    ctx = cloud.ctx
+    res = {}
+
+    def flt(y_limit):
+        out, cout = ctx.filter_le(cloud, Y, y_limit, colors)
+        res["c"] = cout
+        return out
+
+    kept, y_limit, first = remove_ceiling_sharded(len(cloud), lambda p, pre, m: ctx.kth_shard_pass(cloud, Y, p, pre, m), flt, group)
+    return kept, res.get("c"), y_limit, first

@@ -697,3 +697,14 @@ def test_sharded_kth_passes_on_gpu(ctx):
     finally:
         b.free()
         ctx_b.close()
+
+
+def test_remove_ceiling_sharded_single_rank_equals_remove_ceiling(ctx):
+    from housescan_b200 import VectorUtil
+
+    rng = np.random.default_rng(29)
+    xyz = rng.normal(size=(50_007, 3)).astype(np.float32)
+    cl = ctx.upload(xyz)
+    kept, _, ylim, first = VectorUtil.removeCeilingSharded(cl)
+    ref, _, ylim_ref = ctx.remove_ceiling(cl)
+    assert first == 0 and ylim == ylim_ref and np.array_equal(kept.download().view(np.uint32), ref.download().view(np.uint32))

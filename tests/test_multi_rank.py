@@ -135,6 +135,13 @@ def _kth_worker(rank, world, port, tmp):
             ok = False
         except ValueError:
             pass
+    # removeCeiling over the two shards: global k = n `quot` 5, per-rank filter, offsets of the kept runs
+    from housescan_b200.VectorUtil import remove_ceiling_sharded
+    xyz = np.stack([np.zeros(n, np.float32), y, np.arange(n, dtype=np.float32)], axis=1)
+    kept, ylim, first = remove_ceiling_sharded(hi - lo, fn, lambda lim: xyz[lo:hi][xyz[lo:hi, 1] <= np.float32(lim)])
+    whole, _ = O.remove_ceiling(xyz, None)
+    ok = ok and ylim == O.kth_largest(y, n // 5) and np.array_equal(kept, whole[first:first + len(kept)])
+    ok = ok and (first == 0) == (rank == 0)
     open(os.path.join(tmp, f"kth{rank}"), "w").write("1" if ok else "0")
     dist.destroy_process_group()
 
