@@ -669,6 +669,7 @@ def test_wall_alignment_pipeline_on_gpu(ctx):
 def test_sharded_kth_passes_on_gpu(ctx):
     """hs_kth_shard_pass: the three radix passes of the sharded k-th on one rank, and two 'ranks' emulated by two
     clouds whose histograms are added by hand, against the sorted keys; histograms bit-exact against the oracle's"""
+    import housescan_b200 as hb
     from housescan_b200 import VectorUtil
 
     rng = np.random.default_rng(23)
@@ -685,7 +686,7 @@ def test_sharded_kth_passes_on_gpu(ctx):
     assert np.array_equal(h, O.kth_shard_hist(xyz[:, 1], 0, 0, 0)) and int(h.sum()) == n
     # two shards, histograms summed by hand
     cut = 80_004
-    a, b = ctx.upload(xyz[:cut]), ctx.upload(xyz[cut:])
+    a = ctx.upload(xyz[:cut])
     ctx_b = hb.Context(0)  # every rank has its own context (and key scratch)
     try:
         b = ctx_b.upload(xyz[cut:])
