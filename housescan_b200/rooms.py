@@ -70,6 +70,26 @@ def Opposite(d: float):
     return ("Opposite", float(d))
 
 
+def bestAxis(normal) -> int:
+    """`snd $ maximum [(abs (n `dotprod` v), ax) | (v, ax) <- [(vec3X, X), (vec3Y, Y), (vec3Z, Z)]]` (Main.hs:2051): the axis the
+    wall normal is most parallel to; on equal components the tuple maximum prefers the LATER axis (Z over Y over X)."""
+    n = np.asarray(normal, np.float32)
+    return max((abs(np.float32(n[a])), a) for a in (X, Y, Z))[1]
+
+
+def connectWalls(conns, relation, wall1, wall2, normal1, normal2):
+    """Main.connectWalls (Main.hs:2039-2068) as a pure function on the connection list.  wall1 / wall2 identify the two selected
+    wall planes (any hashable id; the reference uses plane IDs), normal1 / normal2 are their PlaneEq normals.  Returns
+    (new_conns, message): the connection is consed in front (newest first — this is the edge order groupConnectedComponents sees,
+    Main.hs:2061) unless the two walls disagree on the axis or the pair is already connected in either order."""
+    a1, a2 = bestAxis(normal1), bestAxis(normal2)
+    if a1 != a2:
+        return list(conns), "Could not guess axis of wall connection"
+    if any((wa, wb) in ((wall1, wall2), (wall2, wall1)) for (_, _, wa, wb) in conns):
+        return list(conns), None
+    return [(a1, relation, wall1, wall2)] + list(conns), None
+
+
 def optimizeRoomPositions(room_ids, conns, plane_mean, corner_mean, ctx=None):
     """Main.optimizeRoomPositions (Main.hs:2089-2168) as a pure function.
 

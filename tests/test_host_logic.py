@@ -169,3 +169,21 @@ def test_general_division_sequence_random():
         q1 = _fma32(_fma32(nb, q0, a), yy, q0)
         q2 = _fma32(_fma32(nb, q1, a), yy, q1)
         assert np.array_equal(q2.view(np.uint32), (a / b).view(np.uint32)), b
+
+
+def test_connect_walls_reference_semantics():
+    """Main.connectWalls (Main.hs:2039-2068): axis = the one the normals are most parallel to (ties go to the later axis), walls
+    that disagree are refused, duplicates in either order are ignored, new connections go in front"""
+    from housescan_b200.rooms import X, Y, Z, Opposite, SAME, bestAxis, connectWalls
+
+    assert bestAxis([0.9, 0.1, -0.3]) == X and bestAxis([0.1, -0.8, 0.3]) == Y and bestAxis([0, 0.2, -0.7]) == Z
+    assert bestAxis([0.5, 0.5, 0.0]) == Y and bestAxis([0.5, 0.5, 0.5]) == Z  # tuple maximum: the later axis wins a tie
+    conns = []
+    conns, msg = connectWalls(conns, Opposite(0.1), (1, 0), (2, 1), [1, 0, 0], [-0.99, 0.1, 0])
+    assert msg is None and conns == [(X, Opposite(0.1), (1, 0), (2, 1))]
+    conns, msg = connectWalls(conns, SAME, (2, 4), (3, 5), [0, 0.1, 1], [0, 0, -1])
+    assert conns[0] == (Z, SAME, (2, 4), (3, 5)) and len(conns) == 2  # newest first
+    again, _ = connectWalls(conns, SAME, (2, 1), (1, 0), [1, 0, 0], [1, 0, 0])
+    assert again == conns  # already connected (reversed order counts)
+    refused, msg = connectWalls(conns, SAME, (5, 0), (6, 2), [1, 0, 0], [0, 1, 0])
+    assert refused == conns and msg == "Could not guess axis of wall connection"
