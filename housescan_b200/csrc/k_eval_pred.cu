@@ -402,7 +402,12 @@ __device__ __forceinline__ void point(ChainsP& c, const RoomK& R, float x, float
   else add_point_pred(c, R, x, y, z);
 }
 
-template <int NCONS, int STAGES, int GPT, int PT, int WH>
+// tools only (mode key 5): per-block timestamps of the DBG instantiation land here; the product instantiation (DBG = false) is
+// compiled without a single extra instruction
+__device__ unsigned long long* g_warp_dbg = nullptr;
+#define WDBG(k) do { if (DBG && threadIdx.x == 0) g_warp_dbg[8 * blockIdx.x + (k)] = globaltimer_ns(); } while (0)
+
+template <int NCONS, int STAGES, int GPT, int PT, int WH, bool DBG = false>
 __global__ void __launch_bounds__(NCONS + 32, 1)
 k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_constant__ PredTable tbl, int64_t gpb,
                          double* __restrict__ partials, int* __restrict__ meta, unsigned int* ticket, double* __restrict__ out,
@@ -466,6 +471,7 @@ k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_
   double* my_wacc = wacc + warp * HS_NACC;
   float* my_wtmp = wtmp + warp * 24;
   int64_t tt = 0;
+  WDBG(0);  // block start
   for (int r = rfirst; r <= rlast; ++r) {
     const int64_t lo = max(tbl.off[r], p0), hi = min(tbl.off[r + 1], p1);
     RoomK R;
@@ -496,6 +502,7 @@ k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_
       int since_flush = 0;
       for (int t = 0; t < nfull; ++t) {
         if (WH == 2) mbar_wait_s_test(full_s + 8 * stage, parity); else if (WH == 1) mbar_wait_s(full_s + 8 * stage, parity); else mbar_wait(full + stage, parity);
+        if (DBG && t == 0 && r == rfirst) WDBG(1);  // first tile has landed
         // this thread's GPT groups of the tile (group g * NCONS + tid): 4 consecutive points = 3 x LDS.128 each (48 B lane stride:
         // conflict-free quarter-warps)
         const uint32_t base = tiles_s + stage * TILE_BYTES;
@@ -552,6 +559,7 @@ k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_
   }
 
   // ---------------- last block sums the partials per room in block order (parallel fetch, then fixed-order sums)
+  WDBG(2);  // streaming and per-room block sums done
   __threadfence();
   consumers_sync_p<NCONS>();
   if (threadIdx.x == 0) {
@@ -560,6 +568,8 @@ k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_
     if (is_last) *ticket = 0u;
   }
   consumers_sync_p<NCONS>();
+  WDBG(3);  // ticket taken
+  if (DBG && threadIdx.x == 0) g_warp_dbg[8 * blockIdx.x + 4] = is_last;
   if (!is_last) return;
   __threadfence();
   const int64_t ppb = gpb * 4;
@@ -615,11 +625,13 @@ k_rooms_cuboid_sums_warp(const float* __restrict__ xyz, int64_t n, const __grid_
       out[o] = sum;
     }
   }
+  WDBG(5);  // final reduction written
   // ---------------- multi-GPU: the records of all ranks are summed over peer memory before the kernel ends (k_peer.cuh)
   if (px.world > 1) {
     consumers_sync_p<NCONS>();
     peer_allreduce(px, out, nrooms * HS_REC, static_cast<int>(threadIdx.x), NCONS, [] { consumers_sync_p<NCONS>(); });
   }
+  WDBG(6);
 }
 
 
@@ -853,7 +865,7 @@ static int32_t launch_pred_t(hs_ctx* ctx, const float* xyz, int64_t n, const Pre
   return HS_OK;
 }
 
-template <int NCONS, int STAGES, int GPT = 1, int PT = 1, int WH = 0>
+template <int NCONS, int STAGES, int GPT = 1, int PT = 1, int WH = 0, bool DBG = false>
 static int32_t launch_warp_t(hs_ctx* ctx, const float* xyz, int64_t n, const PredTable& tbl, double* d_rec_out) {
   const int64_t G = (n + 3) >> 2;
   int64_t nb = ctx->sm_count;
@@ -869,12 +881,13 @@ static int32_t launch_warp_t(hs_ctx* ctx, const float* xyz, int64_t n, const Pre
                       static_cast<size_t>(NCONS / 32) * 24 * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_rooms_cuboid_sums_warp<NCONS, STAGES, GPT, PT, WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_rooms_cuboid_sums_warp<NCONS, STAGES, GPT, PT, WH, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (DBG) HS_CUDA_TRY(ctx, cudaMemcpyToSymbol(g_warp_dbg, &ctx->d_dbg, sizeof(ctx->d_dbg)));
     attr_set = true;
   }
   PeerExchange px = {};
   if (ctx->px_next) { px = ctx->px; px.epoch = ++ctx->px.epoch; ctx->px_next = false; }  // fused exchange: consumed by this launch
-  k_rooms_cuboid_sums_warp<NCONS, STAGES, GPT, PT, WH><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out, px);
+  k_rooms_cuboid_sums_warp<NCONS, STAGES, GPT, PT, WH, DBG><<<static_cast<int>(nb), NCONS + 32, smem, ctx->stream>>>(xyz, n, tbl, gpb, partials, meta, ctx->d_ticket, d_rec_out, px);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;
@@ -919,7 +932,10 @@ int32_t launch_rooms_cuboid_sums_pred(hs_ctx* ctx, const float* xyz, int64_t n, 
     }
   // product default: 12 consumer warps + the producer warp, 3 ring stages of 72 KB, 16 points per thread per tile, FMNMX point
   // block (profiles/r01_sweep8_tile_size.log: 220.6 us per 100 M points = 0.83 of the measured HBM peak)
-  if (ctx->modes[HS_MODE_EVAL_VARIANT] == 0) return launch_warp_t<384, 3, 4, 2>(ctx, xyz, n, t, d_rec_out);
+  if (ctx->modes[HS_MODE_EVAL_VARIANT] == 0) {
+    if (ctx->modes[HS_MODE_DEBUG_TIMES] && ctx->d_dbg) return launch_warp_t<384, 3, 4, 2, 0, true>(ctx, xyz, n, t, d_rec_out);  // tools: timestamps
+    return launch_warp_t<384, 3, 4, 2>(ctx, xyz, n, t, d_rec_out);
+  }
   if (ctx->modes[HS_MODE_EVAL_VARIANT] == 6) {  // warp-private rings: consumers = warps * 100 + groups per thread * 10 + ring depth
     switch (ctx->modes[HS_MODE_EVAL_CONSUMERS]) {
       case 1614: return launch_wring_t<16, 1, 4>(ctx, xyz, n, t, d_rec_out);

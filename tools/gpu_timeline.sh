@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 for n in 240000 12500000 100000008; do
-  timeout 200 python tools/prof_eval.py --reps 20 --var 2 --n $n --blocks 2>&1 | head -6
-  timeout 200 python tools/prof_eval.py --reps 20 --n $n 2>&1 | head -1
-done > gpurun_out/eval_timeline_pred.log 2>&1
-cat gpurun_out/eval_timeline_pred.log
+  timeout 200 python tools/prof_eval.py --reps 20 --n $n --blocks2 2>&1 | head -6
+done > gpurun_out/eval_timeline_warp.log 2>&1
+cat gpurun_out/eval_timeline_warp.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "cuboid or rooms or smoke" --timeout 120 2>&1 | tail -2

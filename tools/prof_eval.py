@@ -24,6 +24,7 @@ ap.add_argument("--time", action="store_true")
 ap.add_argument("--psleep", type=int, default=0)
 ap.add_argument("--rooms", type=int, default=12)
 ap.add_argument("--blocks", action="store_true", help="print the per-block timeline of the last launch")
+ap.add_argument("--blocks2", action="store_true", help="per-block timeline of the DEFAULT kernel (its timestamped instantiation, mode key 5)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 ctx = hb.Context(0)
@@ -84,3 +85,36 @@ if a.blocks:
     print("last block:", int(np.argmax(t[:, 3])), "its end %.1f" % en[np.argmax(t[:, 3])])
     for b in [35, 36, 37, 72, 73, 110, 12, 90]:
         print("block", b, "start %.1f" % st[b], "seg events (head done, main done, rem done, reduce done):", [[round((x - t0) / 1e3, 1) if x else None for x in ev[b, k]] for k in range(2)])
+
+
+if a.blocks2:
+    import ctypes as C
+    from housescan_b200 import _lib
+    lib = C.CDLL(_lib.SO_PATH)
+    ctx.set_mode(5, 1)
+    for _ in range(4):
+        ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"timestamped instantiation: {e0.elapsed_time(e1) / a.reps * 1e3:.1f} us/launch")
+    nb = 148
+    buf = (C.c_uint64 * (8 * nb))()
+    lib.hs_dbg_block_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    rc = lib.hs_dbg_block_times(ctx.h, buf, 2 * nb)
+    t = np.array(buf[: 8 * nb], dtype=np.int64).reshape(nb, 8)
+    live = t[:, 0] > 0
+    t0 = t[live, 0].min()
+    us = lambda c: (t[live, c] - t0) / 1e3
+    st, first, main, tick = us(0), us(1), us(2), us(3)
+    last = int(np.flatnonzero(live)[np.argmax(t[live, 4])])
+    print(f"rc={rc} blocks {int(live.sum())} | start: max {st.max():.1f} | first tile landed after start: median {np.median(first - st):.1f} max {(first - st).max():.1f}"
+          f" | streaming end: min {main.min():.1f} median {np.median(main):.1f} p90 {np.percentile(main, 90):.1f} max {main.max():.1f}"
+          f" | ticket taken: max {tick.max():.1f}")
+    print(f"last block {last}: streaming end {(t[last, 2] - t0) / 1e3:.1f}, ticket {(t[last, 3] - t0) / 1e3:.1f}, final reduction written {(t[last, 5] - t0) / 1e3:.1f}, kernel end {(t[last, 6] - t0) / 1e3:.1f}")
+    order = np.flatnonzero(live)[np.argsort(main)]
+    print("latest streaming ends (block, us):", [(int(b), round(float((t[b, 2] - t0) / 1e3), 1)) for b in order[-10:]])
