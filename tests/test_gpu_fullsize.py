@@ -28,6 +28,7 @@ def _cloud(ctx, dev, n, seed):
     buf = torch.empty(3 * n + 32, dtype=torch.float32, device=dev)
     pts = buf[: 3 * n].view(n, 3)
     pts.copy_((torch.rand(n, 3, device=dev, generator=g) - 0.5) * torch.tensor([5.0, 2.6, 4.0], device=dev) + torch.tensor([0.3, 1.4, 4.0], device=dev))
+    torch.cuda.synchronize()  # torch filled the buffer on ITS stream; the library reads it on its own
     return ctx.wrap(buf.data_ptr(), n, keepalive=buf), buf, pts
 
 
@@ -97,6 +98,8 @@ def test_c3_apartment_records_100m(ctx, dev):
     per = 8_333_334
     n = per * 12
     buf, pts = bench.gen_points_torch(torch, dev, params, [per] * 12, seed=3)
+    torch.cuda.synchronize()  # the generator runs on torch's stream, the library on its own: without this the first evaluation
+    # can read room 11 while it is still being written (seen as an order-dependent mismatch between kernel forms)
     cloud = ctx.wrap(buf.data_ptr(), n, keepalive=buf)
     offs = np.arange(13, dtype=np.int64) * per
     rec = ctx.rooms_cuboid_sums(cloud, offs, pe)
