@@ -145,6 +145,7 @@ def test_c4_components_20m(ctx, dev):
     src, dst = e[0].to(torch.int32).contiguous(), e[1].to(torch.int32).contiguous()
     E = src.numel()
     lab = torch.empty(N, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # torch built the edge list on its stream; the library reads it on its own
     ctx._chk(ctx.lib.hs_cc_label_dev(ctx.h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), E, N, C.c_void_p(lab.data_ptr())))
     torch.cuda.synchronize()
     l64 = lab.long()
@@ -170,6 +171,7 @@ def test_c5_depth_stream_200_frames(ctx, dev):
     cloud = ctx.wrap(out.data_ptr(), npx, keepalive=out)
     mask = torch.empty(npx, dtype=torch.uint8, device=dev)
     nv = C.c_int64()
+    torch.cuda.synchronize()  # frames were replicated on torch's stream
     ctx._chk(ctx.lib.hs_backproject_ref_dev(ctx.h, C.c_void_p(frames.data_ptr()), w, h * nf, cloud.h, C.c_void_p(mask.data_ptr()), C.byref(nv)))
     torch.cuda.synchronize()
     valid = frames.view(-1) != 0

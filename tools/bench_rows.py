@@ -170,6 +170,7 @@ if want("A1"):
     base, _ = synth.depth_stream(8, w, h)
     frames = torch.from_numpy(base.astype(np.int32)).to(dev).to(torch.int16).repeat((nf + 7) // 8, 1, 1)[:nf].contiguous()
     npx = nf * w * h
+    torch.cuda.synchronize()
     # A1-A3 on a whole replayed stream treated as ONE tall frame (w x nf*h): mask + ordered compaction + scaling
     bp_out = torch.empty(npx * 3 + 16, dtype=torch.float32, device=dev)
     bp_cloud = ctx.wrap(bp_out.data_ptr(), npx, keepalive=bp_out)
@@ -234,6 +235,7 @@ if want("A10"):
     E = src.numel()
     del e, keep, right, down, vid
     lab = torch.empty(N, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
     fn = lambda: ctx._chk(lib.hs_cc_label_dev(ctx.h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), E, N, C.c_void_p(lab.data_ptr())))
     ms = timed(fn, reps=3, warm=1)
     l64 = lab.long()
