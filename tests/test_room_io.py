@@ -268,3 +268,44 @@ def test_pcd_header_fuzz_never_crashes(built_lib, tmp_path):
         except hb.HsError:
             bad += 1
     assert bad >= 8 and ok + bad == len(cases)
+
+
+# ------------------------------------------------------------------ committed room fixture (tests/golden/room, make_room_fixture.py)
+GOLDEN_ROOM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "room")
+
+
+def _golden_expected():
+    import json
+
+    with open(os.path.join(GOLDEN_ROOM, "expected.json")) as fh:
+        return json.load(fh)
+
+
+def test_golden_room_fixture_pins_the_oracle_and_the_host_parsers(built_lib):
+    exp = _golden_expected()
+    cloud, cols, planes = O.load_room(GOLDEN_ROOM)
+    assert len(cloud) == exp["n"] == 1203
+    assert int(cloud.view(np.uint32).astype(np.uint64).sum()) == exp["cloud_u32_sum"]
+    assert cloud[:3].view(np.uint32).tolist() == exp["cloud_first"] and cloud[-2:].view(np.uint32).tolist() == exp["cloud_last"]
+    assert cols[:3].view(np.uint32).tolist() == exp["colors_first"]
+    assert int(cols.view(np.uint32).astype(np.uint64).sum()) == exp["colors_u32_sum"]
+    assert planes.view(np.uint32).tolist() == exp["planes_inward"]
+    # the C ABI's host-side parsers on the same files
+    raw = RoomIO.planeEqsFromFile(os.path.join(GOLDEN_ROOM, "planes.txt"))
+    assert raw.view(np.uint32).tolist() == exp["planes_raw"]
+    assert RoomIO.pcdInfo(os.path.join(GOLDEN_ROOM, "cloud_downsampled.pcd")) == (1203, True, "binary_compressed")
+    assert RoomIO.pcdInfo(os.path.join(GOLDEN_ROOM, "cloud_plane_hull3.pcd")) == (12, False, "ascii")
+    # three of the six planes were written with PCL's sign flipped: makeInwardFacing turns exactly those around
+    flipped = [k for k in range(6) if np.array_equal(np.array(exp["planes_raw"][k], np.uint32).view(np.float32), -np.array(exp["planes_inward"][k], np.uint32).view(np.float32))]
+    assert len(flipped) == 3
+
+
+@pytest.mark.gpu
+def test_golden_room_fixture_through_the_gpu_path(ctx):
+    exp = _golden_expected()
+    cl, col, planes = RoomIO.loadRoom(ctx, GOLDEN_ROOM)
+    xyz, c = cl.download(), col.download()
+    assert len(cl) == exp["n"] and int(xyz.view(np.uint32).astype(np.uint64).sum()) == exp["cloud_u32_sum"]
+    assert xyz[:3].view(np.uint32).tolist() == exp["cloud_first"] and c[:3].view(np.uint32).tolist() == exp["colors_first"]
+    assert int(c.view(np.uint32).astype(np.uint64).sum()) == exp["colors_u32_sum"]
+    assert planes.view(np.uint32).tolist() == exp["planes_inward"]
