@@ -91,3 +91,7 @@ foreign import ccall safe "hs_write_pcd" c_write_pcd :: Ptr HsCtx -> Ptr HsCloud
 foreign import ccall safe "hs_kth_shard_pass"
   c_kth_shard_pass :: Ptr HsCtx -> Ptr HsCloud -> Int32 -> Int32 -> Word32 -> Word32 -> Ptr Word32 -> IO Int32
 foreign import ccall unsafe "hs_kth_float_of_key" c_kth_float_of_key :: Word32 -> CFloat
+-- plane algebra of the room-editing actions (Main.hs:1553-1578, :1681-1688), host only
+foreign import ccall unsafe "hs_rotation_between_plane_eqs" c_rotation_between_plane_eqs :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
+foreign import ccall unsafe "hs_rotate_plane_eq_around" c_rotate_plane_eq_around :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
+foreign import ccall unsafe "hs_translate_plane_eq" c_translate_plane_eq :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32

@@ -86,6 +86,9 @@ SIGNATURES = {
     "hs_kth_shard_pass": (i32, [vp, vp, i32, i32, u32, u32, vp]),
     "hs_kth_key_of_float": (u32, [f32]),
     "hs_kth_float_of_key": (f32, [u32]),
+    "hs_rotation_between_plane_eqs": (i32, [vp, vp, vp]),
+    "hs_rotate_plane_eq_around": (i32, [vp, vp, vp, vp]),
+    "hs_translate_plane_eq": (i32, [vp, vp, vp]),
     "hs_version": (C.c_char_p, []),
 }
 

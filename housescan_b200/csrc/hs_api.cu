@@ -873,6 +873,28 @@ int32_t hs_load_room(hs_ctx* ctx, const char* dir, hs_cloud** cloud_out, hs_clou
   return HS_OK;
 }
 
+// ---- plane algebra of the room-editing actions (Main.hs:1553-1578, :1681-1688): host only, Float, reference evaluation order --------
+int32_t hs_rotation_between_plane_eqs(const float plane1[4], const float plane2[4], float R_out[9]) {
+  if (!plane1 || !plane2 || !R_out) return HS_EINVAL;
+  const hs::M3<float> R = hs::rotation_between_normals(hs::V3<float>{plane1[0], plane1[1], plane1[2]}, hs::V3<float>{plane2[0], plane2[1], plane2[2]});
+  for (int r = 0; r < 3; ++r) { R_out[3 * r] = R.r[r].x; R_out[3 * r + 1] = R.r[r].y; R_out[3 * r + 2] = R.r[r].z; }
+  return HS_OK;
+}
+int32_t hs_rotate_plane_eq_around(const float center[3], const float R[9], const float plane_in[4], float plane_out[4]) {
+  if (!center || !R || !plane_in || !plane_out) return HS_EINVAL;
+  const hs::M3<float> M{{{R[0], R[1], R[2]}, {R[3], R[4], R[5]}, {R[6], R[7], R[8]}}};
+  const hs::PlaneEq e = hs::rotate_plane_eq_around(hs::V3<float>{center[0], center[1], center[2]}, M,
+                                                   hs::PlaneEq{hs::V3<float>{plane_in[0], plane_in[1], plane_in[2]}, plane_in[3]});
+  plane_out[0] = e.n.x; plane_out[1] = e.n.y; plane_out[2] = e.n.z; plane_out[3] = e.d;
+  return HS_OK;
+}
+int32_t hs_translate_plane_eq(const float off[3], const float plane_in[4], float plane_out[4]) {
+  if (!off || !plane_in || !plane_out) return HS_EINVAL;
+  const hs::PlaneEq e = hs::translate_plane_eq(hs::V3<float>{off[0], off[1], off[2]}, hs::PlaneEq{hs::V3<float>{plane_in[0], plane_in[1], plane_in[2]}, plane_in[3]});
+  plane_out[0] = e.n.x; plane_out[1] = e.n.y; plane_out[2] = e.n.z; plane_out[3] = e.d;
+  return HS_OK;
+}
+
 // ---- host-side module mirrors ------------------------------------------------------------------------------------------------------
 int32_t hs_cuboid_from_params(const double params[10], double out[24]) { if (!params || !out) return HS_EINVAL; hs::cuboid_from_params(params, out); return HS_OK; }
 double hs_errfun(const double corners[24], const double params[10]) { return hs::errfun(corners, params); }

@@ -65,6 +65,22 @@ template <class T> inline M3<T> rot_from_quat(V4<T> q_raw) {
 // rotateAround c R p
 template <class T> inline V3<T> rotate_around(V3<T> c, const M3<T>& R, V3<T> p) { return rowmul(p - c, R) + c; }
 
+// rotMatrix3' (unit axis v) a = (1 - cos a) v v^T + [[c, s z, -s y], [-s z, c, s x], [s y, -s x, c]]: Rodrigues' rotation by +a about
+// v for ROW vectors (p' = p .* R), the convention of Main.hs:10 and of the doc comment at Main.hs:1548-1552
+template <class T> inline M3<T> rot_matrix3_unit(V3<T> v, T ang) {
+  const T c = std::cos(ang), s = std::sin(ang), k = T(1) - c;
+  return M3<T>{{{k * (v.x * v.x) + c, k * (v.x * v.y) + s * v.z, k * (v.x * v.z) + (-(s * v.y))},
+                {k * (v.y * v.x) + (-(s * v.z)), k * (v.y * v.y) + c, k * (v.y * v.z) + s * v.x},
+                {k * (v.z * v.x) + s * v.y, k * (v.z * v.y) + (-(s * v.x)), k * (v.z * v.z) + c}}};
+}
+// rotationBetweenPlaneEqs (Main.hs:1553-1560): the rotation that turns normal n1 into the direction of n2; `crossprod` on Normal3
+// re-normalises, so the axis is unit(n1 x n2); (anti)parallel normals give NaNs exactly as the reference does (no guard there)
+inline M3<float> rotation_between_normals(V3<float> n1, V3<float> n2) {
+  const V3<float> axis = unit(cross(n1, n2));
+  const float costheta = dot(n1, n2) / (norm(n1) * norm(n2));
+  return rot_matrix3_unit(axis, std::acos(costheta));
+}
+
 // PlaneEq n d (Main.hs:1357) and its constructors / movers
 struct PlaneEq {
   V3<float> n;

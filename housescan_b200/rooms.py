@@ -70,6 +70,33 @@ def Opposite(d: float):
     return ("Opposite", float(d))
 
 
+def rotationBetweenPlaneEqs(plane1, plane2) -> np.ndarray:
+    """Main.hs:1553-1560: the row-vector rotation R (p' = p .* R) that turns plane1's normal into the direction of plane2's"""
+    from . import _lib as L
+
+    R = np.empty(9, np.float32)
+    L.load().hs_rotation_between_plane_eqs(L.ptr(L.as_f32(plane1, (4,))), L.ptr(L.as_f32(plane2, (4,))), L.ptr(R))
+    return R.reshape(3, 3)
+
+
+def rotatePlaneEqAround(center, R, plane) -> np.ndarray:
+    """Main.hs:1571-1578 (re-normalised by mkPlaneEq)"""
+    from . import _lib as L
+
+    out = np.empty(4, np.float32)
+    L.load().hs_rotate_plane_eq_around(L.ptr(L.as_f32(center, (3,))), L.ptr(L.as_f32(R, (9,))), L.ptr(L.as_f32(plane, (4,))), L.ptr(out))
+    return out
+
+
+def translatePlaneEq(offset, plane) -> np.ndarray:
+    """Main.hs:1681-1688"""
+    from . import _lib as L
+
+    out = np.empty(4, np.float32)
+    L.load().hs_translate_plane_eq(L.ptr(L.as_f32(offset, (3,))), L.ptr(L.as_f32(plane, (4,))), L.ptr(out))
+    return out
+
+
 def bestAxis(normal) -> int:
     """`snd $ maximum [(abs (n `dotprod` v), ax) | (v, ax) <- [(vec3X, X), (vec3Y, Y), (vec3Z, Z)]]` (Main.hs:2051): the axis the
     wall normal is most parallel to; on equal components the tuple maximum prefers the LATER axis (Z over Y over X)."""

@@ -162,6 +162,13 @@ HS_API int32_t hs_make_inward_facing(const float room_center[3], const float* pl
 /* loadRoom (Main.hs:1740-1765): dir/cloud_downsampled.pcd, dir/planes.txt, dir/cloud_plane_hull<i>.pcd; planes inward facing */
 HS_API int32_t hs_load_room(hs_ctx* ctx, const char* dir, hs_cloud** cloud_out, hs_cloud** colors_out, float* planes_out, int32_t cap, int32_t* K_out);
 
+/* Plane algebra behind the room-editing actions that move a room's planes together with its cloud (host only, Float):
+ * rotationBetweenPlaneEqs (Main.hs:1553-1560; row-vector rotation R with n1 .* R parallel to n2, NaN for (anti)parallel normals as
+ * in the reference), rotatePlaneEqAround (:1571-1578), translatePlaneEq (:1681-1688).  The cloud side is hs_rotate_around /
+ * hs_translate with the same R / offset. */
+HS_API int32_t hs_rotation_between_plane_eqs(const float plane1[4], const float plane2[4], float R_rowmajor_out[9]);
+HS_API int32_t hs_rotate_plane_eq_around(const float center[3], const float R_rowmajor[9], const float plane_in[4], float plane_out[4]);
+HS_API int32_t hs_translate_plane_eq(const float offset[3], const float plane_in[4], float plane_out[4]);
 /* roomProjectionToString / roomProjectionToXfFormat (Main.hs:2271-2302); buf receives a NUL-terminated string */
 HS_API int32_t hs_proj_to_string(const float m_rowmajor[16], char* buf, int32_t buflen);
 HS_API int32_t hs_proj_to_xf(const float m_rowmajor[16], char* buf, int32_t buflen);

@@ -187,3 +187,25 @@ def test_connect_walls_reference_semantics():
     assert again == conns  # already connected (reversed order counts)
     refused, msg = connectWalls(conns, SAME, (5, 0), (6, 2), [1, 0, 0], [0, 1, 0])
     assert refused == conns and msg == "Could not guess axis of wall connection"
+
+
+def test_plane_algebra_matches_oracle_bit_for_bit(built_lib):
+    """rotationBetweenPlaneEqs / rotatePlaneEqAround / translatePlaneEq (Main.hs:1553-1578, :1681-1688) through the C ABI against
+    the oracle's restatement; and the property the reference's doc comment states: n1 .* R points along n2"""
+    from housescan_b200.rooms import rotatePlaneEqAround, rotationBetweenPlaneEqs, translatePlaneEq
+
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        p1 = O.mk_plane_eq(rng.normal(size=3), rng.normal())
+        p2 = O.mk_plane_eq(rng.normal(size=3), rng.normal())
+        R = rotationBetweenPlaneEqs(p1, p2)
+        assert np.array_equal(R.view(np.uint32), O.rotation_between_normals(p1[:3], p2[:3]).view(np.uint32))
+        assert np.allclose(p1[:3] @ R, p2[:3], atol=2e-6)
+        c = rng.normal(size=3).astype(np.float32)
+        a = rotatePlaneEqAround(c, R, p1)
+        assert np.array_equal(a.view(np.uint32), O.rotate_plane_eq_around(c, R, p1).view(np.uint32))
+        off = rng.normal(size=3).astype(np.float32)
+        t = translatePlaneEq(off, p2)
+        assert np.array_equal(t.view(np.uint32), O.translate_plane_eq(off, p2).view(np.uint32))
+    with np.errstate(invalid="ignore"):
+        assert np.isnan(rotationBetweenPlaneEqs([0, 0, 1, 0], [0, 0, 1, 5])).any()  # parallel normals: NaN, as in the reference
