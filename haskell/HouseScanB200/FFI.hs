@@ -95,3 +95,4 @@ foreign import ccall unsafe "hs_kth_float_of_key" c_kth_float_of_key :: Word32 -
 foreign import ccall unsafe "hs_rotation_between_plane_eqs" c_rotation_between_plane_eqs :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
 foreign import ccall unsafe "hs_rotate_plane_eq_around" c_rotate_plane_eq_around :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
 foreign import ccall unsafe "hs_translate_plane_eq" c_translate_plane_eq :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
+foreign import ccall unsafe "hs_plane_corner" c_plane_corner :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32

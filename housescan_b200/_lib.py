@@ -89,6 +89,7 @@ SIGNATURES = {
     "hs_rotation_between_plane_eqs": (i32, [vp, vp, vp]),
     "hs_rotate_plane_eq_around": (i32, [vp, vp, vp, vp]),
     "hs_translate_plane_eq": (i32, [vp, vp, vp]),
+    "hs_plane_corner": (i32, [vp, vp, vp, vp]),
     "hs_version": (C.c_char_p, []),
 }
 

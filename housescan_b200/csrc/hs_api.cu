@@ -895,6 +895,11 @@ int32_t hs_translate_plane_eq(const float off[3], const float plane_in[4], float
   return HS_OK;
 }
 
+int32_t hs_plane_corner(const float plane1[4], const float plane2[4], const float plane3[4], float corner_out[3]) {
+  if (!plane1 || !plane2 || !plane3 || !corner_out) return HS_EINVAL;
+  return hs::plane_corner(plane1, plane2, plane3, corner_out) ? HS_OK : HS_ESINGULAR;  // Nothing (Main.hs:1428-1430)
+}
+
 // ---- host-side module mirrors ------------------------------------------------------------------------------------------------------
 int32_t hs_cuboid_from_params(const double params[10], double out[24]) { if (!params || !out) return HS_EINVAL; hs::cuboid_from_params(params, out); return HS_OK; }
 double hs_errfun(const double corners[24], const double params[10]) { return hs::errfun(corners, params); }

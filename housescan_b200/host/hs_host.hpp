@@ -46,6 +46,10 @@ BFGSResult bfgs(const std::function<bool(const double*, double*, double*)>& eval
 bool lstsq_distances(const int32_t* ii, const int32_t* jj, const double* d, int m, int n_nodes, double* pos, double* rmse);
 void eig_sym3(const double sc[6], double evals[3], double evecs[3][3]);
 
+// planeCorner (Main.hs:1413-1430): the point where three planes meet, n_k . x = d_k solved in Double (LU with partial pivoting, the
+// algorithm of LAPACK dgesv behind hmatrix's linearSolve) and rounded to Float; false if a pivot is exactly zero (safeLinearSolve -> Nothing)
+bool plane_corner(const float p1[4], const float p2[4], const float p3[4], float out[3]);
+
 std::string show_float(float x);
 std::string proj_to_string(const float m[16]);
 std::string proj_to_xf(const float m[16]);

@@ -6,6 +6,7 @@
 // follows the published PCD v0.7 layout and attoparsec's documented `double` grammar (see parse_double below).
 #include <algorithm>
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,6 +83,37 @@ void make_inward_facing(const float center[3], const float* plane_means, float* 
       planes[4 * k] = -n.x; planes[4 * k + 1] = -n.y; planes[4 * k + 2] = -n.z; planes[4 * k + 3] = -planes[4 * k + 3];
     }
   }
+}
+
+// planeCorner (Main.hs:1413-1430).  Column-oriented LU with partial pivoting on the 3x3 system, then the two triangular solves: the
+// operation order of dgetf2 / dgetrs, so the Doubles agree with LAPACK's and the Floats they round to are the reference's.
+bool plane_corner(const float p1[4], const float p2[4], const float p3[4], float out[3]) {
+  double A[3][3] = {{p1[0], p1[1], p1[2]}, {p2[0], p2[1], p2[2]}, {p3[0], p3[1], p3[2]}};
+  double b[3] = {p1[3], p2[3], p3[3]};
+  int piv[3];
+  for (int j = 0; j < 3; ++j) {
+    int p = j;
+    for (int i = j + 1; i < 3; ++i)
+      if (std::fabs(A[i][j]) > std::fabs(A[p][j])) p = i;  // idamax: first maximum
+    piv[j] = p;
+    if (A[p][j] == 0.0) return false;
+    if (p != j)
+      for (int c = 0; c < 3; ++c) std::swap(A[j][c], A[p][c]);
+    const double r = 1.0 / A[j][j];  // dgetf2 scales the column by the reciprocal of the pivot
+    for (int i = j + 1; i < 3; ++i) A[i][j] *= r;
+    for (int c = j + 1; c < 3; ++c)
+      for (int i = j + 1; i < 3; ++i) A[i][c] -= A[i][j] * A[j][c];
+  }
+  for (int j = 0; j < 3; ++j)
+    if (piv[j] != j) std::swap(b[j], b[piv[j]]);
+  for (int j = 0; j < 3; ++j)  // L y = b (unit lower), column oriented
+    for (int i = j + 1; i < 3; ++i) b[i] -= A[i][j] * b[j];
+  for (int j = 2; j >= 0; --j) {  // U x = y, column oriented
+    b[j] /= A[j][j];
+    for (int i = 0; i < j; ++i) b[i] -= A[i][j] * b[j];
+  }
+  out[0] = static_cast<float>(b[0]); out[1] = static_cast<float>(b[1]); out[2] = static_cast<float>(b[2]);
+  return true;
 }
 
 // pointMean (Main.hs:1596-1601): Float left fold, then multiply by 1 / n

@@ -97,6 +97,15 @@ def translatePlaneEq(offset, plane) -> np.ndarray:
     return out
 
 
+def planeCorner(plane1, plane2, plane3):
+    """Main.hs:1413-1430: the point where three planes meet, or None when the 3x3 system is singular (`Nothing`)"""
+    from . import _lib as L
+
+    out = np.empty(3, np.float32)
+    rc = L.load().hs_plane_corner(L.ptr(L.as_f32(plane1, (4,))), L.ptr(L.as_f32(plane2, (4,))), L.ptr(L.as_f32(plane3, (4,))), L.ptr(out))
+    return None if rc == L.HS_ESINGULAR else out
+
+
 def bestAxis(normal) -> int:
     """`snd $ maximum [(abs (n `dotprod` v), ax) | (v, ax) <- [(vec3X, X), (vec3Y, Y), (vec3Z, Z)]]` (Main.hs:2051): the axis the
     wall normal is most parallel to; on equal components the tuple maximum prefers the LATER axis (Z over Y over X)."""

@@ -169,6 +169,9 @@ HS_API int32_t hs_load_room(hs_ctx* ctx, const char* dir, hs_cloud** cloud_out, 
 HS_API int32_t hs_rotation_between_plane_eqs(const float plane1[4], const float plane2[4], float R_rowmajor_out[9]);
 HS_API int32_t hs_rotate_plane_eq_around(const float center[3], const float R_rowmajor[9], const float plane_in[4], float plane_out[4]);
 HS_API int32_t hs_translate_plane_eq(const float offset[3], const float plane_in[4], float plane_out[4]);
+/* planeCorner (Main.hs:1413-1430): the corner where three planes meet (3x3 solve in Double, result in Float);
+ * HS_ESINGULAR = Nothing when the system has an exactly zero pivot (parallel planes) */
+HS_API int32_t hs_plane_corner(const float plane1[4], const float plane2[4], const float plane3[4], float corner_out[3]);
 /* roomProjectionToString / roomProjectionToXfFormat (Main.hs:2271-2302); buf receives a NUL-terminated string */
 HS_API int32_t hs_proj_to_string(const float m_rowmajor[16], char* buf, int32_t buflen);
 HS_API int32_t hs_proj_to_xf(const float m_rowmajor[16], char* buf, int32_t buflen);

@@ -767,3 +767,15 @@ def kth_shard_hist(keys, pass_no, prefix, mask):
     d = (sel >> np.uint32(shift)) & np.uint32((1 << bits) - 1)
     np.add.at(h, d, 1)
     return h
+
+
+# ------------------------------------------------------------------ planeCorner (Main.hs:1413-1430)
+def plane_corner(p1, p2, p3):
+    """3x3 solve in Double through LAPACK dgesv (numpy.linalg.solve = the routine behind hmatrix's linearSolve), result in Float;
+    None for an exactly singular system (safeLinearSolve -> Nothing)."""
+    A = np.array([np.asarray(p, np.float32)[:3] for p in (p1, p2, p3)], np.float64)
+    b = np.array([np.float32(p[3]) for p in (p1, p2, p3)], np.float64)
+    try:
+        return np.linalg.solve(A, b).astype(np.float32)
+    except np.linalg.LinAlgError:
+        return None

@@ -209,3 +209,26 @@ def test_plane_algebra_matches_oracle_bit_for_bit(built_lib):
         assert np.array_equal(t.view(np.uint32), O.translate_plane_eq(off, p2).view(np.uint32))
     with np.errstate(invalid="ignore"):
         assert np.isnan(rotationBetweenPlaneEqs([0, 0, 1, 0], [0, 0, 1, 5])).any()  # parallel normals: NaN, as in the reference
+
+
+def test_plane_corner_matches_lapack_and_the_cuboid_corners(built_lib):
+    """planeCorner (Main.hs:1413-1430) against numpy's dgesv on random plane triples, and on a cuboid's own walls: every corner of
+    cuboidFromParams is where its three walls meet (the reference's fitCuboidToRoom relies on that, Main.hs:1805-1812)"""
+    from housescan_b200 import FitCuboidBFGS
+    from housescan_b200.rooms import planeCorner
+
+    rng = np.random.default_rng(12)
+    worst = 0
+    for _ in range(300):
+        pl = [O.mk_plane_eq(rng.normal(size=3), rng.normal() * 3) for _ in range(3)]
+        got, exp = planeCorner(*pl), O.plane_corner(*pl)
+        ulps = np.abs(got.view(np.int32).astype(np.int64) - exp.view(np.int32).astype(np.int64)).max()
+        worst = max(worst, int(ulps))
+    assert worst <= 1, worst  # same algorithm as LAPACK's; at most the last Float bit may differ (measured: 0)
+    assert planeCorner([1, 0, 0, 1], [1, 0, 0, 2], [0, 1, 0, 0]) is None and O.plane_corner([1, 0, 0, 1], [1, 0, 0, 2], [0, 1, 0, 0]) is None
+    params = np.array([0.3, -0.2, 4.0, 5.0, 2.6, 4.0, 0.9, 0.1, 0.3, 0.2])
+    planes = hb.planes_from_cuboid(params)
+    corners = FitCuboidBFGS.cuboidFromParams(params)
+    found = np.array([planeCorner(planes[i], planes[2 + j], planes[4 + k]) for i in (0, 1) for j in (0, 1) for k in (0, 1)])
+    for c in corners:
+        assert np.abs(found - c.astype(np.float32)).sum(axis=1).min() < 1e-5
