@@ -96,3 +96,7 @@ foreign import ccall unsafe "hs_rotation_between_plane_eqs" c_rotation_between_p
 foreign import ccall unsafe "hs_rotate_plane_eq_around" c_rotate_plane_eq_around :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
 foreign import ccall unsafe "hs_translate_plane_eq" c_translate_plane_eq :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
 foreign import ccall unsafe "hs_plane_corner" c_plane_corner :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
+-- roomProj bookkeeping (Main.hs:1674, :1708, :1720)
+foreign import ccall unsafe "hs_proj_compose" c_proj_compose :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
+foreign import ccall unsafe "hs_proj_translate" c_proj_translate :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
+foreign import ccall unsafe "hs_proj_rotate_around" c_proj_rotate_around :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32

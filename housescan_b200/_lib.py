@@ -90,6 +90,9 @@ SIGNATURES = {
     "hs_rotate_plane_eq_around": (i32, [vp, vp, vp, vp]),
     "hs_translate_plane_eq": (i32, [vp, vp, vp]),
     "hs_plane_corner": (i32, [vp, vp, vp, vp]),
+    "hs_proj_compose": (i32, [vp, vp, vp]),
+    "hs_proj_translate": (i32, [vp, vp, vp]),
+    "hs_proj_rotate_around": (i32, [vp, vp, vp, vp]),
     "hs_version": (C.c_char_p, []),
 }
 

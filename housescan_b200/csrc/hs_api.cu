@@ -895,6 +895,33 @@ int32_t hs_translate_plane_eq(const float off[3], const float plane_in[4], float
   return HS_OK;
 }
 
+// roomProj bookkeeping of rotateRoomAround / translateRoom / projectRoom (Main.hs:1665-1720)
+int32_t hs_proj_compose(const float a[16], const float b[16], float out[16]) {
+  if (!a || !b || !out) return HS_EINVAL;
+  hs::M4 A, B;
+  std::memcpy(A.m, a, sizeof A.m); std::memcpy(B.m, b, sizeof B.m);
+  const hs::M4 r = hs::proj_compose(A, B);
+  std::memcpy(out, r.m, sizeof r.m);
+  return HS_OK;
+}
+int32_t hs_proj_translate(const float proj[16], const float off[3], float out[16]) {
+  if (!proj || !off || !out) return HS_EINVAL;
+  hs::M4 P;
+  std::memcpy(P.m, proj, sizeof P.m);
+  const hs::M4 r = hs::proj_translate4(hs::V3<float>{off[0], off[1], off[2]}, P);
+  std::memcpy(out, r.m, sizeof r.m);
+  return HS_OK;
+}
+int32_t hs_proj_rotate_around(const float proj[16], const float center[3], const float R[9], float out[16]) {
+  if (!proj || !center || !R || !out) return HS_EINVAL;
+  hs::M4 P;
+  std::memcpy(P.m, proj, sizeof P.m);
+  const hs::M3<float> M{{{R[0], R[1], R[2]}, {R[3], R[4], R[5]}, {R[6], R[7], R[8]}}};
+  const hs::M4 r = hs::proj_rotate_around(hs::V3<float>{center[0], center[1], center[2]}, M, P);
+  std::memcpy(out, r.m, sizeof r.m);
+  return HS_OK;
+}
+
 int32_t hs_plane_corner(const float plane1[4], const float plane2[4], const float plane3[4], float corner_out[3]) {
   if (!plane1 || !plane2 || !plane3 || !corner_out) return HS_EINVAL;
   return hs::plane_corner(plane1, plane2, plane3, corner_out) ? HS_OK : HS_ESINGULAR;  // Nothing (Main.hs:1428-1430)

@@ -97,4 +97,33 @@ inline PlaneEq translate_plane_eq(V3<float> off, PlaneEq e) {                   
   return mk_plane_eq(e.n, dot(o2, e.n));
 }
 
+// Proj4 algebra (roomProj, Main.hs:314): 4x4 Float matrices for ROW vectors, translation in row 3; `.*.` is the plain matrix
+// product with every entry summed left to right ((a0 b0 + a1 b1) + a2 b2) + a3 b3
+struct M4 { float m[16]; };
+inline M4 proj_identity() { M4 r{}; r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.0f; return r; }
+inline M4 proj_compose(const M4& A, const M4& B) {
+  M4 r;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float acc = A.m[4 * i] * B.m[j];
+      for (int k = 1; k < 4; ++k) acc = acc + A.m[4 * i + k] * B.m[4 * k + j];
+      r.m[4 * i + j] = acc;
+    }
+  return r;
+}
+inline M4 proj_translate4(V3<float> v, const M4& M) {  // translate4 v: post-translation (Main.hs:1708)
+  M4 T = proj_identity();
+  T.m[12] = v.x; T.m[13] = v.y; T.m[14] = v.z;
+  return proj_compose(M, T);
+}
+inline M4 proj_linear(const M3<float>& R) {
+  M4 L = proj_identity();
+  for (int r = 0; r < 3; ++r) { L.m[4 * r] = R.r[r].x; L.m[4 * r + 1] = R.r[r].y; L.m[4 * r + 2] = R.r[r].z; }
+  return L;
+}
+inline M4 proj_rotate_around(V3<float> c, const M3<float>& R, const M4& M) {  // translate4 c . (.*. linear R) . translate4 (neg c), Main.hs:1674
+  const V3<float> nc{-c.x, -c.y, -c.z};
+  return proj_translate4(c, proj_compose(proj_translate4(nc, M), proj_linear(R)));
+}
+
 }  // namespace hs

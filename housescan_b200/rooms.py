@@ -97,6 +97,108 @@ def translatePlaneEq(offset, plane) -> np.ndarray:
     return out
 
 
+# ---- roomProj bookkeeping and the room movers (Main.hs:1665-1735) -------------------------------------------------------------------
+def _proj(fn_name, *args):
+    from . import _lib as L
+
+    out = np.empty(16, np.float32)
+    getattr(L.load(), fn_name)(*[L.ptr(a) for a in args], L.ptr(out))
+    return out.reshape(4, 4)
+
+
+def projCompose(a, b):
+    """`a .*. b` in Float (Main.hs:1720)"""
+    from . import _lib as L
+    return _proj("hs_proj_compose", L.as_f32(a, (16,)), L.as_f32(b, (16,)))
+
+
+def projTranslate(proj, off):
+    """`translate4 off proj` (Main.hs:1708)"""
+    from . import _lib as L
+    return _proj("hs_proj_translate", L.as_f32(proj, (16,)), L.as_f32(off, (3,)))
+
+
+def projRotateAround(proj, center, R):
+    """`translate4 c . (.*. linear R) . translate4 (neg c) $ proj` (Main.hs:1674)"""
+    from . import _lib as L
+    return _proj("hs_proj_rotate_around", L.as_f32(proj, (16,)), L.as_f32(center, (3,)), L.as_f32(R, (9,)))
+
+
+class Room:
+    """The moving parts of the reference's `Room` (Main.hs:308-316): planes (PlaneEq rows), the cloud, corners and roomProj, moved
+    together exactly as rotateRoomAround / translateRoom / projectRoom do (Main.hs:1665-1730).  The cloud lives wherever `engine`
+    keeps it: on the GPU the engine is a `Context` and the cloud a device `Cloud` (hs_rotate_around / hs_translate / hs_transform /
+    hs_mean_extent); anything with the same four methods will do.  Plane hull points are not carried (the GUI draws them; nothing on
+    the compute path reads them)."""
+
+    def __init__(self, engine, cloud, planes, corners=(), proj=None, name="ANON"):
+        self.engine, self.cloud, self.name = engine, cloud, name
+        self.planes = np.array(planes, np.float32).reshape(-1, 4)
+        self.corners = np.array(corners, np.float32).reshape(-1, 3)
+        self.proj = np.eye(4, dtype=np.float32) if proj is None else np.array(proj, np.float32).reshape(4, 4)
+
+    def roomMean(self) -> np.ndarray:
+        mean, _ = self.engine.mean_extent(self.cloud)  # cloudMean: Double sums on the GPU, then Float
+        return np.asarray(mean, np.float64).astype(np.float32)
+
+    def rotateRoomAround(self, center, R):
+        c, R = np.asarray(center, np.float32), np.asarray(R, np.float32).reshape(3, 3)
+        self.planes = np.stack([rotatePlaneEqAround(c, R, p) for p in self.planes]) if len(self.planes) else self.planes
+        self.cloud = self.engine.rotate_around(self.cloud, c, R)
+        self.corners = np.stack([_rotate_around(c, R, v) for v in self.corners]) if len(self.corners) else self.corners
+        self.proj = projRotateAround(self.proj, c, R)
+        return self
+
+    def rotateRoom(self, R):
+        return self.rotateRoomAround(self.roomMean(), R)
+
+    def translateRoom(self, off):
+        off = np.asarray(off, np.float32)
+        self.planes = np.stack([translatePlaneEq(off, p) for p in self.planes]) if len(self.planes) else self.planes
+        self.cloud = self.engine.translate(self.cloud, off)
+        self.corners = (self.corners + off).astype(np.float32)
+        self.proj = projTranslate(self.proj, off)
+        return self
+
+    def projectRoom(self, proj):
+        """rotate about the origin, then translate, with R and t read from the rows of `proj`; pattern-fails like the reference
+        unless the last column is exactly (0, 0, 0, 1) (Main.hs:1725-1728)"""
+        P = np.asarray(proj, np.float32).reshape(4, 4)
+        if not np.array_equal(P[:, 3], np.array([0, 0, 0, 1], np.float32)):
+            raise ValueError("projectRoom: last column of the projection is not (0,0,0,1)")
+        R, off, zero = P[:3, :3], P[3, :3], np.zeros(3, np.float32)
+        self.planes = np.stack([translatePlaneEq(off, rotatePlaneEqAround(zero, R, p)) for p in self.planes]) if len(self.planes) else self.planes
+        self.cloud = self.engine.transform(self.cloud, P)
+        if len(self.corners):  # corners go through the full 4-vector product: (x y z 1) .* proj
+            self.corners = np.stack([_row_times_proj(v, P) for v in self.corners])
+        self.proj = projCompose(self.proj, P)
+        return self
+
+
+def _rotate_around(c, R, p):
+    """rotateAround c R p = ((p - c) .* R) + c in Float, left-to-right sums (Main.hs:1582-1583)"""
+    f32 = np.float32
+    d = (np.asarray(p, f32) - c).astype(f32)
+    out = np.empty(3, f32)
+    for j in range(3):
+        out[j] = f32(f32(f32(d[0] * R[0, j]) + f32(d[1] * R[1, j])) + f32(d[2] * R[2, j]))
+    return (out + c).astype(f32)
+
+
+def _row_times_proj(v, P):
+    f32 = np.float32
+    x = np.array([v[0], v[1], v[2], 1.0], f32)
+    out = np.empty(4, f32)
+    for j in range(4):
+        acc = f32(x[0] * P[0, j])
+        for k in range(1, 4):
+            acc = f32(acc + f32(x[k] * P[k, j]))
+        out[j] = acc
+    if out[3] != f32(1.0):
+        raise ValueError("myTrim")  # Main.hs:1723-1724
+    return out[:3].copy()
+
+
 def planeCorner(plane1, plane2, plane3):
     """Main.hs:1413-1430: the point where three planes meet, or None when the 3x3 system is singular (`Nothing`)"""
     from . import _lib as L

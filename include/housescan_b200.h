@@ -169,6 +169,11 @@ HS_API int32_t hs_load_room(hs_ctx* ctx, const char* dir, hs_cloud** cloud_out, 
 HS_API int32_t hs_rotation_between_plane_eqs(const float plane1[4], const float plane2[4], float R_rowmajor_out[9]);
 HS_API int32_t hs_rotate_plane_eq_around(const float center[3], const float R_rowmajor[9], const float plane_in[4], float plane_out[4]);
 HS_API int32_t hs_translate_plane_eq(const float offset[3], const float plane_in[4], float plane_out[4]);
+/* roomProj bookkeeping (row-major 4x4, right-multiplied, Float): `a .*. b` (projectRoom, Main.hs:1720), `translate4 off proj`
+ * (translateRoom, :1708), `translate4 c . (.*. linear R) . translate4 (neg c) $ proj` (rotateRoomAround, :1674) */
+HS_API int32_t hs_proj_compose(const float a[16], const float b[16], float out[16]);
+HS_API int32_t hs_proj_translate(const float proj[16], const float offset[3], float out[16]);
+HS_API int32_t hs_proj_rotate_around(const float proj[16], const float center[3], const float R_rowmajor[9], float out[16]);
 /* planeCorner (Main.hs:1413-1430): the corner where three planes meet (3x3 solve in Double, result in Float);
  * HS_ESINGULAR = Nothing when the system has an exactly zero pivot (parallel planes) */
 HS_API int32_t hs_plane_corner(const float plane1[4], const float plane2[4], const float plane3[4], float corner_out[3]);

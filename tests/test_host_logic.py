@@ -232,3 +232,59 @@ def test_plane_corner_matches_lapack_and_the_cuboid_corners(built_lib):
     found = np.array([planeCorner(planes[i], planes[2 + j], planes[4 + k]) for i in (0, 1) for j in (0, 1) for k in (0, 1)])
     for c in corners:
         assert np.abs(found - c.astype(np.float32)).sum(axis=1).min() < 1e-5
+
+
+class _OracleEngine:
+    """CPU stand-in for the Context methods a Room uses (the oracle is the checker's cloud engine here)"""
+
+    def mean_extent(self, cloud):
+        return O.point_mean_f64(cloud), None
+
+    def rotate_around(self, cloud, c, R):
+        return O.rotate_cloud_around(cloud, c, R)
+
+    def translate(self, cloud, off):
+        return O.translate_cloud(cloud, off)
+
+    def transform(self, cloud, P):
+        return O.project_cloud(cloud, P)
+
+
+def test_proj_algebra_and_room_movers(built_lib):
+    """hs_proj_* against the oracle's Float matrix algebra (bit for bit), and rotateRoomAround / translateRoom / projectRoom
+    (Main.hs:1665-1730) moving planes, cloud, corners and roomProj consistently: replaying the accumulated roomProj on the fresh
+    room reproduces the incrementally moved one (the reference's projTest property, Main.hs:2543-2634)"""
+    from housescan_b200 import FitCuboidBFGS
+    from housescan_b200.rooms import Room, projCompose, projRotateAround, projTranslate
+
+    rng = np.random.default_rng(21)
+    A = rng.normal(size=(4, 4)).astype(np.float32)
+    B = rng.normal(size=(4, 4)).astype(np.float32)
+    c, off = rng.normal(size=3).astype(np.float32), rng.normal(size=3).astype(np.float32)
+    R = O.rot_matrix3([1, 2, 3], 0.7, np.float32)
+    assert np.array_equal(projCompose(A, B).view(np.uint32), O.proj_compose(A, B).view(np.uint32))
+    assert np.array_equal(projTranslate(A, off).view(np.uint32), O.proj_translate4(off, A).view(np.uint32))
+    assert np.array_equal(projRotateAround(A, c, R).view(np.uint32), O.proj_rotate_around(c, R, A).view(np.uint32))
+
+    params = np.array([0.3, -0.2, 4.0, 5.0, 2.6, 4.0, 0.9, 0.1, 0.3, 0.2])
+    xyz, _ = synth.cuboid_room_cloud(5_000, params, sigma=0.0, seed=3)
+    planes = hb.planes_from_cuboid(params)
+    corners = FitCuboidBFGS.cuboidFromParams(params).astype(np.float32)
+    room = Room(_OracleEngine(), xyz.copy(), planes, corners)
+    room.rotateRoom(O.rot_matrix3([1, 0, 0], math.radians(90), np.float32)).translateRoom([6, 0, -1.5]).rotateRoomAround([1, 2, 3], R)
+    fresh = Room(_OracleEngine(), xyz.copy(), planes, corners).projectRoom(room.proj)
+    assert np.allclose(room.cloud, fresh.cloud, atol=5e-5) and np.allclose(room.corners, fresh.corners, atol=5e-5)
+    assert np.allclose(room.planes, fresh.planes, atol=5e-5)
+    assert np.array_equal(fresh.proj.view(np.uint32), O.proj_compose(np.eye(4, dtype=np.float32), room.proj).view(np.uint32))
+    # the moved planes still carry the moved points: every point of the noiseless cloud lies on its nearest moved wall
+    a, r = O.plane_assign(room.cloud, room.planes)
+    assert np.abs(r).max() < 1e-4
+    # the moved corners are where the moved walls meet
+    from housescan_b200.rooms import planeCorner
+    found = np.array([planeCorner(room.planes[i], room.planes[2 + j], room.planes[4 + k]) for i in (0, 1) for j in (0, 1) for k in (0, 1)])
+    for cc in room.corners:
+        assert np.abs(found - cc).sum(axis=1).min() < 1e-4
+    with pytest.raises(ValueError, match="last column"):
+        bad = np.eye(4, dtype=np.float32)
+        bad[0, 3] = 0.5
+        room.projectRoom(bad)
