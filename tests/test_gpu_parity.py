@@ -354,7 +354,10 @@ def test_proj_replay_equivalence_on_gpu(ctx):
     mean, _ = ctx.mean_extent(ctx.translate(cl, [6, 0, 0]))
     m = mean.astype(np.float32)
     inc = ctx.rotate_around(ctx.translate(cl, [6, 0, 0]), m, Rx90).download()
-    proj = O.proj_rotate_around(m, Rx90, O.proj_translate4([6, 0, 0], O.proj_identity()))
+    from housescan_b200 import rooms
+
+    proj = rooms.projRotateAround(rooms.projTranslate(np.eye(4, dtype=np.float32), [6, 0, 0]), m, Rx90)  # the product's own roomProj algebra
+    assert np.array_equal(proj.view(np.uint32), O.proj_rotate_around(m, Rx90, O.proj_translate4([6, 0, 0], O.proj_identity())).view(np.uint32))
     rep = ctx.transform(cl, proj).download()
     assert np.allclose(inc, rep, atol=5e-5)
 
