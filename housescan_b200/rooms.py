@@ -175,6 +175,30 @@ class Room:
         return self
 
 
+def fitCuboidToRoom(room: "Room", conns=(), room_id=None):
+    """Main.fitCuboidToRoom (Main.hs:1814-1849): fit the 10-parameter cuboid to the room's 8 corners (fitCuboidFromCenterFirst, the
+    reference's Nelder-Mead), replace the room's planes by the cuboid's six walls (makePlanesFromCuboid) and its corners by the
+    cuboid's (corner order re-used positionally), and drop the wall connections that referred to the old planes of this room
+    (connections are (axis, relation, (room, wall), (room, wall)) as in connectWalls).
+    Returns (message lines, params, steps, err, remaining connections); with fewer than 8 corners nothing changes."""
+    from . import FitCuboidBFGS
+    from .core import planes_from_cuboid
+
+    log = [f"fitting cuboid to room {room_id if room_id is not None else room.name}"]
+    if len(room.corners) < 8:
+        log.append("not enough room corners; need 8")
+        return log, None, 0, None, list(conns)
+    params, steps, err, _ = FitCuboidBFGS.fitCuboidFromCenterFirst(np.asarray(room.corners[:8], np.float64))
+    log.append(f"fit cuboid in {steps} steps, RMSE: {float(np.sqrt(err))}")  # sqrt err, not divided by 8 (Main.hs:1827)
+    pf = np.asarray(params, np.float64).astype(np.float32).astype(np.float64)  # `map toFloat params` before the planes are made
+    room.planes = np.array(planes_from_cuboid(pf), np.float32).reshape(6, 4)
+    new = FitCuboidBFGS.cuboidFromParams(params).astype(np.float32)
+    k = min(len(new), len(room.corners))
+    room.corners = new[:k].copy()  # parallel list comprehension: as many corners as there were ids
+    kept = [w for w in conns if not (room_id is not None and (w[2][0] == room_id or w[3][0] == room_id))]
+    return log, np.asarray(params, np.float64), int(steps), float(err), kept
+
+
 def _rotate_around(c, R, p):
     """rotateAround c R p = ((p - c) .* R) + c in Float, left-to-right sums (Main.hs:1582-1583)"""
     f32 = np.float32

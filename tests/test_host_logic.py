@@ -288,3 +288,27 @@ def test_proj_algebra_and_room_movers(built_lib):
         bad = np.eye(4, dtype=np.float32)
         bad[0, 3] = 0.5
         room.projectRoom(bad)
+
+
+def test_fit_cuboid_to_room_glue(built_lib):
+    """Main.fitCuboidToRoom (Main.hs:1814-1849) on one of the reference's real rooms: planes and corners are replaced by the fitted
+    cuboid's, every plane holds exactly 4 of the 8 new corners (the reference's own assert, Main.hs:1881), connections of the
+    room's old walls disappear, fewer than 8 corners change nothing"""
+    from housescan_b200.rooms import X, Opposite, Room, fitCuboidToRoom
+
+    corners = np.array(json.load(open(os.path.join(os.path.dirname(__file__), "golden", "room_corners.json")))["testroom1"], np.float32)
+    room = Room(_OracleEngine(), np.zeros((4, 3), np.float32), np.zeros((0, 4), np.float32), corners)
+    conns = [(X, Opposite(0.1), (7, 0), (9, 1)), (X, Opposite(0.1), (3, 0), (4, 1))]
+    log, params, steps, err, kept = fitCuboidToRoom(room, conns, room_id=7)
+    assert steps > 50 and err < 1.0 and "RMSE" in log[1]  # the author's bar for these rooms (FitCuboidBFGS.hs:278)
+    assert kept == [(X, Opposite(0.1), (3, 0), (4, 1))]
+    assert room.planes.shape == (6, 4) and room.corners.shape == (8, 3)
+    on = np.abs(room.corners @ room.planes[:, :3].T - room.planes[:, 3]) < 1e-4
+    assert (on.sum(axis=0) == 4).all() and (on.sum(axis=1) == 3).all()  # 4 corners per wall, 3 walls per corner
+    # the fitted box sits on the picked corners as a SET: the ids are re-used positionally (Main.hs:1839), so id <-> place is the
+    # reference's to scramble; the closest-corner objective does not care about order
+    d = np.linalg.norm(room.corners[:, None, :] - corners[None, :, :], axis=2)
+    assert d.min(axis=1).max() < 0.6 and len(set(d.argmin(axis=1))) == 8
+    few = Room(_OracleEngine(), np.zeros((4, 3), np.float32), np.zeros((0, 4), np.float32), corners[:5])
+    log, params, steps, err, kept = fitCuboidToRoom(few, conns, room_id=7)
+    assert params is None and "need 8" in log[1] and kept == conns and len(few.corners) == 5
