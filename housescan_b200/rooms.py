@@ -160,6 +160,53 @@ class Room:
         self.proj = projTranslate(self.proj, off)
         return self
 
+    def roomAutoAlignAxis(self, axis):
+        """Main.roomAutoAlignAxis (Main.hs:1895-1906): the plane whose normal is most parallel to `axis` (maximumBy: the LAST of equal
+        maxima) is turned onto `axis` by rotating the whole room about its mean.  autoAlignFloor = roomAutoAlignAxis (0, 1, 0)."""
+        if len(self.planes) == 0:
+            return "room has no planes"
+        ax = np.asarray(axis, np.float32)
+        f32 = np.float32
+        dots = [f32(f32(f32(ax[0] * p[0]) + f32(ax[1] * p[1])) + f32(ax[2] * p[2])) for p in self.planes]
+        best = 0
+        for i in range(1, len(dots)):
+            if dots[i] >= dots[best]:  # Data.List.maximumBy keeps the last maximum
+                best = i
+        from . import _lib as L
+
+        target = np.empty(4, np.float32)  # mkPlaneEq axis 1
+        nrm = f32(np.sqrt(f32(f32(f32(ax[0] * ax[0]) + f32(ax[1] * ax[1])) + f32(ax[2] * ax[2]))))
+        inv = f32(f32(1.0) / nrm)
+        target[:3] = [f32(ax[0] * inv), f32(ax[1] * inv), f32(ax[2] * inv)]
+        target[3] = f32(f32(1.0) / nrm)
+        self.rotateRoom(rotationBetweenPlaneEqs(self.planes[best], target))
+        return None
+
+    def autoAlignFloor(self):
+        return self.roomAutoAlignAxis([0.0, 1.0, 0.0])
+
+    def suggestPoints(self, cutoff_factor=1.2):
+        """Main.suggestPoints (Main.hs:1521-1538): corners of every plane triple p < q < s (planeCorner), kept when they lie within
+        cutoffFactor x (largest distance of a cloud point from the room mean) of the room mean.  Mean and extent are the GPU
+        reductions of hs_mean_extent.  Returns (kept corners [m, 3], number of triples)."""
+        mean, maxdist = self.engine.mean_extent(self.cloud)
+        m = np.asarray(mean, np.float64).astype(np.float32)
+        cutoff = np.float32(np.float32(cutoff_factor) * np.float32(maxdist))
+        K, kept, triples = len(self.planes), [], 0
+        for i in range(K):
+            for j in range(i + 1, K):
+                for k in range(j + 1, K):
+                    triples += 1
+                    c = planeCorner(self.planes[i], self.planes[j], self.planes[k])
+                    if c is None:
+                        continue
+                    with np.errstate(over="ignore", invalid="ignore"):  # nearly parallel planes meet far away: inf / nan never pass the cutoff
+                        d = (c - m).astype(np.float32)
+                        dist = np.float32(np.sqrt(np.float32(np.float32(np.float32(d[0] * d[0]) + np.float32(d[1] * d[1])) + np.float32(d[2] * d[2]))))
+                    if dist <= cutoff:
+                        kept.append(c)
+        return (np.array(kept, np.float32).reshape(-1, 3), triples)
+
     def projectRoom(self, proj):
         """rotate about the origin, then translate, with R and t read from the rows of `proj`; pattern-fails like the reference
         unless the last column is exactly (0, 0, 0, 1) (Main.hs:1725-1728)"""

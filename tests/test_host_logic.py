@@ -238,7 +238,9 @@ class _OracleEngine:
     """CPU stand-in for the Context methods a Room uses (the oracle is the checker's cloud engine here)"""
 
     def mean_extent(self, cloud):
-        return O.point_mean_f64(cloud), None
+        m = O.point_mean_f64(cloud)
+        d = (np.asarray(cloud, np.float32) - m.astype(np.float32)).astype(np.float64)
+        return m, np.float32(np.sqrt((d * d).sum(axis=1).max()))
 
     def rotate_around(self, cloud, c, R):
         return O.rotate_cloud_around(cloud, c, R)
@@ -312,3 +314,26 @@ def test_fit_cuboid_to_room_glue(built_lib):
     few = Room(_OracleEngine(), np.zeros((4, 3), np.float32), np.zeros((0, 4), np.float32), corners[:5])
     log, params, steps, err, kept = fitCuboidToRoom(few, conns, room_id=7)
     assert params is None and "need 8" in log[1] and kept == conns and len(few.corners) == 5
+
+
+def test_auto_align_floor_and_corner_suggestions(built_lib):
+    """roomAutoAlignAxis / autoAlignFloor (Main.hs:1895-1910) and suggestPoints (Main.hs:1521-1538) on a tilted cuboid room: after the
+    alignment one wall normal is the up axis; the 6 planes have 20 triples of which exactly the 8 real corners survive the cutoff"""
+    from housescan_b200 import FitCuboidBFGS
+    from housescan_b200.rooms import Room
+
+    params = np.array([0.3, -0.2, 4.0, 5.0, 2.6, 4.0, 0.95, 0.05, 0.2, 0.1])  # a slightly tilted room
+    xyz, _ = synth.cuboid_room_cloud(4_000, params, sigma=0.0, seed=5)
+    room = Room(_OracleEngine(), xyz.copy(), hb.planes_from_cuboid(params), FitCuboidBFGS.cuboidFromParams(params).astype(np.float32))
+    before = room.planes.copy()
+    assert room.autoAlignFloor() is None
+    up = room.planes[:, 1]
+    assert np.isclose(up.max(), 1.0, atol=1e-6) and np.isclose(up.min(), -1.0, atol=1e-6)  # floor and ceiling normals are +-Y now
+    assert not np.allclose(before, room.planes)
+    a, r = O.plane_assign(room.cloud, room.planes)
+    assert np.abs(r).max() < 1e-4  # cloud and planes moved together
+    sugg, triples = room.suggestPoints(1.2)
+    assert triples == 20 and len(sugg) == 8
+    d = np.linalg.norm(sugg[:, None, :] - room.corners[None, :, :], axis=2)
+    assert d.min(axis=1).max() < 1e-4  # the suggestions are the room's corners
+    assert Room(_OracleEngine(), xyz, np.zeros((0, 4), np.float32)).autoAlignFloor() == "room has no planes"
