@@ -100,3 +100,4 @@ foreign import ccall unsafe "hs_plane_corner" c_plane_corner :: Ptr CFloat -> Pt
 foreign import ccall unsafe "hs_proj_compose" c_proj_compose :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
 foreign import ccall unsafe "hs_proj_translate" c_proj_translate :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
 foreign import ccall unsafe "hs_proj_rotate_around" c_proj_rotate_around :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
+foreign import ccall safe "hs_ply_info" c_ply_info :: CString -> Ptr Int64 -> Ptr Int32 -> Ptr Int32 -> IO Int32

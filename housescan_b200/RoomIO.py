@@ -108,3 +108,12 @@ def transformCloudFile(ctx: Context, src: str, matrix, dst: str):
         rgb = np.rint(col.download() * np.float32(255.0)).astype(np.uint8)
     (ctx.write_ply if dst.lower().endswith(".ply") else ctx.write_pcd)(out, dst, rgb)
     return len(out)
+
+
+def plyInfo(path: str):
+    """(vertices, has colours, "ascii" | "binary_little_endian") of a PLY file's header; raises on anything the reader would refuse"""
+    n, rgb, asc = C.c_int64(), C.c_int32(), C.c_int32()
+    rc = L.load().hs_ply_info(os.fsencode(path), C.byref(n), C.byref(rgb), C.byref(asc))
+    if rc != L.HS_OK:
+        raise HsError(rc, f"{path}: not a readable PLY vertex cloud")
+    return n.value, bool(rgb.value), ("ascii" if asc.value else "binary_little_endian")

@@ -83,6 +83,7 @@ SIGNATURES = {
     "hs_transform_from_text": (i32, [C.c_char_p, i64, vp]),
     "hs_cloud_from_ply": (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(vp)]),
     "hs_write_pcd": (i32, [vp, vp, vp, C.c_char_p]),
+    "hs_ply_info": (i32, [C.c_char_p, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
     "hs_kth_shard_pass": (i32, [vp, vp, i32, i32, u32, u32, vp]),
     "hs_kth_key_of_float": (u32, [f32]),
     "hs_kth_float_of_key": (f32, [u32]),

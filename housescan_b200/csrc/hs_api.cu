@@ -771,6 +771,23 @@ static int32_t staged_to_device(hs_ctx* ctx, const PcdStaged& st, int64_t n, con
   return HS_OK;
 }
 
+int32_t hs_ply_info(const char* path, int64_t* n_vertices, int32_t* has_rgb, int32_t* is_ascii) {
+  if (!path) return HS_EINVAL;
+  try {
+    std::vector<char> buf;
+    std::string err;
+    hs::PlyHeader h;
+    if (!hs::read_file(path, &buf, &err) || !hs::ply_parse_header(buf.data(), buf.size(), &h, &err)) return HS_EIO;
+    const int f[6] = {h.find("x"), h.find("y"), h.find("z"), h.find("red"), h.find("green"), h.find("blue")};
+    for (int c = 0; c < 3; ++c)
+      if (f[c] < 0 || h.sizes[f[c]] != 4 || (h.types[f[c]] != "float" && h.types[f[c]] != "float32")) return HS_EIO;
+    if (n_vertices) *n_vertices = h.n;
+    if (has_rgb) *has_rgb = f[3] >= 0 && f[4] >= 0 && f[5] >= 0 && h.sizes[f[3]] == 1 && h.sizes[f[4]] == 1 && h.sizes[f[5]] == 1;
+    if (is_ascii) *is_ascii = h.ascii ? 1 : 0;
+    return HS_OK;
+  } catch (const std::exception&) { return HS_ENOMEM; }
+}
+
 int32_t hs_cloud_from_pcd(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out) {
   if (!ctx) return HS_EINVAL;
   if (!path || !cloud_out) { ctx->err = "hs_cloud_from_pcd: bad arguments"; return HS_EINVAL; }

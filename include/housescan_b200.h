@@ -154,6 +154,7 @@ HS_API int32_t hs_pcd_info(const char* path, int64_t* n_points, int32_t* has_rgb
 HS_API int32_t hs_transform_from_text(const char* text, int64_t len, float m_rowmajor_out[16]);
 /* PLY vertex clouds: format ascii or binary_little_endian, `element vertex` first, float x y z [+ uchar red green blue] */
 HS_API int32_t hs_cloud_from_ply(hs_ctx* ctx, const char* path, hs_cloud** cloud_out, hs_cloud** colors_out);
+HS_API int32_t hs_ply_info(const char* path, int64_t* n_vertices, int32_t* has_rgb, int32_t* is_ascii); /* header only, no device */
 /* binary PCD v0.7, FIELDS x y z [rgb] (what pcl_transform_point_cloud ... -matrix would have written, Main.hs:2305-2313) */
 HS_API int32_t hs_write_pcd(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb_or_null, const char* path);
 

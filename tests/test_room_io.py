@@ -309,3 +309,34 @@ def test_golden_room_fixture_through_the_gpu_path(ctx):
     assert xyz[:3].view(np.uint32).tolist() == exp["cloud_first"] and c[:3].view(np.uint32).tolist() == exp["colors_first"]
     assert int(c.view(np.uint32).astype(np.uint64).sum()) == exp["colors_u32_sum"]
     assert planes.view(np.uint32).tolist() == exp["planes_inward"]
+
+
+def test_ply_header_parser_and_fuzz(built_lib, tmp_path):
+    xyz = np.arange(30, dtype=np.float32).reshape(10, 3)
+    p = str(tmp_path / "a.ply")
+    _write_ply_ascii(p, xyz, rgb=np.zeros((10, 3), int), extra=True)
+    assert RoomIO.plyInfo(p) == (10, True, "ascii")
+    bin_hdr = b"ply\nformat binary_little_endian 1.0\nelement vertex 10\nproperty float x\nproperty float y\nproperty float z\nend_header\n"
+    q = tmp_path / "b.ply"
+    q.write_bytes(bin_hdr + xyz.tobytes())
+    assert RoomIO.plyInfo(str(q)) == (10, False, "binary_little_endian")
+    rng = np.random.default_rng(5)
+    cases = [bin_hdr.replace(b"vertex 10", b"vertex 99999999999999") + xyz.tobytes(), bin_hdr.replace(b"float x", b"double x") + xyz.tobytes(),
+             bin_hdr.replace(b"binary_little_endian", b"binary_big_endian"), bin_hdr.replace(b"element vertex 10", b"element face 3"),
+             bin_hdr.replace(b"property float z", b"property list uchar int z"), b"ply\n", b"", bin_hdr[:-11]]
+    for _ in range(200):
+        b = bytearray(bin_hdr + xyz.tobytes())
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(0, len(bin_hdr)))] = int(rng.integers(32, 127))
+        cases.append(bytes(b))
+    ok = bad = 0
+    for i, c in enumerate(cases):
+        f = tmp_path / f"fz{i}.ply"
+        f.write_bytes(c)
+        try:
+            n, _, _ = RoomIO.plyInfo(str(f))
+            assert 0 <= n <= len(c)
+            ok += 1
+        except hb.HsError:
+            bad += 1
+    assert bad >= 8 and ok + bad == len(cases)
