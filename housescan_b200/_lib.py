@@ -49,6 +49,15 @@ SIGNATURES = {
     "hs_peer_mailbox_create": (i32, [vp, i32, i32, vp]),
     "hs_peer_mailbox_connect": (i32, [vp, vp]),
     "hs_rooms_cuboid_sums_allreduce_async": (i32, [vp, vp, vp, i32, vp, vp]),
+    "hs_peer_group_create_local": (i32, [vp, i32]),
+    "hs_eval_session_begin": (i32, [vp, vp, vp, i32, i32, C.POINTER(vp)]),
+    "hs_eval_session_post": (i32, [vp, vp, i32]),
+    "hs_eval_session_wait": (i32, [vp, i64, vp]),
+    "hs_eval_session_eval": (i32, [vp, vp, vp]),
+    "hs_eval_session_done": (i64, [vp]),
+    "hs_eval_session_device_results": (vp, [vp]),
+    "hs_eval_session_stop": (i32, [vp]),
+    "hs_eval_session_end": (i32, [vp]),
     "hs_cuboid_grad_from_sums": (i32, [vp, vp, C.POINTER(f64), vp, vp]),
     "hs_plane_sums": (i32, [vp, vp, vp, i32, vp, i32, vp]),
     "hs_scatter3x3": (i32, [vp, vp, vp, vp]),

@@ -14,13 +14,16 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libhousescan_b200.so")
-CU = ["hs_api.cu", "k_planes.cu", "k_eval_fast.cu", "k_eval_pred.cu", "k_transform.cu", "k_depth.cu", "k_graph.cu", "k_select.cu", "k_pcd.cu"]
+CU = ["hs_api.cu", "k_planes.cu", "k_eval.cu", "k_transform.cu", "k_depth.cu", "k_graph.cu", "k_select.cu", "k_pcd.cu"]
 HOST = ["hs_host.cpp", "hs_roomio.cpp"]
 HEADERS = [
     os.path.join(ROOT, "include", "housescan_b200.h"),
     os.path.join(HERE, "csrc", "hs_internal.cuh"),
     os.path.join(HERE, "csrc", "k_common.cuh"),
     os.path.join(HERE, "csrc", "k_ring.cuh"),
+    os.path.join(HERE, "csrc", "k_eval.cuh"),
+    os.path.join(HERE, "csrc", "k_eval_point.cuh"),
+    os.path.join(HERE, "csrc", "k_peer.cuh"),
     os.path.join(HERE, "host", "hs_host.hpp"),
     os.path.join(HERE, "host", "vec.hpp"),
 ]

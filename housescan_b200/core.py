@@ -40,6 +40,75 @@ class Cloud:
             pass
 
 
+class EvalSession:
+    """A resident multi-evaluation kernel (`hs_eval_session_*`): the cloud and the room offsets are fixed, parameter sets are
+    posted one after the other (or many at once) and every evaluation's records come back without a relaunch."""
+
+    def __init__(self, ctx: "Context", cloud: Cloud, room_offsets, allreduce: bool = False):
+        self.ctx = ctx
+        self._ro = np.ascontiguousarray(room_offsets, dtype=np.int64)
+        self.nrooms = self._ro.size - 1
+        self._keep = cloud
+        self.posted = 0
+        h = C.c_void_p()
+        ctx._chk(ctx.lib.hs_eval_session_begin(ctx.h, cloud.h, ptr(self._ro), self.nrooms, 1 if allreduce else 0, C.byref(h)))
+        self.h = h
+
+    def post(self, params) -> int:
+        """enqueue evaluations (params: count x nrooms x 10); returns the sequence number of the last one"""
+        p = as_f64(params).reshape(-1, self.nrooms, 10)
+        self.ctx._chk(self.ctx.lib.hs_eval_session_post(self.h, ptr(p), p.shape[0]))
+        self.posted += p.shape[0]
+        return self.posted - 1
+
+    def wait(self, seq: int, want_record: bool = True):
+        rec = np.empty((self.nrooms, HS_REC), np.float64) if want_record else None
+        self.ctx._chk(self.ctx.lib.hs_eval_session_wait(self.h, seq, ptr(rec)))
+        return rec
+
+    def eval(self, params) -> np.ndarray:
+        p = as_f64(params, (self.nrooms, 10))
+        rec = np.empty((self.nrooms, HS_REC), np.float64)
+        self.ctx._chk(self.ctx.lib.hs_eval_session_eval(self.h, ptr(p), ptr(rec)))
+        self.posted += 1
+        return rec
+
+    @property
+    def done(self) -> int:
+        return int(self.ctx.lib.hs_eval_session_done(self.h))
+
+    @property
+    def device_results_ptr(self) -> int:
+        return int(self.ctx.lib.hs_eval_session_device_results(self.h) or 0)
+
+    def stop(self):
+        self.ctx._chk(self.ctx.lib.hs_eval_session_stop(self.h))
+
+    def close(self):
+        if self.h:
+            h, self.h = self.h, None
+            self.ctx._chk(self.ctx.lib.hs_eval_session_end(h))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.h:
+            h, self.h = self.h, None
+            rc = self.ctx.lib.hs_eval_session_end(h)
+            if exc[0] is None:
+                self.ctx._chk(rc)
+        return False
+
+
+def peer_group_local(ctxs) -> None:
+    """ranks = the given contexts (one per device, all in this process): `hs_peer_group_create_local`"""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = L.load().hs_peer_group_create_local(arr, len(ctxs))
+    if rc:
+        raise HsError(rc, (L.load().hs_last_error(ctxs[0].h) or b"").decode())
+
+
 class Context:
     """One CUDA device + stream (`hs_ctx`).  Raises HsError(HS_ECUDA) when no sm_100 GPU is present."""
 
@@ -164,6 +233,9 @@ class Context:
     def rooms_cuboid_sums_allreduce_async(self, cloud: Cloud, room_offsets: np.ndarray, params: np.ndarray, d_rec_ptr: int):
         self._chk(self.lib.hs_rooms_cuboid_sums_allreduce_async(self.h, cloud.h, ptr(room_offsets), room_offsets.size - 1, ptr(params), C.c_void_p(d_rec_ptr)))
 
+    def eval_session(self, cloud: Cloud, room_offsets, allreduce: bool = False) -> EvalSession:
+        return EvalSession(self, cloud, room_offsets, allreduce)
+
     def plane_sums(self, cloud: Cloud, room_offsets, planes, K: int):
         ro = np.ascontiguousarray(room_offsets, dtype=np.int64)
         nrooms = ro.size - 1
@@ -185,17 +257,17 @@ class Context:
 
     # -- (3) transforms
     def transform(self, cloud: Cloud, m, out: Cloud | None = None) -> Cloud:
-        out = out or self.alloc(len(cloud))
+        out = out if out is not None else self.alloc(len(cloud))
         self._chk(self.lib.hs_transform(self.h, cloud.h, ptr(as_f32(m, (16,))), out.h))
         return out
 
     def rotate_around(self, cloud: Cloud, center, R, out: Cloud | None = None) -> Cloud:
-        out = out or self.alloc(len(cloud))
+        out = out if out is not None else self.alloc(len(cloud))
         self._chk(self.lib.hs_rotate_around(self.h, cloud.h, ptr(as_f32(center, (3,))), ptr(as_f32(R, (9,))), out.h))
         return out
 
     def translate(self, cloud: Cloud, off, out: Cloud | None = None) -> Cloud:
-        out = out or self.alloc(len(cloud))
+        out = out if out is not None else self.alloc(len(cloud))
         self._chk(self.lib.hs_translate(self.h, cloud.h, ptr(as_f32(off, (3,))), out.h))
         return out
 
@@ -255,7 +327,7 @@ class Context:
         out = self.alloc(len(cloud))
         cout = self.alloc(len(cloud)) if colors is not None else None
         n = C.c_int64()
-        self._chk(self.lib.hs_filter_le(self.h, cloud.h, axis, limit, colors.h if colors else None, out.h, cout.h if cout else None, C.byref(n)))
+        self._chk(self.lib.hs_filter_le(self.h, cloud.h, axis, limit, colors.h if colors is not None else None, out.h, cout.h if cout is not None else None, C.byref(n)))
         return out, cout
 
     def remove_ceiling(self, cloud: Cloud, colors: Cloud | None = None):
@@ -263,7 +335,7 @@ class Context:
         cout = self.alloc(len(cloud)) if colors is not None else None
         n = C.c_int64()
         yl = C.c_float()
-        self._chk(self.lib.hs_remove_ceiling(self.h, cloud.h, colors.h if colors else None, out.h, cout.h if cout else None, C.byref(n), C.byref(yl)))
+        self._chk(self.lib.hs_remove_ceiling(self.h, cloud.h, colors.h if colors is not None else None, out.h, cout.h if cout is not None else None, C.byref(n), C.byref(yl)))
         return out, cout, np.float32(yl.value)
 
     # -- optimiser on the cloud

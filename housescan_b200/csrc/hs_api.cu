@@ -8,13 +8,19 @@
 
 #include "../host/hs_host.hpp"
 #include "hs_internal.cuh"
+#include "k_peer.cuh"
 
 static thread_local std::string g_create_err;
 
+// Every entry point that touches the device goes through here: one in-flight call per ctx; an open evaluation session owns the
+// stream (anything enqueued behind its resident kernel would wait for hs_eval_session_end); and a peer exchange that timed out
+// in an earlier asynchronous call is reported by the next call as HS_ENCCL (the kernels raise the mapped status word).
 #define HS_LOCK(ctx)                                     \
   if (!(ctx)) return HS_EINVAL;                          \
   std::lock_guard<std::mutex> lock__((ctx)->mu);         \
-  if (cudaSetDevice((ctx)->device) != cudaSuccess) { (ctx)->err = "cudaSetDevice failed"; return HS_ECUDA; }
+  if (cudaSetDevice((ctx)->device) != cudaSuccess) { (ctx)->err = "cudaSetDevice failed"; return HS_ECUDA; } \
+  if ((ctx)->session) { (ctx)->err = "an evaluation session is open on this context: hs_eval_session_end first"; return HS_EINVAL; } \
+  if ((ctx)->h_status && *(volatile uint32_t*)(ctx)->h_status) { *(volatile uint32_t*)(ctx)->h_status = 0; (ctx)->err = "a peer did not deliver its records in an earlier exchange (timed out); the records of that call are NaN"; return HS_ENCCL; }
 
 #define HS_FAIL(ctx, code, msg) \
   do { (ctx)->err = (msg); return (code); } while (0)
@@ -79,6 +85,9 @@ int32_t hs_ctx_create(int32_t device, hs_ctx** out) {
   if ((e = cudaMalloc(&ctx->d_ticket, 256)) != cudaSuccess) return fail(e);
   if ((e = cudaMemset(ctx->d_ticket, 0, 256)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&ctx->d_small, sizeof(double) * (HS_MAX_ROOMS * HS_REC + 64))) != cudaSuccess) return fail(e);
+  if ((e = cudaHostAlloc(&ctx->h_status, 64, cudaHostAllocMapped)) != cudaSuccess) return fail(e);
+  std::memset(ctx->h_status, 0, 64);
+  if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_status), ctx->h_status, 0)) != cudaSuccess) return fail(e);
   if (hs_ensure_scratch(ctx, 1 << 22) != HS_OK || hs_ensure_pinned(ctx, 1 << 20) != HS_OK) { g_create_err = ctx->err; delete ctx; return HS_ECUDA; }
   // tuning knobs can also come from the environment (HS_MODE_<key>=<value>, keys as in hs_ctx_set_mode)
   for (int k = 0; k < 16; ++k) {
@@ -89,24 +98,19 @@ int32_t hs_ctx_create(int32_t device, hs_ctx** out) {
   return HS_OK;
 }
 
-// tools only (not in the public header): per-block {start, main loop done, end, is_last} timestamps of the last evaluation launch
-extern "C" HS_API int32_t hs_dbg_block_times(hs_ctx* ctx, unsigned long long* out, int32_t nblocks) {
-  if (!ctx || !ctx->d_dbg || nblocks > 1024) return HS_EINVAL;
-  cudaStreamSynchronize(ctx->stream);
-  return cudaMemcpy(out, ctx->d_dbg, sizeof(unsigned long long) * 4 * nblocks, cudaMemcpyDeviceToHost) == cudaSuccess ? HS_OK : HS_ECUDA;
-}
-
 int32_t hs_ctx_destroy(hs_ctx* ctx) {
   if (!ctx) return HS_OK;
+  if (ctx->session) hs_eval_session_end(ctx->session);  // stops the resident kernel
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  hs_eval_state_free(ctx);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_small) cudaFree(ctx->d_small);
-  if (ctx->d_dbg) cudaFree(ctx->d_dbg);
   for (int p = 0; p < HS_PEER_MAX; ++p) if (ctx->peer_mapped[p]) cudaIpcCloseMemHandle(ctx->peer_mapped[p]);
   if (ctx->d_mailbox) cudaFree(ctx->d_mailbox);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return HS_OK;
@@ -130,10 +134,6 @@ int64_t hs_ctx_launch_count(const hs_ctx* ctx) { return ctx ? ctx->launches : 0;
 int32_t hs_ctx_set_mode(hs_ctx* ctx, int32_t key, int32_t value) {
   if (!ctx || key < 0 || key >= 16) return HS_EINVAL;
   ctx->modes[key] = value;
-  if (key == HS_MODE_DEBUG_TIMES && value && !ctx->d_dbg) {
-    HS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_dbg, sizeof(unsigned long long) * 4 * 1024));
-    HS_CUDA_TRY(ctx, cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 4 * 1024));
-  }
   return HS_OK;
 }
 
@@ -342,20 +342,14 @@ static int32_t rooms_sums_enqueue(hs_ctx* ctx, const hs_cloud* cloud, const int6
     t.off[t.nrooms] = room_offsets[r0 + t.nrooms];
     const int mode = ctx->modes[HS_MODE_EVAL_KERNEL];
     if (mode == HS_EVAL_FAST && !t.paired) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: fast kernel needs antiparallel plane pairs");
-    const bool fast = t.paired && mode != HS_EVAL_EXACT;
-    // mode key 3 picks the throughput kernel: 0 (default) warp-accumulator scalar form, 2 / 5 / 6 its tuning relatives
-    // (k_eval_pred.cu), 7 / 1 / 4 the packed f32x2 forms (k_eval_fast.cu).  All produce the same record.
-    const int var = ctx->modes[HS_MODE_EVAL_VARIANT];
-    const bool scalar_family = var == 0 || var == 2 || var == 5 || var == 6;
-    auto launch = !fast ? launch_rooms_cuboid_sums : (scalar_family ? launch_rooms_cuboid_sums_pred : launch_rooms_cuboid_sums_fast);
     const bool want_exchange = exchange && ctx->px.world > 1;
-    ctx->px_next = want_exchange;  // the default kernel folds the exchange into its tail and clears this
-    if (int32_t rc = launch(ctx, cloud->d, cloud->n, t, d_out + static_cast<size_t>(r0) * HS_REC)) { ctx->px_next = false; return rc; }
-    if (ctx->px_next) {  // any other kernel: one more (single-block) launch does the exchange
-      ctx->px_next = false;
-      PeerExchange px = ctx->px;
-      px.epoch = ++ctx->px.epoch;
-      if (int32_t rc = launch_peer_allreduce(ctx, d_out + static_cast<size_t>(r0) * HS_REC, t.nrooms * HS_REC, px)) return rc;
+    double* d_chunk = d_out + static_cast<size_t>(r0) * HS_REC;
+    if (t.paired && mode != HS_EVAL_EXACT) {  // throughput kernel (k_eval.cuh): the exchange happens inside the same launch
+      if (int32_t rc = launch_eval(ctx, cloud->d, cloud->n, t, d_chunk, want_exchange)) return rc;
+    } else {  // exact-products Double kernel (k_planes.cu) + one more single-warp launch for the exchange
+      if (int32_t rc = launch_rooms_cuboid_sums(ctx, cloud->d, cloud->n, t, d_chunk)) return rc;
+      if (want_exchange)
+        if (int32_t rc = launch_peer_allreduce(ctx, d_chunk, t.nrooms * HS_REC)) return rc;
     }
   }
   return HS_OK;
@@ -380,7 +374,7 @@ int32_t hs_peer_mailbox_create(hs_ctx* ctx, int32_t rank, int32_t world, uint8_t
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   if (!handle_out || world < 1 || world > HS_PEER_MAX || rank < 0 || rank >= world) HS_FAIL(ctx, HS_EINVAL, "hs_peer_mailbox_create: need 0 <= rank < world <= 8");
   if (ctx->d_mailbox) HS_FAIL(ctx, HS_EINVAL, "hs_peer_mailbox_create: this context already has a mailbox");
-  const size_t bytes = static_cast<size_t>(2) * HS_PEER_MAX * HS_MAX_ROOMS * HS_REC * sizeof(double) + HS_PEER_MAX * 32 * sizeof(uint32_t);
+  const size_t bytes = hsk::PEER_MAILBOX_BYTES;
   HS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_mailbox, bytes));
   HS_CUDA_TRY(ctx, cudaMemset(ctx->d_mailbox, 0, bytes));
   HS_CUDA_TRY(ctx, cudaDeviceSynchronize());
@@ -410,6 +404,45 @@ int32_t hs_peer_mailbox_connect(hs_ctx* ctx, const uint8_t* handles) {
   ctx->px.world = world;
   ctx->px.epoch = 0;
   ctx->px.pad = 0;
+  return HS_OK;
+}
+
+// Same-process peer group (one Haskell executable driving several GPUs, housescan.cabal:15-43): ctxs[i] becomes rank i of an
+// n-rank group.  CUDA IPC cannot open a handle in the process that created it, so the mailboxes are addressed directly after
+// cudaDeviceEnablePeerAccess.  The asynchronous entry points may then be issued for all ranks from one host thread.
+int32_t hs_peer_group_create_local(hs_ctx* const* ctxs, int32_t n) {
+  if (!ctxs || n < 1 || n > HS_PEER_MAX) return HS_EINVAL;
+  for (int i = 0; i < n; ++i) {
+    if (!ctxs[i]) return HS_EINVAL;
+    for (int j = 0; j < i; ++j)
+      if (ctxs[j] == ctxs[i] || ctxs[j]->device == ctxs[i]->device) { ctxs[i]->err = "hs_peer_group_create_local: one context per device"; return HS_EINVAL; }
+    if (ctxs[i]->d_mailbox || ctxs[i]->session) { ctxs[i]->err = "hs_peer_group_create_local: context already has a mailbox or an open session"; return HS_EINVAL; }
+  }
+  for (int i = 0; i < n; ++i) {
+    hs_ctx* ctx = ctxs[i];
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    HS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int j = 0; j < n; ++j) {
+      if (j == i) continue;
+      int can = 0;
+      HS_CUDA_TRY(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[j]->device));
+      if (!can) { ctx->err = "hs_peer_group_create_local: device " + std::to_string(ctx->device) + " cannot access device " + std::to_string(ctxs[j]->device); return HS_ECUDA; }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return HS_ECUDA; }
+      (void)cudaGetLastError();
+    }
+    HS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_mailbox, hsk::PEER_MAILBOX_BYTES));
+    HS_CUDA_TRY(ctx, cudaMemset(ctx->d_mailbox, 0, hsk::PEER_MAILBOX_BYTES));
+    HS_CUDA_TRY(ctx, cudaDeviceSynchronize());
+  }
+  for (int i = 0; i < n; ++i) {
+    hs_ctx* ctx = ctxs[i];
+    ctx->px = PeerExchange{};
+    for (int j = 0; j < n; ++j) ctx->px.mailbox[j] = reinterpret_cast<unsigned long long>(ctxs[j]->d_mailbox);
+    ctx->px.rank = i;
+    ctx->px.world = n;
+    ctx->peer_local = true;
+  }
   return HS_OK;
 }
 

@@ -14,13 +14,16 @@
 #define HS_PEER_MAX 8     // ranks in a peer-memory all-reduce group (one NVSwitch domain)
 #define HS_NACC 22        // accumulators of a cuboid-sums record actually reduced (f, Sr[6], B[9], cnt[6])
 
-// peer-memory all-reduce of the record (k_peer.cuh); world == 0: no exchange
+// peer-memory all-reduce of the record (k_peer.cuh); world <= 1: no exchange
 struct PeerExchange {
   unsigned long long mailbox[HS_PEER_MAX];  // device address of every rank's mailbox; [rank] is the local one
   int32_t rank, world;
-  uint32_t epoch;  // launch counter, > 0, identical on all ranks
+  uint32_t epoch;  // host side: evaluations exchanged so far (the next one uses epoch + 1); identical on all ranks
   uint32_t pad;
 };
+
+struct hs_eval_state;    // k_eval.cu: plan cache, control block, partial-record ring of the evaluation kernel
+struct hs_eval_session;  // k_eval.cu: a resident multi-evaluation kernel
 
 struct hs_cloud {
   float* d = nullptr;
@@ -49,13 +52,16 @@ struct hs_ctx {
   char* d_mailbox = nullptr;
   void* peer_mapped[HS_PEER_MAX] = {nullptr};
   PeerExchange px = {};
-  bool px_next = false;
-  unsigned long long* d_dbg = nullptr;  // per-block timestamps of the evaluation kernel (mode key 5; tools only)
+  bool peer_local = false;           // mailboxes of a same-process group: addressed directly, nothing to close
+  uint32_t* h_status = nullptr;      // mapped pinned word the kernels raise (HS_ENCCL on a peer timeout); d_status is its device alias
+  uint32_t* d_status = nullptr;
+  hs_eval_state* eval = nullptr;     // evaluation kernel state (lazily created)
+  hs_eval_session* session = nullptr;  // open evaluation session: it owns the stream until it ends
   std::mutex mu;
 };
 
-enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1, HS_MODE_EVAL_CONSUMERS = 2, HS_MODE_EVAL_VARIANT = 3, HS_MODE_EVAL_TPI = 4, HS_MODE_DEBUG_TIMES = 5,
-       HS_MODE_PRODUCER_SLEEP = 6,  // packed-form evaluation kernel only: ns the producer sleeps between polls (tools)
+enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1,
+       HS_MODE_EVAL_SEG_COST = 2,  // evaluation kernel: cost of an extra room segment in 4-point groups for the weighted partition (0 = default)
        HS_MODE_PS_KERNEL = 7,   // per-plane sums: 0 = ring form (bulk-async tiles, warp-level flushes), 1 = all-Double form, 2 = direct-load Float chains
        HS_MODE_SEL_KERNEL = 8,  // k-th: 0 = 11/11/10-bit passes over compacted keys, 1 = four 8-bit passes over the cloud
        HS_MODE_FILTER_KERNEL = 12,  // order-preserving filter: 0 = count pass + scatter pass, 1 = single pass (decoupled look-back)
@@ -101,9 +107,10 @@ int32_t hs_ensure_scratch(hs_ctx* ctx, size_t bytes);
 int32_t hs_ensure_pinned(hs_ctx* ctx, size_t bytes);
 
 int32_t launch_rooms_cuboid_sums(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);       // exact Double products
-int32_t launch_rooms_cuboid_sums_fast(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);  // packed f32x2 + TMA ring
-int32_t launch_rooms_cuboid_sums_pred(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out);  // scalar predicated + TMA ring
-int32_t launch_peer_allreduce(hs_ctx* ctx, double* d_buf, int count, const PeerExchange& px);  // standalone exchange kernel
+// throughput kernel (k_eval.cu): paired planes only; exchange = sum the records over the peer group inside the same launch
+int32_t launch_eval(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& tbl, double* d_rec_out, bool exchange);
+int32_t launch_peer_allreduce(hs_ctx* ctx, double* d_buf, int count);  // standalone exchange kernel (next epoch)
+void hs_eval_state_free(hs_ctx* ctx);
 int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const PlaneTable& tbl, uint8_t* d_assign, float* d_resid);
 int32_t launch_plane_sums(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out /*K*HS_PS*/);
 

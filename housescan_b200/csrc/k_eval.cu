@@ -1,0 +1,403 @@
+// Host side of the evaluation kernel (k_eval.cuh): the weighted static partition, the one-shot launcher behind
+// hs_rooms_cuboid_sums*, the standalone peer exchange, and the evaluation session API (hs_eval_session_*): a resident kernel
+// that evaluates one parameter set after the other without relaunching — what FitCuboidBFGS's optimiser loop
+// (FitCuboidBFGS.hs:184,201,233: up to 2000 objective evaluations per stage) needs from the device.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <new>
+#include <thread>
+
+#include "../host/hs_host.hpp"
+#include "k_eval.cuh"
+
+namespace hsk {
+
+// product configuration: 12 consumer warps, 3 ring stages of 72 KB, 16 points per thread per tile, Float chains of 256 points
+constexpr int EVK_NCONS = 384, EVK_STAGES = 3, EVK_GPT = 4, EVK_FLUSH = 16;
+constexpr int EVK_SEG_COST_DEFAULT = 768;  // an extra room segment in a block costs about this many 4-point groups (flush + block sum)
+
+constexpr size_t eval_smem_bytes() {
+  return static_cast<size_t>(EVK_STAGES) * EVK_GPT * EVK_NCONS * 48 + 2 * EVK_STAGES * 8 + static_cast<size_t>(2) * (EVK_NCONS / 32) * EV_NRAW * 8 +
+         static_cast<size_t>(EV_PARK) * EV_NRAW * 8;
+}
+
+// standalone exchange for the kernels that do not carry it in their tail (one warp)
+__global__ void __launch_bounds__(32) k_peer_allreduce(double* buf, int count, uint32_t epoch, uint32_t* h_status, const __grid_constant__ PeerExchange px) {
+  peer_push_warp(px, epoch, buf, count);
+  if (!peer_collect_warp(px, epoch, buf, count) && threadIdx.x == 0 && h_status) st_sys_u32(h_status, static_cast<uint32_t>(HS_ENCCL));
+}
+
+}  // namespace hsk
+
+using namespace hsk;
+
+struct hs_eval_state {
+  EvalPlan h_plan;
+  bool plan_valid = false;
+  int plan_seg_cost = 0;
+  EvalPlan* d_plan = nullptr;
+  EvalCtl* d_ctl = nullptr;
+  double* d_partials = nullptr;
+  size_t partials_bytes = 0;
+  double* d_local_rec = nullptr;
+  bool attr_set[2] = {false, false};
+};
+
+struct hs_eval_session {
+  hs_ctx* ctx = nullptr;
+  int32_t nrooms = 0;
+  bool exchange = false;
+  EvalCmd* h_cmds = nullptr;   // mapped
+  EvalCmd* d_cmds = nullptr;
+  EvalHostCtl* h_ctl = nullptr;  // mapped
+  double* h_results = nullptr;   // mapped
+  double* d_results = nullptr;
+  uint32_t posted = 0;
+  bool stopped = false;
+  bool empty = false;  // no point in any room: records are zero, no kernel runs
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// static partition: blocks get contiguous ranges of 4-point groups; a block pays `seg_cost` groups for every room boundary inside
+// its range, so that blocks with two segments finish together with the others
+static int64_t plan_walk(int64_t G, int nb, int64_t target, int seg_cost, const int64_t* bounds, int nbounds, int64_t* g0_out) {
+  int64_t g = 0;
+  for (int b = 0; b < nb; ++b) {
+    if (g0_out) g0_out[b] = g;
+    int64_t end = std::min(G, g + target);
+    for (int it = 0; it < 2; ++it) {  // boundaries strictly inside (4g, 4 end) cost seg_cost groups each
+      int k = 0;
+      for (int i = 0; i < nbounds; ++i) k += (bounds[i] > 4 * g && bounds[i] < 4 * end);
+      end = std::max(std::min(G, g + 1), std::min(G, g + target - static_cast<int64_t>(k) * seg_cost));
+    }
+    g = end;
+  }
+  if (g0_out) g0_out[nb] = G;
+  return g;
+}
+
+static void build_plan(EvalPlan& P, int64_t n, const int64_t* off, int nrooms, int nb_max, int seg_cost) {
+  std::memset(&P, 0, sizeof P);
+  P.n = n;
+  P.nrooms = nrooms;
+  for (int r = 0; r <= nrooms; ++r) P.off[r] = off[r];
+  const int64_t G = (n + 3) >> 2;
+  int64_t nb = std::min<int64_t>(nb_max, (G + EVK_NCONS - 1) / EVK_NCONS);
+  nb = std::max<int64_t>(1, std::min<int64_t>(nb, EV_MAXB));
+  P.nblocks = static_cast<int32_t>(nb);
+  int64_t bounds[HS_MAX_ROOMS];
+  int nbounds = 0;
+  for (int r = 0; r < nrooms; ++r) {
+    if (off[r + 1] > off[r]) {
+      ++P.nrooms_nonempty;
+      if (off[r] > off[0] && off[r] > 0) bounds[nbounds++] = off[r];  // start of a non-empty room that is not the first point
+    }
+  }
+  // smallest target for which nb blocks cover all groups
+  int64_t lo = (G + nb - 1) / nb, hi = lo + static_cast<int64_t>(seg_cost) * (nbounds + 1) + 1;
+  lo = std::max<int64_t>(lo, 1);
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (plan_walk(G, static_cast<int>(nb), mid, seg_cost, bounds, nbounds, nullptr) >= G) hi = mid; else lo = mid + 1;
+  }
+  plan_walk(G, static_cast<int>(nb), lo, seg_cost, bounds, nbounds, P.blk_g0);
+  for (int r = 0; r < nrooms; ++r) { P.room_blo[r] = 0; P.room_nb[r] = 0; }
+  for (int b = 0; b < nb; ++b) {
+    const int64_t p0 = P.blk_g0[b] * 4, p1 = std::min(P.blk_g0[b + 1] * 4, n);
+    int rfirst = 0, rlast = -1;
+    bool any = false;
+    for (int r = 0; r < nrooms; ++r)
+      if (off[r] < p1 && off[r + 1] > p0 && off[r + 1] > off[r] && p1 > p0) {
+        if (!any) { rfirst = r; any = true; }
+        rlast = r;
+        if (P.room_nb[r] == 0) P.room_blo[r] = b;
+        P.room_nb[r] += 1;
+      }
+    P.blk_rfirst[b] = rfirst;
+    P.blk_rlast[b] = rlast;
+  }
+}
+
+static int32_t eval_state(hs_ctx* ctx, hs_eval_state** out) {
+  if (!ctx->eval) {
+    hs_eval_state* st = new (std::nothrow) hs_eval_state();
+    if (!st) { ctx->err = "out of host memory"; return HS_ENOMEM; }
+    ctx->eval = st;
+    HS_CUDA_TRY(ctx, cudaMalloc(&st->d_plan, sizeof(EvalPlan)));
+    HS_CUDA_TRY(ctx, cudaMalloc(&st->d_ctl, sizeof(EvalCtl)));
+    HS_CUDA_TRY(ctx, cudaMemset(st->d_ctl, 0, sizeof(EvalCtl)));
+    HS_CUDA_TRY(ctx, cudaMalloc(&st->d_local_rec, sizeof(double) * EV_D * HS_MAX_ROOMS * HS_REC));
+  }
+  *out = ctx->eval;
+  return HS_OK;
+}
+
+void hs_eval_state_free(hs_ctx* ctx) {
+  hs_eval_state* st = ctx->eval;
+  if (!st) return;
+  if (st->d_plan) cudaFree(st->d_plan);
+  if (st->d_ctl) cudaFree(st->d_ctl);
+  if (st->d_partials) cudaFree(st->d_partials);
+  if (st->d_local_rec) cudaFree(st->d_local_rec);
+  delete st;
+  ctx->eval = nullptr;
+}
+
+// plan for (n, offsets) on this ctx: rebuilt and uploaded only when it changes
+static int32_t eval_prepare(hs_ctx* ctx, int64_t n, const int64_t* off, int nrooms, hs_eval_state** out) {
+  hs_eval_state* st = nullptr;
+  if (int32_t rc = eval_state(ctx, &st)) return rc;
+  const int seg_cost = ctx->modes[HS_MODE_EVAL_SEG_COST] > 0 ? ctx->modes[HS_MODE_EVAL_SEG_COST] : (ctx->modes[HS_MODE_EVAL_SEG_COST] < 0 ? 0 : EVK_SEG_COST_DEFAULT);
+  bool same = st->plan_valid && st->h_plan.n == n && st->h_plan.nrooms == nrooms && st->plan_seg_cost == seg_cost;
+  for (int r = 0; same && r <= nrooms; ++r) same = st->h_plan.off[r] == off[r];
+  if (!same) {
+    build_plan(st->h_plan, n, off, nrooms, ctx->sm_count, seg_cost);
+    st->plan_seg_cost = seg_cost;
+    HS_CUDA_TRY(ctx, cudaMemcpyAsync(st->d_plan, &st->h_plan, sizeof(EvalPlan), cudaMemcpyHostToDevice, ctx->stream));
+    st->plan_valid = true;
+  }
+  const size_t need = sizeof(double) * EV_D * static_cast<size_t>(nrooms) * st->h_plan.nblocks * EV_NRAW;
+  if (need > st->partials_bytes) {
+    if (st->d_partials) { HS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); HS_CUDA_TRY(ctx, cudaFree(st->d_partials)); st->d_partials = nullptr; st->partials_bytes = 0; }
+    HS_CUDA_TRY(ctx, cudaMalloc(&st->d_partials, need));
+    st->partials_bytes = need;
+  }
+  *out = st;
+  return HS_OK;
+}
+
+static void fill_cmd(EvalCmd& c, int r, const float pl[24]) {
+  for (int j = 0; j < 3; ++j) {
+    for (int k = 0; k < 3; ++k) c.c[r][3 * j + k] = pl[8 * j + k];
+    c.c[r][9 + j] = pl[8 * j + 3];
+    c.c[r][12 + j] = pl[8 * j + 7];
+  }
+  c.c[r][15] = 0.f;
+}
+
+int32_t launch_peer_allreduce(hs_ctx* ctx, double* d_buf, int count) {
+  const uint32_t epoch = ++ctx->px.epoch;
+  k_peer_allreduce<<<1, 32, 0, ctx->stream>>>(d_buf, count, epoch, ctx->d_status, ctx->px);
+  ctx->launches++;
+  HS_CUDA_TRY(ctx, cudaGetLastError());
+  return HS_OK;
+}
+
+// caller guarantees the planes are paired (cuboid rooms)
+int32_t launch_eval(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& rt, double* d_rec_out, bool exchange) {
+  hs_eval_state* st = nullptr;
+  if (int32_t rc = eval_prepare(ctx, n, rt.off, rt.nrooms, &st)) return rc;
+  exchange = exchange && ctx->px.world > 1;
+  if (st->h_plan.nrooms_nonempty == 0) {  // nothing to stream: zero records (and still this rank's part in the exchange)
+    HS_CUDA_TRY(ctx, cudaMemsetAsync(d_rec_out, 0, sizeof(double) * rt.nrooms * HS_REC, ctx->stream));
+    return exchange ? launch_peer_allreduce(ctx, d_rec_out, rt.nrooms * HS_REC) : HS_OK;
+  }
+  EvalCmd cmd;
+  std::memset(&cmd, 0, sizeof cmd);
+  for (int r = 0; r < rt.nrooms; ++r) fill_cmd(cmd, r, &rt.pl[r][0][0]);
+  EvalArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.xyz = xyz; a.plan = st->d_plan; a.ctl = st->d_ctl; a.partials = st->d_partials; a.local_rec = st->d_local_rec; a.out = d_rec_out;
+  a.h_status = ctx->d_status;
+  if (exchange) { a.px = ctx->px; a.epoch0 = ++ctx->px.epoch; }
+  auto kern = k_eval<EVK_NCONS, EVK_STAGES, EVK_GPT, EVK_FLUSH, false>;
+  if (!st->attr_set[0]) {
+    HS_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eval_smem_bytes())));
+    st->attr_set[0] = true;
+  }
+  kern<<<st->h_plan.nblocks, EVK_NCONS + 96, eval_smem_bytes(), ctx->stream>>>(a, cmd);
+  ctx->launches++;
+  HS_CUDA_TRY(ctx, cudaGetLastError());
+  return HS_OK;
+}
+
+// ===========================================================================================================================
+// evaluation sessions
+// ===========================================================================================================================
+#define HS_SLOCK(ctx)                                    \
+  if (!(ctx)) return HS_EINVAL;                          \
+  std::lock_guard<std::mutex> lock__((ctx)->mu);         \
+  if (cudaSetDevice((ctx)->device) != cudaSuccess) { (ctx)->err = "cudaSetDevice failed"; return HS_ECUDA; }
+
+static void session_free(hs_eval_session* s) {
+  if (s->h_cmds) cudaFreeHost(s->h_cmds);
+  if (s->h_ctl) cudaFreeHost(s->h_ctl);
+  if (s->h_results) cudaFreeHost(s->h_results);
+  if (s->d_cmds) cudaFree(s->d_cmds);
+  if (s->d_results) cudaFree(s->d_results);
+  delete s;
+}
+
+static inline uint32_t host_load(const uint32_t* p) { return reinterpret_cast<const std::atomic<uint32_t>*>(p)->load(std::memory_order_acquire); }
+static inline void host_store(uint32_t* p, uint32_t v) { reinterpret_cast<std::atomic<uint32_t>*>(p)->store(v, std::memory_order_release); }
+
+static int32_t session_check(hs_eval_session* s, const char* who) {
+  hs_ctx* ctx = s->ctx;
+  const uint32_t err = host_load(&s->h_ctl->error);
+  if (err == 1) { ctx->err = std::string(who) + ": a peer did not deliver its records (exchange timed out)"; return HS_ENCCL; }
+  if (err == 2) { ctx->err = std::string(who) + ": the session was idle for too long and shut itself down"; return HS_ECUDA; }
+  return HS_OK;
+}
+
+// spin until `cond` holds; notices a dead kernel and gives up after 60 s
+template <class Cond>
+static int32_t session_spin(hs_eval_session* s, const char* who, Cond cond) {
+  hs_ctx* ctx = s->ctx;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint64_t it = 0;; ++it) {
+    if (cond()) return HS_OK;
+    if (int32_t rc = session_check(s, who)) return rc;
+    if ((it & 0xfff) == 0xfff) {
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaErrorNotReady && !cond()) {
+        ctx->err = std::string(who) + ": the session kernel is not running" + (q == cudaSuccess ? "" : std::string(" (") + cudaGetErrorString(q) + ")");
+        return HS_ECUDA;
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) { ctx->err = std::string(who) + ": timed out"; return HS_ECUDA; }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
+extern "C" {
+
+int32_t hs_eval_session_begin(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, int32_t allreduce, hs_eval_session** out) {
+  HS_SLOCK(ctx);
+  if (!out || !cloud || !room_offsets || nrooms < 1 || nrooms > HS_MAX_ROOMS) { ctx->err = "hs_eval_session_begin: bad arguments (1 <= nrooms <= 32)"; return HS_EINVAL; }
+  *out = nullptr;
+  if (ctx->session) { ctx->err = "hs_eval_session_begin: this context already has an open session"; return HS_EINVAL; }
+  for (int r = 0; r < nrooms; ++r)
+    if (room_offsets[r] > room_offsets[r + 1]) { ctx->err = "hs_eval_session_begin: room offsets must be non-decreasing"; return HS_EINVAL; }
+  if (room_offsets[0] < 0 || room_offsets[nrooms] > cloud->n) { ctx->err = "hs_eval_session_begin: room offsets outside the cloud"; return HS_EINVAL; }
+  if (allreduce && ctx->px.world < 1) { ctx->err = "hs_eval_session_begin: no peer group (hs_peer_mailbox_create / _connect or hs_peer_group_create_local first)"; return HS_EINVAL; }
+  hs_eval_state* st = nullptr;
+  if (int32_t rc = eval_prepare(ctx, cloud->n, room_offsets, nrooms, &st)) return rc;
+  hs_eval_session* s = new (std::nothrow) hs_eval_session();
+  if (!s) { ctx->err = "out of host memory"; return HS_ENOMEM; }
+  s->ctx = ctx;
+  s->nrooms = nrooms;
+  s->exchange = allreduce && ctx->px.world > 1;
+  s->empty = st->h_plan.nrooms_nonempty == 0;
+  const size_t rec_bytes = sizeof(double) * nrooms * HS_REC;
+  auto fail = [&](cudaError_t e) { ctx->err = std::string("hs_eval_session_begin: ") + cudaGetErrorString(e); session_free(s); return HS_ECUDA; };
+  cudaError_t e;
+  if ((e = cudaHostAlloc(&s->h_cmds, sizeof(EvalCmd) * EV_QCAP, cudaHostAllocMapped)) != cudaSuccess) return fail(e);
+  if ((e = cudaHostAlloc(&s->h_ctl, 64, cudaHostAllocMapped)) != cudaSuccess) return fail(e);
+  if ((e = cudaHostAlloc(&s->h_results, rec_bytes * EV_QCAP, cudaHostAllocMapped)) != cudaSuccess) return fail(e);
+  std::memset(s->h_ctl, 0, 64);
+  std::memset(s->h_results, 0, rec_bytes * EV_QCAP);
+  if ((e = cudaMalloc(&s->d_cmds, sizeof(EvalCmd) * EV_QCAP)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&s->d_results, rec_bytes * EV_QCAP)) != cudaSuccess) return fail(e);
+  if (!s->empty) {
+    EvalArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.xyz = cloud->d; a.plan = st->d_plan; a.ctl = st->d_ctl; a.partials = st->d_partials; a.local_rec = st->d_local_rec; a.out = s->d_results;
+    a.d_cmds = s->d_cmds;
+    void* dp = nullptr;
+    if ((e = cudaHostGetDevicePointer(&dp, s->h_cmds, 0)) != cudaSuccess) return fail(e);
+    a.h_cmds = static_cast<const EvalCmd*>(dp);
+    if ((e = cudaHostGetDevicePointer(&dp, s->h_ctl, 0)) != cudaSuccess) return fail(e);
+    a.h_ctl = static_cast<EvalHostCtl*>(dp);
+    if ((e = cudaHostGetDevicePointer(&dp, s->h_results, 0)) != cudaSuccess) return fail(e);
+    a.h_results = static_cast<double*>(dp);
+    a.h_status = ctx->d_status;
+    a.idle_timeout_ns = 20ull * 1000000000ull;
+    if (s->exchange) { a.px = ctx->px; a.epoch0 = ctx->px.epoch + 1; }
+    auto kern = k_eval<EVK_NCONS, EVK_STAGES, EVK_GPT, EVK_FLUSH, true>;
+    if (!st->attr_set[1]) {
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eval_smem_bytes()))) != cudaSuccess) return fail(e);
+      st->attr_set[1] = true;
+    }
+    if ((e = cudaMemsetAsync(st->d_ctl, 0, sizeof(EvalCtl), ctx->stream)) != cudaSuccess) return fail(e);
+    EvalCmd none;
+    std::memset(&none, 0, sizeof none);
+    kern<<<st->h_plan.nblocks, EVK_NCONS + 128, eval_smem_bytes(), ctx->stream>>>(a, none);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
+  }
+  ctx->session = s;
+  *out = s;
+  return HS_OK;
+}
+
+int32_t hs_eval_session_post(hs_eval_session* s, const double* params, int32_t count) {
+  if (!s) return HS_EINVAL;
+  hs_ctx* ctx = s->ctx;
+  HS_SLOCK(ctx);
+  if (!params || count < 0) { ctx->err = "hs_eval_session_post: bad arguments"; return HS_EINVAL; }
+  if (s->stopped) { ctx->err = "hs_eval_session_post: the session has been stopped"; return HS_EINVAL; }
+  for (int32_t i = 0; i < count; ++i) {
+    if (!s->empty) {
+      // a ring entry is free again once its evaluation is done
+      if (int32_t rc = session_spin(s, "hs_eval_session_post", [&] { return s->posted - host_load(&s->h_ctl->done) < static_cast<uint32_t>(EV_QCAP); })) return rc;
+    }
+    EvalCmd& c = s->h_cmds[s->posted % EV_QCAP];
+    for (int r = 0; r < s->nrooms; ++r) {
+      float pl[24];
+      hs::planes_from_cuboid(params + (static_cast<size_t>(i) * s->nrooms + r) * 10, pl);
+      for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < 3; ++k)
+          if (!(pl[8 * j + k] == -pl[8 * j + 4 + k])) { ctx->err = "hs_eval_session_post: parameters do not give antiparallel wall pairs (NaN?)"; return HS_EINVAL; }
+      fill_cmd(c, r, pl);
+    }
+    ++s->posted;
+    if (s->empty) host_store(&s->h_ctl->done, s->posted);  // zero records, already in h_results
+    host_store(&s->h_ctl->posted, s->posted);
+  }
+  return HS_OK;
+}
+
+int64_t hs_eval_session_done(const hs_eval_session* s) { return s ? static_cast<int64_t>(host_load(&s->h_ctl->done)) : -1; }
+
+int32_t hs_eval_session_wait(hs_eval_session* s, int64_t seq, double* rec_out) {
+  if (!s) return HS_EINVAL;
+  hs_ctx* ctx = s->ctx;
+  HS_SLOCK(ctx);
+  if (seq < 0 || seq >= static_cast<int64_t>(s->posted)) { ctx->err = "hs_eval_session_wait: evaluation has not been posted"; return HS_EINVAL; }
+  if (static_cast<int64_t>(s->posted) - seq > EV_QCAP) { ctx->err = "hs_eval_session_wait: record no longer in the result ring (256 evaluations)"; return HS_EINVAL; }
+  if (int32_t rc = session_spin(s, "hs_eval_session_wait", [&] { return static_cast<int64_t>(host_load(&s->h_ctl->done)) > seq; })) return rc;
+  if (int32_t rc = session_check(s, "hs_eval_session_wait")) return rc;
+  if (rec_out) std::memcpy(rec_out, s->h_results + static_cast<size_t>(seq % EV_QCAP) * s->nrooms * HS_REC, sizeof(double) * s->nrooms * HS_REC);
+  return HS_OK;
+}
+
+int32_t hs_eval_session_eval(hs_eval_session* s, const double* params, double* rec_out) {
+  if (!s) return HS_EINVAL;
+  if (int32_t rc = hs_eval_session_post(s, params, 1)) return rc;
+  return hs_eval_session_wait(s, static_cast<int64_t>(s->posted) - 1, rec_out);
+}
+
+int32_t hs_eval_session_stop(hs_eval_session* s) {
+  if (!s) return HS_EINVAL;
+  hs_ctx* ctx = s->ctx;
+  HS_SLOCK(ctx);
+  s->stopped = true;
+  host_store(&s->h_ctl->stop, 1u);
+  return HS_OK;
+}
+
+void* hs_eval_session_device_results(const hs_eval_session* s) { return s ? s->d_results : nullptr; }
+
+int32_t hs_eval_session_end(hs_eval_session* s) {
+  if (!s) return HS_OK;
+  hs_ctx* ctx = s->ctx;
+  HS_SLOCK(ctx);
+  s->stopped = true;
+  host_store(&s->h_ctl->stop, 1u);
+  int32_t rc = HS_OK;
+  const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { ctx->err = std::string("hs_eval_session_end: ") + cudaGetErrorString(e); rc = HS_ECUDA; }
+  if (rc == HS_OK) rc = session_check(s, "hs_eval_session_end");
+  if (rc == HS_OK && !s->empty && host_load(&s->h_ctl->done) != s->posted) { ctx->err = "hs_eval_session_end: the kernel ended before all posted evaluations were done"; rc = HS_ECUDA; }
+  if (s->exchange) ctx->px.epoch += s->posted;  // every rank posted the same evaluations
+  if (ctx->h_status) *ctx->h_status = 0;  // reported through this call
+  ctx->session = nullptr;
+  session_free(s);
+  return rc;
+}
+
+}  // extern "C"

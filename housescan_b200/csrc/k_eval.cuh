@@ -1,0 +1,539 @@
+// Cuboid objective / gradient sums per room (A6 + A5; FitCuboidBFGS.hs:51-76 generalised from 8 corners to the room cloud,
+// planes of Main.hs:1852-1874, distance of Main.hs:1371-1372) — the headline kernel, 12 B/point, and its resident
+// multi-evaluation ("session") form.
+//
+// One CTA per SM.  Warps 0..NW-1 are consumers; then come the producer, the reducer, the finaliser and (session form, block 0
+// only) the dispatcher warp.
+//   producer   one lane streams the block's point range global -> shared in 72 KB tiles with 1-D bulk async copies (the TMA
+//              engine) through a STAGES-deep mbarrier ring.  The cloud does not change between evaluations, so in the session
+//              form it simply keeps streaming: the first tiles of evaluation e+1 are in shared memory before e has finished.
+//   consumers  each thread takes GPT groups (4 points = 48 B = 3 x LDS.128, conflict-free) per tile, evaluates them with the
+//              predicated point block of k_eval_point.cuh into 21 Float chains, and every FLUSH_TILES tiles the warp transposes
+//              its chains with shuffles (lane l ends up with the warp total of chain l: 104 instructions instead of the 22
+//              butterflies of round 1) and lane l adds its total into ONE Double register.  At the end of a room segment the
+//              lanes park their Doubles in shared memory, sync, and go straight on to the next segment / evaluation: they never
+//              touch global memory and never wait for a reduction (at most EV_D evaluations in flight).
+//   reducer    adds the warps' Doubles in warp order into the block's partial record of (evaluation, room), publishes it and
+//              takes the room's ticket; the block that delivers the LAST partial of a room adds the room's partials in block
+//              order (deterministic) and converts the raw sums into the HS_REC record.  Never waits for anything remote.
+//   finaliser  the block that completed the last room of an evaluation finalises it: with a peer group the records are
+//              exchanged over NVLink peer memory (k_peer.cuh) and summed in rank order; evaluations commit in order.
+//   dispatcher polls the host-mapped command ring, copies new plane tables into device memory and publishes them; enforces
+//              the idle watchdog (a forgotten session cannot hang the GPU).
+//
+// The static partition (EvalPlan, computed on the host) gives blocks that hold a room boundary fewer groups, so that all
+// blocks finish an evaluation together although a second segment costs a second flush / block sum.
+#pragma once
+#include "k_common.cuh"
+#include "k_ring.cuh"
+#include "k_eval_point.cuh"
+#include "k_peer.cuh"
+
+namespace hsk {
+
+constexpr int EV_MAXB = 256;   // blocks of a plan (>= SM count)
+constexpr int EV_D = 4;        // evaluations in flight per GPU: partial-record ring, tickets (PEER_SLOTS >= 2 * EV_D)
+constexpr int EV_NRAW = 22;    // raw sums per (block, room): f, T[3], M[3], B[9], C1, C2, Cm[3], N
+constexpr int EV_QCAP = 256;   // command / result ring entries of a session
+constexpr int EV_PARK = 16;    // ring of parked block sums (segments the reducer may lag behind the consumers)
+constexpr int EV_FQ = 8;       // finaliser queue entries (>= EV_D)
+static_assert(PEER_SLOTS >= 2 * EV_D, "mailbox slots must cover two windows of in-flight evaluations");
+
+struct EvalPlan {  // device memory; fixed for a (cloud, room offsets, grid) triple
+  int32_t nblocks, nrooms, nrooms_nonempty, pad;
+  int64_t n;
+  int64_t off[HS_MAX_ROOMS + 1];
+  int64_t blk_g0[EV_MAXB + 1];  // block b owns the 4-point groups [blk_g0[b], blk_g0[b+1])
+  int32_t blk_rfirst[EV_MAXB], blk_rlast[EV_MAXB];      // rooms with points in the block's range (rlast < rfirst: none)
+  int32_t room_blo[HS_MAX_ROOMS], room_nb[HS_MAX_ROOMS];  // blocks with points of the room: room_blo .. room_blo + room_nb - 1
+};
+
+struct EvalCmd {  // one evaluation's plane constants: per room n[3][3] (normals of the + walls), dp[3], dm[3], pad
+  float c[HS_MAX_ROOMS][16];
+};
+
+struct EvalCtl {  // device memory, zero between launches / at session begin
+  uint32_t posted;    // session: commands available in d_cmds
+  uint32_t stop;      // session: no more commands will come
+  uint32_t done_seq;  // evaluations finalised (in order)
+  uint32_t error;     // 1: peer timeout, 2: idle watchdog
+  uint32_t room_ticket[EV_D][HS_MAX_ROOMS];
+  uint32_t rooms_done[EV_D];
+};
+
+struct EvalHostCtl {  // mapped pinned host memory (session)
+  uint32_t posted;  // host -> device: commands written to h_cmds
+  uint32_t stop;    // host -> device
+  uint32_t done;    // device -> host: evaluations whose records are in h_results
+  uint32_t error;   // device -> host
+};
+
+struct EvalArgs {
+  const float* xyz;
+  const EvalPlan* plan;
+  EvalCtl* ctl;
+  double* partials;   // [EV_D][nrooms][nblocks][EV_NRAW]
+  double* local_rec;  // [EV_D][HS_MAX_ROOMS * HS_REC]: this GPU's records before the exchange
+  double* out;        // one-shot: nrooms x HS_REC; session: ring [EV_QCAP][nrooms * HS_REC]
+  EvalCmd* d_cmds;              // session: device command ring [EV_QCAP]
+  const EvalCmd* h_cmds;        // session: host-mapped command ring [EV_QCAP]
+  EvalHostCtl* h_ctl;           // session
+  double* h_results;            // session: host-mapped result ring [EV_QCAP][nrooms * HS_REC]
+  uint32_t* h_status;           // mapped word of the ctx: set to HS_ENCCL when a peer timed out
+  unsigned long long idle_timeout_ns;
+  uint32_t epoch0;              // peer epoch of evaluation 0 (epochs are > 0)
+  uint32_t pad;
+  PeerExchange px;              // world <= 1: no exchange
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_sys_u32(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ float4 ld_sys_v4(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+template <int NCONS>
+__device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
+
+// Transposing warp reduction of the 22 chain values: on return lane l (< 22) holds the warp total of value l.
+// Step S exchanges halves between lanes l and l ^ S: lanes with bit S keep the upper S slots.  Slots 22..31 are zero, so the
+// first step needs selects only for the 6 slot pairs (i, i + 16) that are both live.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 6; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);  // upper lanes end up with unused copies
+  }
+#pragma unroll
+  for (int S = 8; S >= 1; S >>= 1) {
+    const bool up = lane & S;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const float keep = up ? v[i + S] : v[i], send = up ? v[i] : v[i + S];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+    }
+  }
+  return v[0];
+}
+
+// chains of the whole warp -> one Double per lane (lane l accumulates raw sum l).  npts = points this lane added since the last flush.
+__device__ __forceinline__ void flush_chains(ChainsP& c, int& npts, double& dacc, int lane) {
+  float v[32];
+  v[0] = c.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    v[1 + j] = c.T[j]; v[4 + j] = c.M[j]; v[18 + j] = c.Cm[j];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) v[7 + 3 * j + q] = c.B[j][q];
+  }
+  v[16] = c.C1; v[17] = c.C2; v[21] = static_cast<float>(npts);
+#pragma unroll
+  for (int i = 22; i < 32; ++i) v[i] = 0.f;
+  dacc += static_cast<double>(warp_transpose_sum(v, lane));
+  c.clear();
+  npts = 0;
+}
+
+__device__ __forceinline__ void load_room_consts(RoomK& R, const float* c16) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    R.n[j][0] = c16[3 * j]; R.n[j][1] = c16[3 * j + 1]; R.n[j][2] = c16[3 * j + 2];
+    R.dp[j] = c16[9 + j]; R.dm[j] = c16[12 + j];
+  }
+}
+
+// raw room sums -> record component L (= lane); raw value k lives on lane k of the calling warp, lanes >= EV_NRAW hold 0.
+//   rec[0] = f; rec[1+2j] = T_j - M_j (sum r over the + wall), rec[2+2j] = -M_j (sum r over the - wall, r = -s);
+//   rec[7..15] = B; rec[16+2j] = count of the + wall = axis count - Cm_j, rec[17+2j] = Cm_j; axis counts N - C1 - C2, C1, C2
+__device__ __forceinline__ double raw_to_record(double raw, int L) {
+  int ia = 31, ib = 31, ic = 31, id = 31;  // rec = raw[ia] - raw[ib] - raw[ic] - raw[id]; 31 = a lane that holds zero
+  bool neg = false;
+  if (L == 0) ia = 0;
+  else if (L <= 6) { const int j = (L - 1) >> 1; if (L & 1) { ia = 1 + j; ib = 4 + j; } else { ia = 4 + j; neg = true; } }
+  else if (L <= 15) ia = L;
+  else if (L <= 21) {
+    const int j = (L - 16) >> 1;
+    if (L & 1) ia = 18 + j;
+    else { id = 18 + j; if (j == 0) { ia = 21; ib = 16; ic = 17; } else ia = 15 + j; }
+  }
+  const double va = __shfl_sync(0xffffffffu, raw, ia), vb = __shfl_sync(0xffffffffu, raw, ib);
+  const double vc = __shfl_sync(0xffffffffu, raw, ic), vd = __shfl_sync(0xffffffffu, raw, id);
+  const double r = ((va - vb) - vc) - vd;
+  return neg ? -r : r;
+}
+
+template <int NCONS, int STAGES, int GPT, int FLUSH_TILES, bool SESSION>
+__global__ void __launch_bounds__(NCONS + (SESSION ? 128 : 96), 1)
+k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0) {
+  constexpr int NW = NCONS / 32;
+  constexpr int W_PRODUCER = NW, W_REDUCER = NW + 1, W_FINAL = NW + 2, W_DISPATCH = NW + 3;
+  constexpr int TILE_GROUPS = GPT * NCONS;
+  constexpr uint32_t TILE_BYTES = TILE_GROUPS * 48;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* tiles = reinterpret_cast<float4*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(STAGES) * TILE_BYTES);
+  uint64_t* empty = full + STAGES;
+  double* wsum = reinterpret_cast<double*>(empty + STAGES);  // [2][NW][EV_NRAW]: the warps' Doubles of the segment just finished
+  double* parked = wsum + 2 * NW * EV_NRAW;                  // [EV_PARK][EV_NRAW]: block sums waiting for the reducer
+  __shared__ int64_t s_lo[HS_MAX_ROOMS], s_hi[HS_MAX_ROOMS];  // point range of each room segment of this block
+  __shared__ uint32_t s_rq[EV_PARK], s_fq[EV_FQ];            // consumers -> reducer (e << 8 | room), reducer -> finaliser (e)
+  __shared__ volatile uint32_t s_rq_tail, s_rq_head, s_fq_tail, s_exit, s_exit2, s_consumed_lo, s_consumed_hi, s_go;
+
+  const EvalPlan* __restrict__ plan = a.plan;
+  const int b = static_cast<int>(blockIdx.x);
+  const int nrooms = plan->nrooms, nblocks = plan->nblocks;
+  const int rfirst = plan->blk_rfirst[b], rlast = plan->blk_rlast[b];
+  const int nseg = rlast - rfirst + 1;
+  const int warp = static_cast<int>(threadIdx.x >> 5), lane = static_cast<int>(threadIdx.x & 31);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCONS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_rq_tail = 0; s_rq_head = 0; s_fq_tail = 0; s_exit = 0; s_exit2 = 0; s_consumed_lo = 0; s_consumed_hi = 0; s_go = 0;
+  }
+  if (static_cast<int>(threadIdx.x) < nseg) {
+    const int64_t p0 = plan->blk_g0[b] * 4, p1 = min(plan->blk_g0[b + 1] * 4, plan->n);
+    const int r = rfirst + static_cast<int>(threadIdx.x);
+    s_lo[threadIdx.x] = max(plan->off[r], p0);
+    s_hi[threadIdx.x] = min(plan->off[r + 1], p1);
+  }
+  __syncthreads();
+  if (nseg <= 0 && !(SESSION && b == 0 && warp == W_DISPATCH)) return;  // nothing to stream (tiny clouds): no ticket counts on this block
+
+  // =================================================================================================== dispatcher (session)
+  if (SESSION && warp == W_DISPATCH) {
+    if (b != 0) return;
+    uint32_t seq = 0;
+    unsigned long long t_last = peer_now_ns();
+    for (;;) {
+      const uint32_t hp = ld_sys_u32(&a.h_ctl->posted);
+      if (hp != seq) {
+        while (seq != hp) {  // copy the new commands host -> device ring (16 floats = one 64-byte line per room)
+          const float4* src = reinterpret_cast<const float4*>(a.h_cmds[seq % EV_QCAP].c);
+          float4* dst = reinterpret_cast<float4*>(a.d_cmds[seq % EV_QCAP].c);
+          for (int i = lane; i < nrooms * 4; i += 32) dst[i] = ld_sys_v4(src + i);
+          ++seq;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(&a.ctl->posted, seq);
+        t_last = peer_now_ns();
+        continue;
+      }
+      if (ld_sys_u32(&a.h_ctl->stop)) {
+        if (ld_sys_u32(&a.h_ctl->posted) != seq) continue;  // commands posted just before the stop
+        if (lane == 0) st_release_u32(&a.ctl->stop, 1u);
+        return;
+      }
+      if (ld_acquire_u32(&a.ctl->error)) { if (lane == 0) st_release_u32(&a.ctl->stop, 1u); return; }
+      if (ld_acquire_u32(&a.ctl->done_seq) != seq) t_last = peer_now_ns();  // evaluations still running: not idle
+      else if (peer_now_ns() - t_last > a.idle_timeout_ns) {  // watchdog: nobody posts, nobody stops
+        if (lane == 0) { a.ctl->error = 2u; st_sys_u32(&a.h_ctl->error, 2u); __threadfence_system(); st_release_u32(&a.ctl->stop, 1u); }
+        return;
+      }
+      __nanosleep(200);
+    }
+  }
+
+  // =================================================================================================== producer
+  if (warp == W_PRODUCER) {
+    if (lane != 0) return;
+    uint64_t tt = 0;  // tiles issued so far (continuous across rooms and evaluations)
+    bool stop = false;
+    for (uint32_t e = 0; (SESSION || e == 0) && !stop; ++e) {
+      for (int si = 0; si < nseg && !stop; ++si) {
+        const int64_t gl = (s_lo[si] + 3) >> 2, gh = s_hi[si] >> 2;
+        for (int64_t tg = gl; tg < gh; tg += TILE_GROUPS, ++tt) {
+          const int s = static_cast<int>(tt % STAGES);
+          if (tt >= STAGES) {
+            const uint32_t par = static_cast<uint32_t>(((tt / STAGES) - 1) & 1);
+            uint32_t ok;
+            for (;;) {  // poll, then sleep: a bare spin takes issue slots from the consumer warps on this scheduler
+              asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                           : "=r"(ok) : "r"(smem_u32(empty + s)), "r"(par) : "memory");
+              if (ok) break;
+              if (SESSION && s_exit) { stop = true; break; }
+              __nanosleep(100);
+            }
+            if (stop) break;
+          }
+          const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(TILE_GROUPS), gh - tg) * 48);
+          mbar_expect_tx(full + s, bytes);
+          bulk_g2s(tiles + static_cast<size_t>(s) * TILE_GROUPS * 3, reinterpret_cast<const float4*>(a.xyz) + 3 * tg, bytes, full + s);
+        }
+      }
+      if (SESSION && tt == 0) break;  // a block whose segments hold no whole group never streams
+    }
+    if (SESSION) {  // tiles in flight that nobody will consume: the copies must have landed before the block's shared memory goes away
+      while (!s_exit) __nanosleep(100);
+      const uint64_t consumed = (static_cast<uint64_t>(s_consumed_hi) << 32) | s_consumed_lo;
+      for (uint64_t t = consumed; t < tt; ++t) mbar_wait(full + (t % STAGES), static_cast<uint32_t>((t / STAGES) & 1));
+    }
+    return;
+  }
+
+  // =================================================================================================== reducer
+  if (warp == W_REDUCER) {
+    uint32_t head = 0, ftail = 0;
+    for (;;) {
+      bool leave = false;
+      while (s_rq_tail == head) {
+        if (s_exit && s_rq_tail == head) { leave = true; break; }
+        __nanosleep(32);
+      }
+      if (leave) break;
+      __threadfence_block();
+      const uint32_t item = s_rq[head % EV_PARK];
+      const uint32_t e = item >> 8;
+      const int r = static_cast<int>(item & 255u);
+      const uint32_t slot = e % EV_D;
+      // ---- publish the block's partial record of (evaluation, room)
+      const int blo = plan->room_blo[r], nb = plan->room_nb[r];
+      double* part = a.partials + ((static_cast<size_t>(slot) * nrooms + r) * nblocks) * EV_NRAW;
+      if (lane < EV_NRAW) {
+        part[static_cast<size_t>(b - blo) * EV_NRAW + lane] = parked[(head % EV_PARK) * EV_NRAW + lane];
+        __threadfence();
+      }
+      __syncwarp();
+      ++head;
+      if (lane == 0) s_rq_head = head;  // the parked sums of this segment may be overwritten
+      uint32_t last = 0;
+      if (lane == 0) {
+        const uint32_t t = atomicAdd(&a.ctl->room_ticket[slot][r], 1u);
+        last = (t == static_cast<uint32_t>(nb) - 1u);
+        if (last) { a.ctl->room_ticket[slot][r] = 0u; __threadfence(); }
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (!last) continue;
+      // ---- last partial of the room: add the room's partials in block order (all loads of a batch in flight together)
+      double raw = 0.0;
+      if (lane < EV_NRAW) {
+        constexpr int U = 8;
+        for (int k0 = 0; k0 < nb; k0 += U) {
+          double v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) v[u] = (k0 + u < nb) ? __ldcg(part + static_cast<size_t>(k0 + u) * EV_NRAW + lane) : 0.0;
+#pragma unroll
+          for (int u = 0; u < U; ++u) raw += v[u];
+        }
+      }
+      const double rec = raw_to_record(raw, lane);
+      const bool direct = !SESSION && a.px.world <= 1;  // one-shot on one GPU: the record goes straight to its destination
+      double* lrec = direct ? a.out : a.local_rec + static_cast<size_t>(slot) * (HS_MAX_ROOMS * HS_REC);
+      if (lane < HS_REC) { lrec[r * HS_REC + lane] = rec; __threadfence(); }
+      __syncwarp();
+      last = 0;
+      if (lane == 0) {
+        const uint32_t t = atomicAdd(&a.ctl->rooms_done[slot], 1u);
+        last = (t == static_cast<uint32_t>(plan->nrooms_nonempty) - 1u);
+        if (last) { a.ctl->rooms_done[slot] = 0u; __threadfence(); }
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (!last) continue;
+      // ---- last room of the evaluation
+      for (int rr = 0; rr < nrooms; ++rr)  // rooms without points: zero records
+        if (plan->off[rr + 1] == plan->off[rr] && lane < HS_REC) lrec[rr * HS_REC + lane] = 0.0;
+      if (direct) continue;  // the end of the kernel publishes a.out
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        s_fq[ftail % EV_FQ] = e;
+        __threadfence_block();
+        s_fq_tail = ++ftail;
+      }
+    }
+    if (lane == 0) { __threadfence_block(); s_exit2 = 1u; }
+    return;
+  }
+
+  // =================================================================================================== finaliser
+  if (warp == W_FINAL) {
+    uint32_t head = 0;
+    const int count = nrooms * HS_REC;
+    for (;;) {
+      bool leave = false;
+      while (s_fq_tail == head) {
+        if (s_exit2 && s_fq_tail == head) { leave = true; break; }
+        __nanosleep(64);
+      }
+      if (leave) break;
+      __threadfence_block();
+      const uint32_t e = s_fq[head % EV_FQ];
+      ++head;
+      __threadfence();
+      const double* lrec = a.local_rec + static_cast<size_t>(e % EV_D) * (HS_MAX_ROOMS * HS_REC);
+      double* dst = SESSION ? a.out + static_cast<size_t>(e % EV_QCAP) * count : a.out;
+      bool ok = true;
+      if (a.px.world > 1) peer_push_warp(a.px, a.epoch0 + e, lrec, count);
+      if (SESSION) {  // in-order commit: results and done counters advance evaluation by evaluation
+        const unsigned long long t0 = peer_now_ns();
+        while (ld_acquire_u32(&a.ctl->done_seq) != e) {
+          if (peer_now_ns() - t0 > 2 * PEER_TIMEOUT_NS) { ok = false; break; }
+          __nanosleep(64);
+        }
+      }
+      if (a.px.world > 1) ok = peer_collect_warp(a.px, a.epoch0 + e, dst, count) && ok;
+      else for (int i = lane; i < count; i += 32) dst[i] = __ldcg(lrec + i);
+      if (!ok && lane == 0) {
+        a.ctl->error = 1u;
+        if (a.h_status) st_sys_u32(a.h_status, static_cast<uint32_t>(HS_ENCCL));
+        if (SESSION) st_sys_u32(&a.h_ctl->error, 1u);
+      }
+      if (SESSION) {
+        double* hdst = a.h_results + static_cast<size_t>(e % EV_QCAP) * count;
+        for (int i = lane; i < count; i += 32) hdst[i] = dst[i];
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_system();
+          st_sys_u32(&a.h_ctl->done, e + 1u);
+          st_release_u32(&a.ctl->done_seq, e + 1u);
+        }
+      }
+    }
+    return;
+  }
+
+  // =================================================================================================== consumers
+  uint64_t tt = 0;  // tiles consumed so far
+  uint32_t stage = 0, parity = 0;
+  uint32_t qtail = 0;  // segments handed to the reducer so far
+  uint32_t wpar = 0;
+  const uint32_t tiles_s = smem_u32(tiles) + threadIdx.x * 48, empty_s = smem_u32(empty);
+  for (uint32_t e = 0; SESSION || e == 0; ++e) {
+    if (SESSION) {
+      // wait for command e (or the end of the session); never run more than EV_D evaluations ahead of the finalised ones.
+      // One thread decides for the block: a split decision would leave warps behind at the named barrier.
+      if (threadIdx.x == 0) {
+        uint32_t go = 0;
+        for (;;) {
+          const uint32_t posted = ld_acquire_u32(&a.ctl->posted), done = ld_acquire_u32(&a.ctl->done_seq);
+          if (static_cast<int32_t>(posted - e) > 0) {
+            if (e - done < static_cast<uint32_t>(EV_D)) { go = 1; break; }
+          } else if (ld_acquire_u32(&a.ctl->stop) && static_cast<int32_t>(ld_acquire_u32(&a.ctl->posted) - e) <= 0) break;
+          if (ld_acquire_u32(&a.ctl->error)) break;
+          __nanosleep(40);
+        }
+        s_go = go;
+      }
+      consumers_sync<NCONS>();
+      if (!s_go) break;
+    }
+    for (int si = 0; si < nseg; ++si) {
+      const int r = rfirst + si;
+      const int64_t lo = s_lo[si], hi = s_hi[si];
+      RoomK R;
+      if (SESSION) {
+        const float* c16 = a.d_cmds[e % EV_QCAP].c[r];
+        float t[15];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) t[i] = __ldcg(c16 + i);
+        load_room_consts(R, t);
+      } else {
+        load_room_consts(R, cmd0.c[r]);
+      }
+      ChainsP ch;
+      ch.clear();
+      int npts = 0;
+      double dacc = 0.0;
+      const int64_t gl = (lo + 3) >> 2, gh = hi >> 2;
+      if (gl <= gh) {
+        // ragged head / tail points (at most 3 each): the same per-point block, one point per thread
+        const int64_t head_end = gl * 4, tail_begin = gh * 4;
+        const int64_t nh = head_end - lo, ntail = hi - tail_begin;
+        if (static_cast<int64_t>(threadIdx.x) < nh) { const int64_t i = lo + threadIdx.x; add_point_pred2(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        else if (threadIdx.x >= 32 && static_cast<int64_t>(threadIdx.x) - 32 < ntail) { const int64_t i = tail_begin + threadIdx.x - 32; add_point_pred2(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        const int64_t ngroups = gh - gl;
+        const int nfull = static_cast<int>(ngroups / TILE_GROUPS);
+        const int rem_groups = static_cast<int>(ngroups - static_cast<int64_t>(nfull) * TILE_GROUPS);
+        int since_flush = 0;
+        for (int t = 0; t < nfull; ++t) {
+          mbar_wait(full + stage, parity);
+          const uint32_t base = tiles_s + stage * TILE_BYTES;
+          float4 q[GPT][3];
+#pragma unroll
+          for (int g = 0; g < GPT; ++g) { q[g][0] = lds_v4(base + g * NCONS * 48); q[g][1] = lds_v4(base + g * NCONS * 48 + 16); q[g][2] = lds_v4(base + g * NCONS * 48 + 32); }
+          mbar_arrive_s(empty_s + 8 * stage);  // the values are in registers: hand the slot back before the math
+#pragma unroll
+          for (int g = 0; g < GPT; ++g) {
+            add_point_pred2(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
+            add_point_pred2(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
+            add_point_pred2(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
+            add_point_pred2(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
+          }
+          npts += 4 * GPT;
+          if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+          if (++since_flush == FLUSH_TILES) { flush_chains(ch, npts, dacc, lane); since_flush = 0; }
+        }
+        tt += nfull;
+        if (rem_groups) {  // partial last tile of the segment: the threads whose group is in range
+          mbar_wait(full + stage, parity);
+          const uint32_t base = tiles_s + stage * TILE_BYTES;
+          float4 q[GPT][3];
+#pragma unroll
+          for (int g = 0; g < GPT; ++g) {  // out-of-range slots: stale but valid shared memory, skipped below
+            q[g][0] = lds_v4(base + g * NCONS * 48); q[g][1] = lds_v4(base + g * NCONS * 48 + 16); q[g][2] = lds_v4(base + g * NCONS * 48 + 32);
+          }
+          mbar_arrive_s(empty_s + 8 * stage);
+#pragma unroll
+          for (int g = 0; g < GPT; ++g)
+            if (g * NCONS + static_cast<int>(threadIdx.x) < rem_groups) {
+              add_point_pred2(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
+              add_point_pred2(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
+              add_point_pred2(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
+              add_point_pred2(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
+              npts += 4;
+            }
+          if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+          ++tt;
+        }
+      } else {
+        const int64_t i = lo + threadIdx.x;
+        if (i < hi) { add_point_pred2(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+      }
+      flush_chains(ch, npts, dacc, lane);
+      // ---- the block's sums of this segment: warp Doubles added in warp order by warp 0 and parked for the reducer; everybody
+      // else moves on at once (wsum is double-buffered: warp 0 joins the next segment's barrier only after it has read this one)
+      if (lane < EV_NRAW) wsum[(wpar * NW + warp) * EV_NRAW + lane] = dacc;
+      consumers_sync<NCONS>();
+      if (warp == 0) {
+        if (lane == 0)
+          while (qtail - s_rq_head >= static_cast<uint32_t>(EV_PARK)) __nanosleep(32);  // reducer EV_PARK segments behind: only with > 4 tiny rooms per block
+        __syncwarp();
+        if (lane < EV_NRAW) {
+          double sum = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) sum += wsum[(wpar * NW + w) * EV_NRAW + lane];
+          parked[(qtail % EV_PARK) * EV_NRAW + lane] = sum;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          s_rq[qtail % EV_PARK] = (e << 8) | static_cast<uint32_t>(r);
+          __threadfence_block();
+          s_rq_tail = qtail + 1;
+        }
+      }
+      ++qtail;
+      wpar ^= 1u;
+    }
+  }
+  // ---- leaving: tell the producer how far the ring was consumed and let producer / reducer / finaliser drain
+  consumers_sync<NCONS>();
+  if (threadIdx.x == 0) {
+    s_consumed_lo = static_cast<uint32_t>(tt);
+    s_consumed_hi = static_cast<uint32_t>(tt >> 32);
+    __threadfence_block();
+    s_exit = 1u;
+  }
+}
+
+}  // namespace hsk

@@ -1,55 +1,73 @@
-// All-reduce of the per-room records over NVLink peer memory, done by the block that finishes a GPU's reduction.
+// All-reduce of the per-room records over NVLink peer memory, done by ONE WARP of the GPU that finishes a reduction.
 //
 // The path's only exchange is nrooms x 24 doubles (2.3 KB for the 12-room apartment).  Through NCCL that costs a second
-// launch and ~12 us per evaluation (measured at 2 GPUs), which is as long as the 8-GPU shard's whole kernel; here the last
-// block of the reduction kernel writes its record straight into a mailbox slot on every peer (posted NVLink stores), raises a
-// flag there, waits for the other ranks' flags in its own mailbox and adds the slots in rank order — deterministic, and the
-// same result on every rank.  Mailboxes are plain cudaMalloc memory shared between the per-GPU processes with CUDA IPC
-// handles (hs_peer_mailbox_create / hs_peer_mailbox_connect).
+// launch and ~12 us per evaluation (measured at 2 GPUs), which is as long as the 8-GPU shard's whole kernel; here a warp writes
+// the rank's record straight into a mailbox slot on every peer (posted NVLink stores), raises a flag there, waits for the
+// other ranks' flags in its own mailbox and adds the slots in rank order — deterministic, and the same result on every rank.
+// Mailboxes are plain cudaMalloc memory: shared between per-GPU processes with CUDA IPC handles (hs_peer_mailbox_create /
+// hs_peer_mailbox_connect), or addressed directly when all ranks live in one process (hs_peer_group_create_local).
+//
+// Evaluations are numbered by an epoch that every rank counts identically; epoch e uses slot e % PEER_SLOTS.  Slots are
+// re-used only after every rank has consumed them: an evaluation session keeps at most EV_D (= PEER_SLOTS / 2) evaluations in
+// flight per rank, and a rank finalises evaluations in order (k_eval.cuh), so nobody can be PEER_SLOTS epochs ahead of a reader.
 #pragma once
 #include "hs_internal.cuh"
 
 namespace hsk {
 
+constexpr int PEER_SLOTS = 8;
 constexpr size_t PEER_SLOT_DOUBLES = static_cast<size_t>(HS_MAX_ROOMS) * HS_REC;
-constexpr size_t PEER_DATA_DOUBLES = 2 * HS_PEER_MAX * PEER_SLOT_DOUBLES;  // [epoch parity][source rank][record]
-constexpr size_t PEER_FLAG_STRIDE = 32;                                     // uint32 units: one 128-byte line per flag
-constexpr size_t PEER_MAILBOX_BYTES = PEER_DATA_DOUBLES * sizeof(double) + HS_PEER_MAX * PEER_FLAG_STRIDE * sizeof(uint32_t);
+constexpr size_t PEER_DATA_DOUBLES = static_cast<size_t>(PEER_SLOTS) * HS_PEER_MAX * PEER_SLOT_DOUBLES;  // [slot][source rank][record]
+constexpr size_t PEER_FLAG_STRIDE = 32;                                                                  // uint32 units: one 128-byte line per flag
+constexpr size_t PEER_MAILBOX_BYTES = PEER_DATA_DOUBLES * sizeof(double) + static_cast<size_t>(PEER_SLOTS) * HS_PEER_MAX * PEER_FLAG_STRIDE * sizeof(uint32_t);
+constexpr unsigned long long PEER_TIMEOUT_NS = 2000000000ull;  // a dead peer must not hang the GPU
 
 __device__ __forceinline__ unsigned long long peer_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ double* peer_data(unsigned long long mailbox, uint32_t slot, int src) {
+  return reinterpret_cast<double*>(mailbox) + (static_cast<size_t>(slot) * HS_PEER_MAX + src) * PEER_SLOT_DOUBLES;
+}
+__device__ __forceinline__ volatile uint32_t* peer_flag(unsigned long long mailbox, uint32_t slot, int src) {
+  return reinterpret_cast<volatile uint32_t*>(reinterpret_cast<double*>(mailbox) + PEER_DATA_DOUBLES) + (static_cast<size_t>(slot) * HS_PEER_MAX + src) * PEER_FLAG_STRIDE;
+}
 
-// buf[0..count) of this rank -> sum over ranks, in place.  Called by ALL `nthreads` threads of one block; `sync` is a barrier
-// over exactly those threads.  Two data parities suffice: nobody can send epoch e+2 before everybody has sent e+1, and a rank
-// sends e+1 only after it has finished reading e.
-template <class Sync>
-__device__ __forceinline__ void peer_allreduce(const PeerExchange& px, double* buf, int count, int tid, int nthreads, Sync sync) {
-  const int par = static_cast<int>(px.epoch & 1u);
-  double* mine = reinterpret_cast<double*>(px.mailbox[px.rank]);
-  volatile uint32_t* my_flags = reinterpret_cast<volatile uint32_t*>(mine + PEER_DATA_DOUBLES);
-  for (int p = 0; p < px.world; ++p) {  // my record into slot [par][rank] of every mailbox (my own included)
-    double* dst = reinterpret_cast<double*>(px.mailbox[p]) + (static_cast<size_t>(par) * HS_PEER_MAX + px.rank) * PEER_SLOT_DOUBLES;
-    for (int i = tid; i < count; i += nthreads) dst[i] = buf[i];
+// Step 1 (never blocks): this rank's record src[0..count) -> slot [epoch][rank] of every mailbox, then the flags.  One full warp.
+__device__ __forceinline__ void peer_push_warp(const PeerExchange& px, uint32_t epoch, const double* src, int count) {
+  const int lane = static_cast<int>(threadIdx.x & 31);
+  const uint32_t slot = epoch % PEER_SLOTS;
+  for (int p = 0; p < px.world; ++p) {
+    double* dst = peer_data(px.mailbox[p], slot, px.rank);
+    for (int i = lane; i < count; i += 32) dst[i] = __ldcg(src + i);
   }
-  sync();  // the block's stores happen-before the flag threads' system-scope fence below (cumulative release)
-  if (tid < px.world) {  // thread p tells rank p that this rank's record has landed
+  __threadfence_system();
+  __syncwarp();
+  if (lane < px.world) {  // lane p tells rank p that this rank's record has landed
     __threadfence_system();
-    volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<double*>(px.mailbox[tid]) + PEER_DATA_DOUBLES) + px.rank * PEER_FLAG_STRIDE;
-    *f = px.epoch;
-    // and waits for rank p's record in this rank's mailbox (bounded: a dead peer must not hang the GPU)
+    *peer_flag(px.mailbox[lane], slot, px.rank) = epoch;
+  }
+}
+
+// Step 2: wait for every rank's record of this epoch in the local mailbox and add them in rank order into dst[0..count).
+// Returns false (and fills dst with NaN) when a peer did not show up within PEER_TIMEOUT_NS.  One full warp.
+__device__ __forceinline__ bool peer_collect_warp(const PeerExchange& px, uint32_t epoch, double* dst, int count) {
+  const int lane = static_cast<int>(threadIdx.x & 31);
+  const uint32_t slot = epoch % PEER_SLOTS;
+  bool ok = true;
+  if (lane < px.world) {
+    volatile uint32_t* f = peer_flag(px.mailbox[px.rank], slot, lane);
     const unsigned long long t0 = peer_now_ns();
-    while (static_cast<int32_t>(my_flags[tid * PEER_FLAG_STRIDE] - px.epoch) < 0) {
-      if (peer_now_ns() - t0 > 2000000000ull) { my_flags[HS_PEER_MAX * PEER_FLAG_STRIDE - 1] = px.epoch; break; }  // timeout marker
+    while (static_cast<int32_t>(*f - epoch) < 0) {
+      if (peer_now_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
+      __nanosleep(40);
     }
     __threadfence_system();
   }
-  sync();
-  const bool timed_out = my_flags[HS_PEER_MAX * PEER_FLAG_STRIDE - 1] == px.epoch;
-  const volatile double* slots = mine + static_cast<size_t>(par) * HS_PEER_MAX * PEER_SLOT_DOUBLES;
-  for (int i = tid; i < count; i += nthreads) {
+  ok = __all_sync(0xffffffffu, ok);
+  for (int i = lane; i < count; i += 32) {
     double s = 0.0;
-    for (int r = 0; r < px.world; ++r) s += slots[r * PEER_SLOT_DOUBLES + i];  // rank order: identical on every rank
-    buf[i] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : s;
+    for (int r = 0; r < px.world; ++r) s += *reinterpret_cast<const volatile double*>(peer_data(px.mailbox[px.rank], slot, r) + i);  // rank order: identical on every rank
+    dst[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
   }
+  return ok;
 }
 
 }  // namespace hsk

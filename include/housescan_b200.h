@@ -107,6 +107,37 @@ HS_API int32_t hs_peer_mailbox_create(hs_ctx* ctx, int32_t rank, int32_t world, 
 HS_API int32_t hs_peer_mailbox_connect(hs_ctx* ctx, const uint8_t* handles /* world x 64 bytes */);
 HS_API int32_t hs_rooms_cuboid_sums_allreduce_async(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets,
                                                     int32_t nrooms, const double* params, void* d_rec_out);
+/* Same-process peer group: ctxs[i] (one per device, all in THIS process) becomes rank i of an n-rank group whose mailboxes are
+ * addressed directly over NVLink (cudaDeviceEnablePeerAccess).  This is what a single Haskell executable
+ * (housescan.cabal:15-43) uses to drive several GPUs; the *_allreduce_async entry points and sessions may then be issued for
+ * all ranks from one host thread. */
+HS_API int32_t hs_peer_group_create_local(hs_ctx* const* ctxs, int32_t n);
+
+/* ---- evaluation sessions: the optimiser loop's view of the device --------------------------------------------------------
+ * FitCuboidBFGS evaluates its objective up to 2000 times per stage (FitCuboidBFGS.hs:184,201,233 `minimize NMSimplex2 1e-8
+ * maxIt`); over a room cloud every evaluation is one pass of the reduction kernel, so the fixed cost per launch IS the cost of
+ * a fit on several GPUs.  A session launches the kernel once: it stays resident on the SMs, keeps its tile ring primed (the
+ * cloud does not change between evaluations), takes parameter sets from a host-mapped command ring and delivers every
+ * evaluation's records (summed over the peer group when allreduce != 0) into a host-mapped result ring.  Up to 256
+ * evaluations may be posted ahead (line searches, simplex vertices, finite differences); they run back to back.
+ *   begin: rooms as in hs_rooms_cuboid_sums (nrooms <= 32); the cloud must stay alive and unchanged until end.
+ *   post:  params = count x nrooms x 10 doubles; blocks only while 256 evaluations are in flight.
+ *   wait:  blocks until evaluation `seq` (0-based, in posting order) is done; rec_out (may be NULL) = nrooms x HS_REC doubles.
+ *          A record stays readable until 256 further evaluations have been posted.
+ *   eval:  post one + wait for it.      stop: no more posts; the kernel drains and exits (non-blocking).
+ *   end:   stop + wait for the kernel + free.  HS_ENCCL if a peer did not show up within 2 s (its records are NaN).
+ * While a session is open every other call on the same ctx fails with HS_EINVAL (the stream is busy with the resident kernel);
+ * a session nobody talks to for 20 s shuts itself down.  With a peer group all ranks must post the same evaluations. */
+typedef struct hs_eval_session hs_eval_session;
+HS_API int32_t hs_eval_session_begin(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms,
+                                     int32_t allreduce, hs_eval_session** out);
+HS_API int32_t hs_eval_session_post(hs_eval_session* s, const double* params, int32_t count);
+HS_API int32_t hs_eval_session_wait(hs_eval_session* s, int64_t seq, double* rec_out);
+HS_API int32_t hs_eval_session_eval(hs_eval_session* s, const double* params, double* rec_out);
+HS_API int64_t hs_eval_session_done(const hs_eval_session* s); /* evaluations finished so far */
+HS_API void* hs_eval_session_device_results(const hs_eval_session* s); /* device ring [256][nrooms x HS_REC] doubles */
+HS_API int32_t hs_eval_session_stop(hs_eval_session* s);
+HS_API int32_t hs_eval_session_end(hs_eval_session* s);
 /* host chain rule: (params, summed record) -> f, grad, counts */
 HS_API int32_t hs_cuboid_grad_from_sums(const double params[10], const double rec[HS_REC], double* f, double grad[10],
                                         int64_t counts[6]);

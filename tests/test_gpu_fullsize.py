@@ -115,22 +115,40 @@ def test_c3_apartment_records_100m(ctx, dev):
     assert np.array_equal(total[:, 16:22], rec[:, 16:22])
     scale = np.abs(rec) + 1e-9 * np.abs(rec).max(axis=1, keepdims=True)
     assert np.max(np.abs(total - rec) / scale) < 1e-6
-    # the three kernel forms (default, packed f32x2, exact Double products) agree: counts bit-exact, sums within the bar
-    for key0, key3 in ((2, 7), (1, 0)):
-        ctx.set_mode(0, key0)
-        ctx.set_mode(3, key3)
-        other = ctx.rooms_cuboid_sums(cloud, offs, pe)
-        ctx.set_mode(0, 0)
-        ctx.set_mode(3, 0)
-        assert np.array_equal(other[:, 16:22], rec[:, 16:22])
-        assert abs(other[:, 0] - rec[:, 0]).max() <= 1e-6 * rec[:, 0].max()
-    # one room against the oracle (8.3 M points: a second on the CPU)
+    # both kernel forms (throughput default, exact Double products) agree: counts bit-exact, sums within the bar
+    ctx.set_mode(0, 1)
+    other = ctx.rooms_cuboid_sums(cloud, offs, pe)
+    ctx.set_mode(0, 0)
+    assert np.array_equal(other[:, 16:22], rec[:, 16:22])
+    assert abs(other[:, 0] - rec[:, 0]).max() <= 1e-6 * rec[:, 0].max()
+    # ALL 12 rooms x 22 sums against the oracle (100 M points: a fraction of a second per room on the CPU).  Counts bit-exact; every
+    # sum within the north-star bar of 1e-6 of its magnitude sum (sum of |terms|, which the exact kernel's record stands in for).
     import oracle as O
 
-    r0 = O.cuboid_sums(pts[:per].cpu().numpy(), pe[0])
-    assert np.array_equal(r0[16:22], rec[0, 16:22]) and abs(r0[0] - rec[0, 0]) <= 1e-6 * r0[0]
-    f, g, cnt = hb.cuboid_grad_from_sums(pe[0], rec[0])
-    assert np.isfinite(g).all() and cnt.sum() == per
+    host = pts.cpu().numpy()
+    for r in range(12):
+        xyz_r = host[offs[r] : offs[r + 1]]
+        ro = O.cuboid_sums(xyz_r, pe[r])
+        assert np.array_equal(ro[16:22], rec[r, 16:22]), r
+        a, res = O.plane_assign(xyz_r, O.planes_from_cuboid(pe[r]))
+        res = res.astype(np.float64)
+        sc = np.zeros(22)
+        sc[0] = np.sum(res * res)
+        for k in range(6):
+            sc[1 + k] = np.sum(np.abs(res[a == k]))
+        for j in range(3):
+            m = (a >> 1) == j
+            sc[7 + 3 * j : 10 + 3 * j] = np.sum(np.abs(res[m, None] * xyz_r[m].astype(np.float64)), axis=0)
+        sc[16:22] = 1.0
+        assert np.max(np.abs(rec[r, :22] - ro[:22]) / np.maximum(sc, 1e-300)) < 1e-6, r
+        f_g, g_g, c_g = hb.cuboid_grad_from_sums(pe[r], rec[r])
+        f_o, g_o, c_o = hb.cuboid_grad_from_sums(pe[r], ro)
+        assert abs(f_g - f_o) <= 1e-6 * f_o and np.array_equal(c_g, c_o) and c_g.sum() == per
+    # the resident session form gives the very same records, evaluation after evaluation (bit-identical: same partition, same order)
+    with ctx.eval_session(cloud, offs) as sess:
+        last = sess.post(np.stack([pe, pe * (1 + 1e-4), pe]))
+        r0, r1, r2 = sess.wait(last - 2), sess.wait(last - 1), sess.wait(last)
+    assert np.array_equal(r0, rec) and np.array_equal(r2, rec) and not np.array_equal(r1, rec)
 
 
 def test_c4_components_20m(ctx, dev):

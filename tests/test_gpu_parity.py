@@ -128,21 +128,18 @@ def test_plane_assign_generic_k(ctx):
         assert np.array_equal(a_g, a_o) and np.array_equal(r_g.view(np.uint32), r_o.view(np.uint32))
 
 
-# evaluation kernels: "exact" = every product in Double (k_planes.cu); "fast" = the product default, the warp-accumulator
-# throughput kernel (k_eval_pred.cu: scalar Float products, 128-point Float chains, warp shuffle sums, Double accumulation);
-# "packed" = the packed-f32x2 form it replaced (k_eval_fast.cu, mode key 3 = 7), kept as a cross-check.  Assignment (counts)
-# is bit-exact in all; sums: exact 1e-11 of the magnitude sum, fast / packed 1e-6 (the north-star bar; measured ~1e-7).
-EVAL_MODES = {"exact": (1, 0, 1e-11), "fast": (2, 0, 1e-6), "packed": (2, 7, 1e-6)}
+# evaluation kernels: "exact" = every product in Double (k_planes.cu); "fast" = the product default, the throughput kernel
+# (k_eval.cuh: scalar Float products, 256-point Float chains, transposing warp sums, Double accumulation).  Assignment (counts)
+# is bit-exact in both; sums: exact 1e-11 of the magnitude sum, fast 1e-6 (the north-star bar; measured ~1e-7).
+EVAL_MODES = {"exact": (1, 1e-11), "fast": (2, 1e-6)}
 
 
-@pytest.fixture(params=["exact", "fast", "packed"])
+@pytest.fixture(params=["exact", "fast"])
 def eval_mode(request, ctx):
-    mode, variant, tol = EVAL_MODES[request.param]
+    mode, tol = EVAL_MODES[request.param]
     ctx.set_mode(0, mode)
-    ctx.set_mode(3, variant)
     yield tol
     ctx.set_mode(0, 0)
-    ctx.set_mode(3, 0)
 
 
 def _record_scale(xyz, params):
