@@ -37,6 +37,13 @@ UNIT = "points/s"
 BYTES_PER_POINT = 12.0  # residual+gradient evaluation reads 12 B/pt, writes ~0
 
 
+def workload_config(n_total):
+    """the `config` object: identical in both arms (the driver compares them)"""
+    return {"workload": "12-room grid apartment (BASELINE configs[2]): per-room cuboid residual + gradient sums, nearest-plane assignment",
+            "rooms": N_ROOMS, "points_total": int(n_total),
+            "l2": "inputs larger than L2: every step streams all %.0f MB of points (L2 is 126 MB per GPU)" % (n_total * 12 / 1e6)}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -159,21 +166,30 @@ def run_reference(args, rank, world):
     import oracle as O
     from housescan_b200 import synth
 
-    if os.environ.get("TORCHELASTIC_RUN_ID") and os.environ.get("OMP_NUM_THREADS") == "1" and not os.environ.get("HS_REF_CHILD"):
-        # torchrun exports OMP_NUM_THREADS=1 to its workers (and libgomp sizes its pool and wait policy from it at load time): run
-        # this arm in a child with the launcher's settings removed, so that it uses all host threads exactly as at N = 1
-        import subprocess
-        env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS" and not k.startswith("TORCHELASTIC")}
-        env["HS_REF_CHILD"] = "1"
-        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK"):
+    if not os.environ.get("HS_REF_CHILD"):
+        # Always in a child process with the launcher's settings removed, so that the arm is the SAME process set-up at every N:
+        # torchrun exports OMP_NUM_THREADS=1 to its workers (libgomp sizes its pool and wait policy from it at load time) and its
+        # workers inherit whatever affinity the launcher had.  The child uses every host CPU, unbound threads, active waiting.
+        env = {k: v for k, v in os.environ.items() if not k.startswith(("TORCHELASTIC", "OMP_", "GOMP_", "KMP_", "MKL_"))}
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "GROUP_WORLD_SIZE", "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k, None)
+        env["HS_REF_CHILD"] = "1"
+        env["OMP_PROC_BIND"] = "false"
+        env["OMP_WAIT_POLICY"] = "active"
+        env["OMP_DYNAMIC"] = "false"
         cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", str(args.gpus), "--steps", str(args.steps),
                "--warmup", str(args.warmup), "--scaling", args.scaling, "--ref-pts-per-room", str(args.ref_pts_per_room)]
         out = subprocess.run(cmd, env=env, capture_output=True, text=True)
         sys.stderr.write(out.stderr)
         sys.stdout.write(out.stdout)
         sys.stdout.flush()
+        if out.returncode != 0:
+            raise SystemExit(out.returncode)
         return
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count()))  # whatever the launcher pinned us to: all host CPUs
+    except Exception:
+        pass
     O.build()
     per_room = args.ref_pts_per_room
     params = room_params()
@@ -194,11 +210,11 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
     cores = O.num_threads()
-    sample = f"{N_ROOMS} rooms x {per_room} pts per step ({n} pts), all 12 records per step, OpenMP {cores} threads"
+    sample = f"{N_ROOMS} rooms x {per_room} pts per step ({n} pts = the full workload), all 12 records per step, OpenMP {cores} threads, affinity {len(os.sched_getaffinity(0))} CPUs"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 geometry / f64 accumulation",
-        "data": "synthetic", "config": {"workload": "12-room grid apartment, cuboid residual+gradient sums per room (BASELINE configs[2]); bounded CPU sample", "rooms": N_ROOMS, "points_per_step": n},
+        "data": "synthetic", "config": workload_config(n),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -213,11 +229,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--pts-per-room", type=int, default=PTS_PER_ROOM)
-    ap.add_argument("--ref-pts-per-room", type=int, default=2_000_000)
+    ap.add_argument("--ref-pts-per-room", type=int, default=PTS_PER_ROOM, help="reference arm: points per room per step (default = the full workload)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--mode", type=int, default=-1, help="evaluation kernel variant (hs_ctx_set_mode key 0)")
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="session", choices=["session", "launch"],
+                    help="session = one resident kernel runs all K evaluations (hs_eval_session_*); launch = one kernel launch per evaluation")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: p2p = records summed over NVLink peer memory inside the reduction kernel (product path); nccl = kernel + dist.all_reduce")
     args = ap.parse_args()
@@ -276,6 +294,7 @@ def main():
     torch.cuda.synchronize()
 
     use_p2p = world > 1 and args.collective == "p2p"
+    use_session = args.path == "session" and (world == 1 or use_p2p)
     collective_check = None
     if use_p2p:
         ctx.peer_connect(rank, world)  # CUDA IPC mailboxes, handles exchanged through torch.distributed
@@ -290,13 +309,38 @@ def main():
         if not collective_check < 1e-12:
             raise SystemExit(f"peer-memory all-reduce disagrees with NCCL: max rel {collective_check}")
 
-    def step():
-        if use_p2p:
-            ctx.rooms_cuboid_sums_allreduce_async(cloud, offs, pe, rec.data_ptr())
-        else:
-            ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
-            if world > 1:
-                dist.all_reduce(rec)
+    # The optimiser's view of the device (FitCuboidBFGS.hs:184,201,233: thousands of objective evaluations over an unchanged cloud):
+    # an evaluation session = ONE resident kernel launch that runs the posted evaluations back to back, each a full pass over the
+    # rank's points followed (N > 1) by the all-reduce of the records over NVLink peer memory.  One step = one evaluation.
+    pe_alt = np.ascontiguousarray(pe * (1.0 + 1e-4))  # consecutive evaluations use different parameters, as an optimiser's do
+
+    def param_batch(k):
+        return np.ascontiguousarray(np.stack([pe if i % 2 == 0 else pe_alt for i in range(k)]))
+
+    def run_steps(k, batch=None):
+        """enqueue k steps on the stream; returns the open session (or None) - the caller closes it after its events"""
+        if use_session:
+            sess = ctx.eval_session(cloud, offs, allreduce=world > 1)
+            sess.post(param_batch(k) if batch is None else batch)
+            sess.stop()  # non-blocking: the kernel leaves after the last posted evaluation
+            return sess
+        for i in range(k):
+            p = pe if i % 2 == 0 else pe_alt
+            if use_p2p:
+                ctx.rooms_cuboid_sums_allreduce_async(cloud, offs, p, rec.data_ptr())
+            else:
+                ctx.rooms_cuboid_sums_async(cloud, offs, p, rec.data_ptr())
+                if world > 1:
+                    dist.all_reduce(rec)
+        return None
+
+    def finish(sess, want_last=False):
+        out = None
+        if sess is not None:
+            if want_last:
+                out = sess.wait(sess.posted - 1)
+            sess.close()
+        return out
 
     def barrier():
         if world > 1:
@@ -309,54 +353,65 @@ def main():
 
     # ---- warm-up (>= W steps and >= 0.3 s so clocks settle and the sampler sees load)
     t_w = time.perf_counter()
-    for _ in range(args.warmup):
-        step()
+    finish(run_steps(args.warmup))
     torch.cuda.synchronize()
-    while True:  # every rank must run the same number of steps: rank 0's clock decides, in chunks of 20
+    while True:  # every rank must run the same number of steps: rank 0's clock decides, in chunks of 100
         go = torch.tensor([1.0 if time.perf_counter() - t_w < 0.3 else 0.0], device=dev)
         if world > 1:
             dist.broadcast(go, 0)
         if go.item() == 0.0:
             break
-        for _ in range(20):
-            step()
+        finish(run_steps(100))
         torch.cuda.synchronize()
 
-    # ---- value: K steps, device-timed, max over ranks
+    # ---- value: K steps, device-timed (CUDA events on the launching stream), max over ranks
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timed_batch = param_batch(args.steps)
     barrier()
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` lists the timed regions only (no-op without a profiler)
     l0 = ctx.launch_count
     ev0.record()
-    for _ in range(args.steps):
-        step()
+    sess = run_steps(args.steps, timed_batch)
     ev1.record()
     barrier()
     launches = ctx.launch_count - l0
+    last_rec = finish(sess, want_last=True)
     ms = ev0.elapsed_time(ev1)
+    k_ms_timed = ms / args.steps  # this rank's own time per step (before the max over ranks)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = n_total * args.steps / (ms * 1e-3)
-    rec_host = rec.cpu().numpy().reshape(N_ROOMS, hb.HS_REC).copy()
+    if last_rec is None:
+        last_rec = rec.cpu().numpy().reshape(N_ROOMS, hb.HS_REC).copy()
+    last_params = pe if (args.steps - 1) % 2 == 0 else pe_alt
 
-    # ---- roofline of the dominant kernel: kernel-only launches, same stream, events around the loop
+    # ---- the same evaluation as one launch per step (hs_rooms_cuboid_sums_async: what a caller without a session gets), no exchange
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        ctx.rooms_cuboid_sums_async(cloud, offs, pe, rec.data_ptr())
+        ctx.rooms_cuboid_sums_async(cloud, offs, last_params, rec.data_ptr())
     ev1.record()
     torch.cuda.synchronize()
-    k_ms = ev0.elapsed_time(ev1) / args.steps
+    launch_ms = ev0.elapsed_time(ev1) / args.steps
+    rec_host = rec.cpu().numpy().reshape(N_ROOMS, hb.HS_REC).copy()
+    session_equals_launch = None
+    if use_session and world == 1:  # same partition, same order of additions: bit-identical
+        session_equals_launch = bool(np.array_equal(last_rec, rec_host))
+        if not session_equals_launch:
+            raise SystemExit("session records differ from the one-launch-per-evaluation records")
+    # roofline of the dominant kernel = the kernel of the timed region: algorithmic bytes of the evaluations one launch ran / its duration
+    k_ms = k_ms_timed if use_session else launch_ms
     peak, peak_src = measured_peak_gbs()
     achieved = BYTES_PER_POINT * n_local / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tj = json.load(fh)
             if int(tj.get("points_per_launch", -1)) == int(n_local):
                 traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = "profiles/traffic.json (ncu --set full capture of one evaluation launch of this workload; not measured in this run)"
     except Exception:
         pass
 
@@ -404,39 +459,57 @@ def main():
         O.build()
         hp = host_pts.numpy()
         reps, t_cpu, n_cpu = 0, 0.0, 0
-        O.cuboid_sums(hp[: min(n_local, 1_000_000)], pe[0])
-        check = None
+        O.cuboid_sums(hp[: min(n_local, 1_000_000)], last_params[0])
+        check = np.zeros((N_ROOMS, hb.HS_REC))
         while t_cpu < 10.0 and reps < 8:
             t0 = time.perf_counter()
             for r in range(N_ROOMS):
-                rr = O.cuboid_sums(hp[offs[r] : offs[r + 1]], pe[r])
-                if reps == 0 and r == 0:
-                    check = rr
+                rr = O.cuboid_sums(hp[offs[r] : offs[r + 1]], last_params[r])
+                if reps == 0:
+                    check[r] = rr
             t_cpu += time.perf_counter() - t0
             n_cpu += n_local
             reps += 1
+        # the whole 12 x 22 record of the timed path against the oracle: counts bit-exact; sums relative to the room's largest sum
+        # of the same kind (f | sum r | B-moments), the scale the optimiser sees them at
+        got = last_rec
+        rel = np.zeros_like(check[:, :16])
+        for lo_, hi_ in ((0, 1), (1, 7), (7, 16)):
+            sc = np.abs(check[:, lo_:hi_]).max(axis=1, keepdims=True)
+            rel[:, lo_:hi_] = np.abs(got[:, lo_:hi_] - check[:, lo_:hi_]) / np.maximum(sc, 1e-300)
         cpu = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                "sample": f"{reps} x the full {n_local}-pt workload (12 rooms), OpenMP over all host threads",
-               "parity_room0_counts_equal": bool(np.array_equal(check[16:22], rec_host[0, 16:22])),
-               "parity_room0_f_rel": float(abs(check[0] - rec_host[0, 0]) / check[0])}
+               "parity_counts_equal_all_rooms": bool(np.array_equal(check[:, 16:22], got[:, 16:22])),
+               "parity_sums_max_rel_all_rooms": float(rel.max()),
+               "parity_f_max_rel": float(rel[:, 0].max())}
+        if not (cpu["parity_counts_equal_all_rooms"] and cpu["parity_f_max_rel"] < 1e-6):
+            raise SystemExit(f"GPU records disagree with the oracle: {cpu}")
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32 geometry / f64 accumulation", "data": "synthetic",
-            "config": {"workload": "12-room grid apartment (BASELINE configs[2]): per-room cuboid residual + gradient sums, nearest-plane assignment",
-                       "rooms": N_ROOMS, "points_total": int(n_total), "points_per_gpu": int(n_local), "sharding": f"point-range x{world}",
-                       "l2": "inputs larger than L2 (%.0f MB per GPU per step, L2 126 MB)" % (n_local * 12 / 1e6),
+            "config": workload_config(n_total),
+            "detail": {"path": ("evaluation session (hs_eval_session_*): one resident kernel, one step = one posted evaluation" if use_session else "one kernel launch per evaluation"),
+                       "points_per_gpu": int(n_local), "sharding": f"point-range x{world}",
                        "collective": ("none" if world == 1 else ("records summed over NVLink peer memory inside the reduction kernel (12x24 f64, CUDA IPC mailboxes)" if use_p2p
                                       else "nccl all_reduce of 12x24 f64 per step")),
                        "collective_vs_nccl_max_rel": collective_check},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 12), "d2h_bytes_per_step": int(N_ROOMS * hb.HS_REC * 8),
-                    "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps, "h2d_gbs_per_gpu": n_local * 12 / (e_ms / e2e_steps * 1e-3) / 1e9,
+                    "path": "hs_cloud_write (pinned host -> HBM) + one evaluation launch (+ exchange) + record D2H, every step"},
             "gpu_launches": int(launches),
+            "evaluations_per_launch": (args.steps if use_session else 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "k_rooms_cuboid_sums", "kernel_ms": k_ms, "bytes_per_point": BYTES_PER_POINT,
-                         "points_per_launch": int(n_local), "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": ("k_eval<session>: ONE launch ran the %d timed evaluations; kernel_ms = its duration / %d" % (args.steps, args.steps)) if use_session else "k_eval (one launch per evaluation)",
+                         "kernel_ms": k_ms, "bytes_per_point": BYTES_PER_POINT,
+                         "points_per_launch": int(n_local) * (args.steps if use_session else 1), "points_per_evaluation": int(n_local),
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "one_launch_per_evaluation": {"kernel_ms": launch_ms, "achieved": BYTES_PER_POINT * n_local / (launch_ms * 1e-3) / 1e9,
+                                                       "frac": BYTES_PER_POINT * n_local / (launch_ms * 1e-3) / 1e9 / peak},
+                         "session_records_equal_launch_records": session_equals_launch},
             "clocks": clocks,
             "cpu_baseline": cpu,
             "gpts_per_s": value / 1e9,

@@ -4,7 +4,7 @@
 module HouseScanB200.FFI where
 
 import Data.Int (Int32, Int64)
-import Data.Word (Word8, Word16, Word32)
+import Data.Word (Word8, Word16, Word32, Word64)
 import Foreign.C.String (CString)
 import Foreign.C.Types (CDouble(..), CFloat(..))
 import Foreign.Ptr (Ptr)
@@ -67,6 +67,22 @@ foreign import ccall safe "hs_peer_mailbox_create"  c_peer_mailbox_create  :: Pt
 foreign import ccall safe "hs_peer_mailbox_connect" c_peer_mailbox_connect :: Ptr HsCtx -> Ptr Word8 -> IO Int32
 foreign import ccall safe "hs_rooms_cuboid_sums_allreduce_async"
   c_rooms_cuboid_sums_allreduce :: Ptr HsCtx -> Ptr HsCloud -> Ptr Int64 -> Int32 -> Ptr CDouble -> Ptr () -> IO Int32
+
+-- one executable, several GPUs: ctxs of this process become ranks 0..n-1 (housescan.cabal:15-43 builds ONE executable)
+foreign import ccall safe "hs_peer_group_create_local" c_peer_group_create_local :: Ptr (Ptr HsCtx) -> Int32 -> IO Int32
+
+-- evaluation sessions: the optimiser loop of FitCuboidBFGS.hs:184,201,233 against ONE resident kernel (no launch per evaluation)
+data HsEvalSession
+foreign import ccall safe "hs_eval_session_begin"
+  c_eval_session_begin :: Ptr HsCtx -> Ptr HsCloud -> Ptr Int64 -> Int32 -> Int32 -> Ptr (Ptr HsEvalSession) -> IO Int32
+foreign import ccall safe "hs_eval_session_post"  c_eval_session_post  :: Ptr HsEvalSession -> Ptr CDouble -> Int32 -> IO Int32
+foreign import ccall safe "hs_eval_session_wait"  c_eval_session_wait  :: Ptr HsEvalSession -> Int64 -> Ptr CDouble -> IO Int32
+foreign import ccall safe "hs_eval_session_eval"  c_eval_session_eval  :: Ptr HsEvalSession -> Ptr CDouble -> Ptr CDouble -> IO Int32
+foreign import ccall unsafe "hs_eval_session_done" c_eval_session_done :: Ptr HsEvalSession -> IO Int64
+foreign import ccall unsafe "hs_eval_session_times" c_eval_session_times :: Ptr HsEvalSession -> Int64 -> Ptr Word64 -> Ptr Word64 -> IO Int32
+foreign import ccall unsafe "hs_eval_session_device_results" c_eval_session_device_results :: Ptr HsEvalSession -> IO (Ptr ())
+foreign import ccall safe "hs_eval_session_stop"  c_eval_session_stop  :: Ptr HsEvalSession -> IO Int32
+foreign import ccall safe "hs_eval_session_end"   c_eval_session_end   :: Ptr HsEvalSession -> IO Int32
 
 -- room input formats (SURVEY.md 8f rank 1): planeEqsFromFile Main.hs:1379-1389, cloudFromFile :1332-1345, loadRoom :1740-1765
 foreign import ccall unsafe "hs_plane_eqs_from_text"

@@ -56,6 +56,7 @@ SIGNATURES = {
     "hs_eval_session_eval": (i32, [vp, vp, vp]),
     "hs_eval_session_done": (i64, [vp]),
     "hs_eval_session_device_results": (vp, [vp]),
+    "hs_eval_session_times": (i32, [vp, i64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hs_eval_session_stop": (i32, [vp]),
     "hs_eval_session_end": (i32, [vp]),
     "hs_cuboid_grad_from_sums": (i32, [vp, vp, C.POINTER(f64), vp, vp]),

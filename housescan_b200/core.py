@@ -73,6 +73,12 @@ class EvalSession:
         self.posted += 1
         return rec
 
+    def times(self, seq: int):
+        """device clock (ns) of evaluation seq: (command seen by the device, records committed)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx._chk(self.ctx.lib.hs_eval_session_times(self.h, seq, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     @property
     def done(self) -> int:
         return int(self.ctx.lib.hs_eval_session_done(self.h))

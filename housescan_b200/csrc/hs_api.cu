@@ -1001,11 +1001,30 @@ int32_t hs_fit_cuboid_cloud_bfgs(hs_ctx* ctx, const hs_cloud* cloud, const doubl
   if (!ctx) return HS_EINVAL;
   if (!cloud || !init || !params_out) { ctx->err = "hs_fit_cuboid_cloud_bfgs: bad arguments"; return HS_EINVAL; }
   int32_t last_rc = HS_OK;
+  // The optimiser loop talks to ONE resident kernel (an evaluation session): every objective evaluation is a parameter set posted
+  // to the device and a 24-Double record coming back, not a kernel launch.  The exact-products mode keeps the launch-per-evaluation form.
+  hs_eval_session* sess = nullptr;
+  const int64_t off[2] = {0, cloud->n};
+  if (ctx->modes[HS_MODE_EVAL_KERNEL] != HS_EVAL_EXACT) {
+    if (int32_t rc = hs_eval_session_begin(ctx, cloud, off, 1, 0, &sess)) return rc;
+  }
   auto eval = [&](const double* x, double* f, double* g) {
-    last_rc = hs_cuboid_residual_grad(ctx, cloud, x, f, g, nullptr);
+    if (sess) {
+      double rec[HS_REC];
+      last_rc = hs_eval_session_eval(sess, x, rec);
+      if (last_rc == HS_OK) hs::cuboid_grad_from_sums(x, rec, f, g, nullptr);
+    } else {
+      last_rc = hs_cuboid_residual_grad(ctx, cloud, x, f, g, nullptr);
+    }
     return last_rc == HS_OK;
   };
   hs::BFGSResult r = hs::bfgs(eval, init, 10, max_iter > 0 ? max_iter : 200, gtol > 0 ? gtol : 1e-6);
+  if (sess) {
+    const std::string msg = ctx->err;
+    const int32_t rc_end = hs_eval_session_end(sess);
+    if (last_rc != HS_OK) ctx->err = msg;  // the evaluation's own message, not the close's
+    else if (rc_end != HS_OK) return rc_end;
+  }
   if (!r.ok) return last_rc != HS_OK ? last_rc : HS_ECUDA;
   for (int i = 0; i < 10; ++i) params_out[i] = r.x[i];
   if (f_out) *f_out = r.f;

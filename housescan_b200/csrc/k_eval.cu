@@ -43,17 +43,24 @@ struct hs_eval_state {
   size_t partials_bytes = 0;
   double* d_local_rec = nullptr;
   bool attr_set[2] = {false, false};
+  // session rings (allocated at the first session of the ctx, sized for HS_MAX_ROOMS, kept: begin must cost a launch, not five allocations)
+  EvalCmd* h_cmds = nullptr;     // mapped
+  EvalCmd* d_cmds = nullptr;
+  EvalHostCtl* h_ctl = nullptr;  // mapped
+  double* h_results = nullptr;   // mapped
+  double* d_results = nullptr;
+  unsigned long long* h_times = nullptr;  // mapped
 };
 
 struct hs_eval_session {
   hs_ctx* ctx = nullptr;
   int32_t nrooms = 0;
   bool exchange = false;
-  EvalCmd* h_cmds = nullptr;   // mapped
-  EvalCmd* d_cmds = nullptr;
-  EvalHostCtl* h_ctl = nullptr;  // mapped
-  double* h_results = nullptr;   // mapped
+  EvalCmd* h_cmds = nullptr;     // the rings of the ctx's hs_eval_state (one session per ctx at a time)
+  EvalHostCtl* h_ctl = nullptr;
+  double* h_results = nullptr;
   double* d_results = nullptr;
+  unsigned long long* h_times = nullptr;
   uint32_t posted = 0;
   bool stopped = false;
   bool empty = false;  // no point in any room: records are zero, no kernel runs
@@ -141,6 +148,12 @@ void hs_eval_state_free(hs_ctx* ctx) {
   if (st->d_ctl) cudaFree(st->d_ctl);
   if (st->d_partials) cudaFree(st->d_partials);
   if (st->d_local_rec) cudaFree(st->d_local_rec);
+  if (st->h_cmds) cudaFreeHost(st->h_cmds);
+  if (st->h_ctl) cudaFreeHost(st->h_ctl);
+  if (st->h_results) cudaFreeHost(st->h_results);
+  if (st->h_times) cudaFreeHost(st->h_times);
+  if (st->d_cmds) cudaFree(st->d_cmds);
+  if (st->d_results) cudaFree(st->d_results);
   delete st;
   ctx->eval = nullptr;
 }
@@ -221,13 +234,19 @@ int32_t launch_eval(hs_ctx* ctx, const float* xyz, int64_t n, const RoomTable& r
   std::lock_guard<std::mutex> lock__((ctx)->mu);         \
   if (cudaSetDevice((ctx)->device) != cudaSuccess) { (ctx)->err = "cudaSetDevice failed"; return HS_ECUDA; }
 
-static void session_free(hs_eval_session* s) {
-  if (s->h_cmds) cudaFreeHost(s->h_cmds);
-  if (s->h_ctl) cudaFreeHost(s->h_ctl);
-  if (s->h_results) cudaFreeHost(s->h_results);
-  if (s->d_cmds) cudaFree(s->d_cmds);
-  if (s->d_results) cudaFree(s->d_results);
-  delete s;
+static void session_free(hs_eval_session* s) { delete s; }
+
+static int32_t session_rings(hs_ctx* ctx, hs_eval_state* st) {
+  if (st->h_cmds) return HS_OK;
+  const size_t rec_bytes = sizeof(double) * HS_MAX_ROOMS * HS_REC;
+  HS_CUDA_TRY(ctx, cudaHostAlloc(&st->h_ctl, 64, cudaHostAllocMapped));
+  HS_CUDA_TRY(ctx, cudaHostAlloc(&st->h_results, rec_bytes * EV_QCAP, cudaHostAllocMapped));
+  HS_CUDA_TRY(ctx, cudaMalloc(&st->d_cmds, sizeof(EvalCmd) * EV_QCAP));
+  HS_CUDA_TRY(ctx, cudaMalloc(&st->d_results, rec_bytes * EV_QCAP));
+  HS_CUDA_TRY(ctx, cudaHostAlloc(&st->h_times, sizeof(unsigned long long) * 2 * EV_QCAP, cudaHostAllocMapped));
+  std::memset(st->h_times, 0, sizeof(unsigned long long) * 2 * EV_QCAP);
+  HS_CUDA_TRY(ctx, cudaHostAlloc(&st->h_cmds, sizeof(EvalCmd) * EV_QCAP, cudaHostAllocMapped));
+  return HS_OK;
 }
 
 static inline uint32_t host_load(const uint32_t* p) { return reinterpret_cast<const std::atomic<uint32_t>*>(p)->load(std::memory_order_acquire); }
@@ -276,27 +295,24 @@ int32_t hs_eval_session_begin(hs_ctx* ctx, const hs_cloud* cloud, const int64_t*
   if (allreduce && ctx->px.world < 1) { ctx->err = "hs_eval_session_begin: no peer group (hs_peer_mailbox_create / _connect or hs_peer_group_create_local first)"; return HS_EINVAL; }
   hs_eval_state* st = nullptr;
   if (int32_t rc = eval_prepare(ctx, cloud->n, room_offsets, nrooms, &st)) return rc;
+  if (int32_t rc = session_rings(ctx, st)) return rc;
   hs_eval_session* s = new (std::nothrow) hs_eval_session();
   if (!s) { ctx->err = "out of host memory"; return HS_ENOMEM; }
   s->ctx = ctx;
+  s->h_cmds = st->h_cmds; s->h_ctl = st->h_ctl; s->h_results = st->h_results; s->d_results = st->d_results; s->h_times = st->h_times;
   s->nrooms = nrooms;
   s->exchange = allreduce && ctx->px.world > 1;
   s->empty = st->h_plan.nrooms_nonempty == 0;
   const size_t rec_bytes = sizeof(double) * nrooms * HS_REC;
   auto fail = [&](cudaError_t e) { ctx->err = std::string("hs_eval_session_begin: ") + cudaGetErrorString(e); session_free(s); return HS_ECUDA; };
   cudaError_t e;
-  if ((e = cudaHostAlloc(&s->h_cmds, sizeof(EvalCmd) * EV_QCAP, cudaHostAllocMapped)) != cudaSuccess) return fail(e);
-  if ((e = cudaHostAlloc(&s->h_ctl, 64, cudaHostAllocMapped)) != cudaSuccess) return fail(e);
-  if ((e = cudaHostAlloc(&s->h_results, rec_bytes * EV_QCAP, cudaHostAllocMapped)) != cudaSuccess) return fail(e);
   std::memset(s->h_ctl, 0, 64);
-  std::memset(s->h_results, 0, rec_bytes * EV_QCAP);
-  if ((e = cudaMalloc(&s->d_cmds, sizeof(EvalCmd) * EV_QCAP)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&s->d_results, rec_bytes * EV_QCAP)) != cudaSuccess) return fail(e);
+  if (s->empty) std::memset(s->h_results, 0, rec_bytes * EV_QCAP);  // no kernel: every record is zero
   if (!s->empty) {
     EvalArgs a;
     std::memset(&a, 0, sizeof a);
     a.xyz = cloud->d; a.plan = st->d_plan; a.ctl = st->d_ctl; a.partials = st->d_partials; a.local_rec = st->d_local_rec; a.out = s->d_results;
-    a.d_cmds = s->d_cmds;
+    a.d_cmds = st->d_cmds;
     void* dp = nullptr;
     if ((e = cudaHostGetDevicePointer(&dp, s->h_cmds, 0)) != cudaSuccess) return fail(e);
     a.h_cmds = static_cast<const EvalCmd*>(dp);
@@ -304,6 +320,8 @@ int32_t hs_eval_session_begin(hs_ctx* ctx, const hs_cloud* cloud, const int64_t*
     a.h_ctl = static_cast<EvalHostCtl*>(dp);
     if ((e = cudaHostGetDevicePointer(&dp, s->h_results, 0)) != cudaSuccess) return fail(e);
     a.h_results = static_cast<double*>(dp);
+    if ((e = cudaHostGetDevicePointer(&dp, s->h_times, 0)) != cudaSuccess) return fail(e);
+    a.h_times = static_cast<unsigned long long*>(dp);
     a.h_status = ctx->d_status;
     a.idle_timeout_ns = 20ull * 1000000000ull;
     if (s->exchange) { a.px = ctx->px; a.epoch0 = ctx->px.epoch + 1; }
@@ -377,6 +395,14 @@ int32_t hs_eval_session_stop(hs_eval_session* s) {
   HS_SLOCK(ctx);
   s->stopped = true;
   host_store(&s->h_ctl->stop, 1u);
+  return HS_OK;
+}
+
+int32_t hs_eval_session_times(const hs_eval_session* s, int64_t seq, uint64_t* seen_ns, uint64_t* done_ns) {
+  if (!s || seq < 0 || seq >= static_cast<int64_t>(s->posted) || static_cast<int64_t>(s->posted) - seq > EV_QCAP) return HS_EINVAL;
+  if (static_cast<int64_t>(host_load(&s->h_ctl->done)) <= seq && !s->empty) return HS_EINVAL;
+  if (seen_ns) *seen_ns = s->h_times[2 * (seq % EV_QCAP)];
+  if (done_ns) *done_ns = s->h_times[2 * (seq % EV_QCAP) + 1];
   return HS_OK;
 }
 

@@ -61,9 +61,9 @@ struct EvalCtl {  // device memory, zero between launches / at session begin
   uint32_t rooms_done[EV_D];
 };
 
-struct EvalHostCtl {  // mapped pinned host memory (session)
-  uint32_t posted;  // host -> device: commands written to h_cmds
-  uint32_t stop;    // host -> device
+struct alignas(16) EvalHostCtl {  // mapped pinned host memory (session)
+  uint32_t posted;  // host -> device: commands written to h_cmds  } read together by the dispatcher
+  uint32_t stop;    // host -> device                               }
   uint32_t done;    // device -> host: evaluations whose records are in h_results
   uint32_t error;   // device -> host
 };
@@ -79,6 +79,7 @@ struct EvalArgs {
   const EvalCmd* h_cmds;        // session: host-mapped command ring [EV_QCAP]
   EvalHostCtl* h_ctl;           // session
   double* h_results;            // session: host-mapped result ring [EV_QCAP][nrooms * HS_REC]
+  unsigned long long* h_times;  // session: host-mapped [EV_QCAP][2] %globaltimer stamps: command seen by the device, records committed
   uint32_t* h_status;           // mapped word of the ctx: set to HS_ENCCL when a peer timed out
   unsigned long long idle_timeout_ns;
   uint32_t epoch0;              // peer epoch of evaluation 0 (epochs are > 0)
@@ -212,12 +213,15 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
   // =================================================================================================== dispatcher (session)
   if (SESSION && warp == W_DISPATCH) {
     if (b != 0) return;
-    uint32_t seq = 0;
+    uint32_t seq = 0, spins = 0;
     unsigned long long t_last = peer_now_ns();
     for (;;) {
-      const uint32_t hp = ld_sys_u32(&a.h_ctl->posted);
+      uint32_t hp, hstop;  // {posted, stop} sit side by side: ONE read over PCIe per poll
+      asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hp), "=r"(hstop) : "l"(&a.h_ctl->posted) : "memory");
       if (hp != seq) {
+        const unsigned long long t_seen = peer_now_ns();
         while (seq != hp) {  // copy the new commands host -> device ring (16 floats = one 64-byte line per room)
+          if (lane == 0) a.h_times[2 * (seq % EV_QCAP)] = t_seen;
           const float4* src = reinterpret_cast<const float4*>(a.h_cmds[seq % EV_QCAP].c);
           float4* dst = reinterpret_cast<float4*>(a.d_cmds[seq % EV_QCAP].c);
           for (int i = lane; i < nrooms * 4; i += 32) dst[i] = ld_sys_v4(src + i);
@@ -227,20 +231,22 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         __syncwarp();
         if (lane == 0) st_release_u32(&a.ctl->posted, seq);
         t_last = peer_now_ns();
+        spins = 0;
         continue;
       }
-      if (ld_sys_u32(&a.h_ctl->stop)) {
-        if (ld_sys_u32(&a.h_ctl->posted) != seq) continue;  // commands posted just before the stop
+      if (hstop) {  // the host stores `posted` before `stop` (release order), and this read saw both: nothing is left behind
         if (lane == 0) st_release_u32(&a.ctl->stop, 1u);
         return;
       }
-      if (ld_acquire_u32(&a.ctl->error)) { if (lane == 0) st_release_u32(&a.ctl->stop, 1u); return; }
-      if (ld_acquire_u32(&a.ctl->done_seq) != seq) t_last = peer_now_ns();  // evaluations still running: not idle
-      else if (peer_now_ns() - t_last > a.idle_timeout_ns) {  // watchdog: nobody posts, nobody stops
-        if (lane == 0) { a.ctl->error = 2u; st_sys_u32(&a.h_ctl->error, 2u); __threadfence_system(); st_release_u32(&a.ctl->stop, 1u); }
-        return;
+      if ((++spins & 15u) == 0u) {  // off the fast path: errors raised by a finaliser, the idle watchdog
+        if (ld_acquire_u32(&a.ctl->error)) { if (lane == 0) st_release_u32(&a.ctl->stop, 1u); return; }
+        if (ld_acquire_u32(&a.ctl->done_seq) != seq) t_last = peer_now_ns();  // evaluations still running: not idle
+        else if (peer_now_ns() - t_last > a.idle_timeout_ns) {  // watchdog: nobody posts, nobody stops
+          if (lane == 0) { a.ctl->error = 2u; st_sys_u32(&a.h_ctl->error, 2u); __threadfence_system(); st_release_u32(&a.ctl->stop, 1u); }
+          return;
+        }
       }
-      __nanosleep(200);
+      __nanosleep(100);
     }
   }
 
@@ -394,6 +400,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         __threadfence_system();
         __syncwarp();
         if (lane == 0) {
+          a.h_times[2 * (e % EV_QCAP) + 1] = peer_now_ns();
           __threadfence_system();
           st_sys_u32(&a.h_ctl->done, e + 1u);
           st_release_u32(&a.ctl->done_seq, e + 1u);

@@ -135,6 +135,8 @@ HS_API int32_t hs_eval_session_post(hs_eval_session* s, const double* params, in
 HS_API int32_t hs_eval_session_wait(hs_eval_session* s, int64_t seq, double* rec_out);
 HS_API int32_t hs_eval_session_eval(hs_eval_session* s, const double* params, double* rec_out);
 HS_API int64_t hs_eval_session_done(const hs_eval_session* s); /* evaluations finished so far */
+/* device clock (%globaltimer, ns) of evaluation `seq`: when the device saw the command, when its records were committed */
+HS_API int32_t hs_eval_session_times(const hs_eval_session* s, int64_t seq, uint64_t* seen_ns, uint64_t* done_ns);
 HS_API void* hs_eval_session_device_results(const hs_eval_session* s); /* device ring [256][nrooms x HS_REC] doubles */
 HS_API int32_t hs_eval_session_stop(hs_eval_session* s);
 HS_API int32_t hs_eval_session_end(hs_eval_session* s);
