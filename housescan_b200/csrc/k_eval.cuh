@@ -48,8 +48,9 @@ struct EvalPlan {  // device memory; fixed for a (cloud, room offsets, grid) tri
   int32_t room_blo[HS_MAX_ROOMS], room_nb[HS_MAX_ROOMS];  // blocks with points of the room: room_blo .. room_blo + room_nb - 1
 };
 
-struct EvalCmd {  // one evaluation's plane constants: per room n[3][3] (normals of the + walls), dp[3], dm[3], pad
-  float c[HS_MAX_ROOMS][16];
+constexpr int EV_CMD_F = 24;  // floats per room: 6 x 16 bytes
+struct EvalCmd {  // one evaluation's plane constants: per room n[3][3] (normals of the + walls), dp[3], dm[3], sa[3], sk[3] (side tests), 1.0f, pad
+  float c[HS_MAX_ROOMS][EV_CMD_F];
 };
 
 struct EvalCtl {  // device memory, zero between launches / at session begin
@@ -149,7 +150,9 @@ __device__ __forceinline__ void load_room_consts(RoomK& R, const float* c16) {
   for (int j = 0; j < 3; ++j) {
     R.n[j][0] = c16[3 * j]; R.n[j][1] = c16[3 * j + 1]; R.n[j][2] = c16[3 * j + 2];
     R.dp[j] = c16[9 + j]; R.dm[j] = c16[12 + j];
+    R.sa[j] = c16[15 + j]; R.sk[j] = c16[18 + j];
   }
+  R.one = c16[21];
 }
 
 // raw room sums -> record component L (= lane); raw value k lives on lane k of the calling warp, lanes >= EV_NRAW hold 0.
@@ -220,11 +223,11 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hp), "=r"(hstop) : "l"(&a.h_ctl->posted) : "memory");
       if (hp != seq) {
         const unsigned long long t_seen = peer_now_ns();
-        while (seq != hp) {  // copy the new commands host -> device ring (16 floats = one 64-byte line per room)
+        while (seq != hp) {  // copy the new commands host -> device ring (24 floats per room)
           if (lane == 0) a.h_times[2 * (seq % EV_QCAP)] = t_seen;
           const float4* src = reinterpret_cast<const float4*>(a.h_cmds[seq % EV_QCAP].c);
           float4* dst = reinterpret_cast<float4*>(a.d_cmds[seq % EV_QCAP].c);
-          for (int i = lane; i < nrooms * 4; i += 32) dst[i] = ld_sys_v4(src + i);
+          for (int i = lane; i < nrooms * (EV_CMD_F / 4); i += 32) dst[i] = ld_sys_v4(src + i);
           ++seq;
         }
         __threadfence();
@@ -438,12 +441,13 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
     for (int si = 0; si < nseg; ++si) {
       const int r = rfirst + si;
       const int64_t lo = s_lo[si], hi = s_hi[si];
+      if (lo >= hi) continue;  // a room without points between two rooms of this block: no segment, no partial, no ticket (room_nb counts none)
       RoomK R;
       if (SESSION) {
         const float* c16 = a.d_cmds[e % EV_QCAP].c[r];
-        float t[15];
+        float t[22];
 #pragma unroll
-        for (int i = 0; i < 15; ++i) t[i] = __ldcg(c16 + i);
+        for (int i = 0; i < 22; ++i) t[i] = __ldcg(c16 + i);
         load_room_consts(R, t);
       } else {
         load_room_consts(R, cmd0.c[r]);
@@ -457,8 +461,8 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         // ragged head / tail points (at most 3 each): the same per-point block, one point per thread
         const int64_t head_end = gl * 4, tail_begin = gh * 4;
         const int64_t nh = head_end - lo, ntail = hi - tail_begin;
-        if (static_cast<int64_t>(threadIdx.x) < nh) { const int64_t i = lo + threadIdx.x; add_point_pred2(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
-        else if (threadIdx.x >= 32 && static_cast<int64_t>(threadIdx.x) - 32 < ntail) { const int64_t i = tail_begin + threadIdx.x - 32; add_point_pred2(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        if (static_cast<int64_t>(threadIdx.x) < nh) { const int64_t i = lo + threadIdx.x; add_point_pred3(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        else if (threadIdx.x >= 32 && static_cast<int64_t>(threadIdx.x) - 32 < ntail) { const int64_t i = tail_begin + threadIdx.x - 32; add_point_pred3(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
         const int64_t ngroups = gh - gl;
         const int nfull = static_cast<int>(ngroups / TILE_GROUPS);
         const int rem_groups = static_cast<int>(ngroups - static_cast<int64_t>(nfull) * TILE_GROUPS);
@@ -472,10 +476,10 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
           mbar_arrive_s(empty_s + 8 * stage);  // the values are in registers: hand the slot back before the math
 #pragma unroll
           for (int g = 0; g < GPT; ++g) {
-            add_point_pred2(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
-            add_point_pred2(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
-            add_point_pred2(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
-            add_point_pred2(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
+            add_point_pred3(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
+            add_point_pred3(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
+            add_point_pred3(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
+            add_point_pred3(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
           }
           npts += 4 * GPT;
           if (++stage == STAGES) { stage = 0; parity ^= 1u; }
@@ -494,10 +498,10 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
 #pragma unroll
           for (int g = 0; g < GPT; ++g)
             if (g * NCONS + static_cast<int>(threadIdx.x) < rem_groups) {
-              add_point_pred2(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
-              add_point_pred2(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
-              add_point_pred2(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
-              add_point_pred2(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
+              add_point_pred3(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
+              add_point_pred3(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
+              add_point_pred3(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
+              add_point_pred3(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
               npts += 4;
             }
           if (++stage == STAGES) { stage = 0; parity ^= 1u; }
@@ -505,7 +509,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         }
       } else {
         const int64_t i = lo + threadIdx.x;
-        if (i < hi) { add_point_pred2(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        if (i < hi) { add_point_pred3(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
       }
       flush_chains(ch, npts, dacc, lane);
       // ---- the block's sums of this segment: warp Doubles added in warp order by warp 0 and parked for the reducer; everybody

@@ -709,3 +709,60 @@ def test_remove_ceiling_sharded_single_rank_equals_remove_ceiling(ctx):
     kept, _, ylim, first = VectorUtil.removeCeilingSharded(cl)
     ref, _, ylim_ref = ctx.remove_ceiling(cl)
     assert first == 0 and ylim == ylim_ref and np.array_equal(kept.download().view(np.uint32), ref.download().view(np.uint32))
+
+
+def test_eval_random_room_layouts(ctx):
+    """throughput kernel against the exact-products kernel over random layouts (empty rooms between rooms, rooms smaller than a
+    group, unaligned offsets, clouds from one group to several tiles per block), twice per layout (tickets must come back to zero),
+    and the resident session form bit-identical to the launches"""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        nrooms = int(rng.integers(1, 9))
+        kind = trial % 4
+        hi = (30, 3_000, 60_000, 700_000)[kind]
+        sizes = rng.integers(0, hi, size=nrooms)
+        sizes[rng.random(nrooms) < 0.25] = 0
+        lead, trail = int(rng.integers(0, 7)), int(rng.integers(0, 7))
+        n = lead + int(sizes.sum()) + trail
+        if n == 0:
+            continue
+        params = np.stack([np.concatenate([rng.normal(size=3), rng.uniform(1, 5, 3), rng.normal(size=4)]) for _ in sizes])
+        xyz = (rng.normal(size=(n, 3)) * 3).astype(np.float32)
+        offs = np.concatenate([[0], np.cumsum(sizes)]) + lead
+        cloud = ctx.upload(xyz)
+        ctx.set_mode(0, 1)
+        exact = ctx.rooms_cuboid_sums(cloud, offs, params)
+        ctx.set_mode(0, 0)
+        for rep in range(2):
+            fast = ctx.rooms_cuboid_sums(cloud, offs, params)
+            assert np.array_equal(fast[:, 16:24], exact[:, 16:24]), (trial, rep, sizes.tolist())
+            scale = np.abs(exact[:, :16]).max(axis=1, keepdims=True) + 1e-30
+            assert np.max(np.abs(fast[:, :16] - exact[:, :16]) / scale) < 2e-5, (trial, rep)  # vs its own magnitude: cancellation-free bound is looser
+        with ctx.eval_session(cloud, offs) as sess:
+            last = sess.post(np.stack([params, params]))
+            assert np.array_equal(sess.wait(last), fast) and np.array_equal(sess.wait(last - 1), fast), (trial, sizes.tolist())
+
+
+def test_eval_side_threshold_is_the_reference_comparison(ctx):
+    """The throughput kernel decides the side of a wall pair with one fused instruction on a host-computed threshold
+    (k_eval.cu side_threshold) instead of comparing the two distances.  Points packed within a few ulps of the mid-plane of the
+    pair that wins the assignment: the per-wall counts must be the reference's (strict `<`, ties keep the + wall), bit for bit."""
+    rng = np.random.default_rng(77)
+    for trial in range(12):
+        j = trial % 3
+        dims = np.array([5.0, 6.0, 7.0])
+        dims[j] = rng.uniform(0.5, 1.5)  # axis j is the nearest pair for points around the centre
+        center = rng.normal(size=3) * (0.0 if trial < 3 else 2.0)
+        quat = np.array([1.0, 0, 0, 0]) if trial < 6 else rng.normal(size=4)
+        params = np.concatenate([center, dims, quat])
+        R = synth.rot_rows_from_quat(params[6:])  # rows = wall normals
+        n = 400_000
+        u = rng.uniform(-0.2, 0.2, size=(n, 3))
+        u[:, j] = rng.uniform(-3e-6, 3e-6, size=n)  # mid-plane of pair j (in room coordinates) +- a dozen ulps
+        u[: n // 8, j] = 0.0
+        xyz = (u @ R + center).astype(np.float32)
+        rec = ctx.rooms_cuboid_sums(ctx.upload(xyz), np.array([0, n]), params[None])
+        ro = O.cuboid_sums(xyz, params)
+        assert np.array_equal(rec[0, 16:22], ro[16:22]), (trial, rec[0, 16:22], ro[16:22])
+        assert rec[0, 16 + 2 * j] > 1000 and rec[0, 17 + 2 * j] > 1000  # both sides populated: the threshold was exercised
+        assert abs(rec[0, 0] - ro[0]) <= 1e-6 * ro[0]
