@@ -43,7 +43,7 @@ struct hs_eval_state {
   double* d_partials = nullptr;
   size_t partials_bytes = 0;
   double* d_local_rec = nullptr;
-  bool attr_set[2] = {false, false};
+  bool attr_set[2] = {false, false};  // MaxDynamicSharedMemorySize set on this ctx's device: one-launch form, session form
   // session rings (allocated at the first session of the ctx, sized for HS_MAX_ROOMS, kept: begin must cost a launch, not five allocations)
   EvalCmd* h_cmds = nullptr;     // mapped
   EvalCmd* d_cmds = nullptr;
@@ -183,47 +183,13 @@ static int32_t eval_prepare(hs_ctx* ctx, int64_t n, const int64_t* off, int nroo
   return HS_OK;
 }
 
-// Side test of one axis, P(t) = |t + dm| < |t - dp| in Float (the reference's strict first-minimum between the two walls of a
-// pair, Main.hs:1371-1372 under minimumBy), as a threshold in t: |t + dm| does not decrease and |t - dp| does not increase while t
-// runs from -dm to dp, so P flips exactly once there.  The flip point is found by bisection over the Float number line with the
-// very operations the kernel executes (this file is compiled without contraction / fast-math).  Returns (a, k) such that
-// P(t) <=> fma(t, a, k) > 0: a = -+2^100, k = +-2^100 c are exact scalings, so the fused result has the exact sign of c - t.
-// Outside the pair's neighbourhood the equivalence holds while the walls' separation is not absorbed by rounding, i.e. for
-// |t| < 2^22 (dp + dm): eight million room sizes away from the room (DESIGN.md states the domain).
-static inline uint32_t f2ord(float f) { uint32_t u; std::memcpy(&u, &f, 4); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
-static inline float ord2f(uint32_t o) { const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; float f; std::memcpy(&f, &u, 4); return f; }
-static void side_threshold(float dp, float dm, float& a, float& k) {
-  a = 0.f; k = 0.f;  // degenerate pair (coinciding walls, non-finite offsets): both distances are equal, the + wall wins, P is never true
-  if (!std::isfinite(dp) || !std::isfinite(dm)) return;
-  auto P = [&](float t) {
-    volatile float sp = t - dp, sm = t + dm;
-    return std::fabs(sm) < std::fabs(sp);
-  };
-  const float two100 = 1.2676506002282294e30f;  // 2^100
-  const float tm = -dm;                         // the - wall sits at t = -dm, the + wall at t = dp
-  if (tm == dp) return;
-  // walk from the - wall (P true) to the + wall (P false), whichever way round they lie
-  uint32_t lo = f2ord(tm), hi = f2ord(dp);
-  const bool up = lo < hi;
-  if (!P(tm) || P(dp)) return;  // cannot happen for finite distinct walls; keep the safe answer
-  while ((up ? hi - lo : lo - hi) > 1u) {
-    const uint32_t mid = up ? lo + (hi - lo) / 2 : hi + (lo - hi) / 2;
-    if (P(ord2f(mid))) lo = mid; else hi = mid;
-  }
-  const float c = ord2f(hi);  // first t (coming from the - wall) for which P is false
-  if (up) { a = -two100; k = c * two100; }   // P(t) <=> t < c
-  else    { a = two100;  k = -c * two100; }  // P(t) <=> t > c
-}
-
 static void fill_cmd(EvalCmd& c, int r, const float pl[24]) {
   for (int j = 0; j < 3; ++j) {
     for (int k = 0; k < 3; ++k) c.c[r][3 * j + k] = pl[8 * j + k];
     c.c[r][9 + j] = pl[8 * j + 3];
     c.c[r][12 + j] = pl[8 * j + 7];
-    side_threshold(pl[8 * j + 3], pl[8 * j + 7], c.c[r][15 + j], c.c[r][18 + j]);
   }
-  c.c[r][21] = 1.f;
-  c.c[r][22] = c.c[r][23] = 0.f;
+  c.c[r][15] = 0.f;
 }
 
 int32_t launch_peer_allreduce(hs_ctx* ctx, double* d_buf, int count) {

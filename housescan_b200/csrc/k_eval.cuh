@@ -48,8 +48,8 @@ struct EvalPlan {  // device memory; fixed for a (cloud, room offsets, grid) tri
   int32_t room_blo[HS_MAX_ROOMS], room_nb[HS_MAX_ROOMS];  // blocks with points of the room: room_blo .. room_blo + room_nb - 1
 };
 
-constexpr int EV_CMD_F = 24;  // floats per room: 6 x 16 bytes
-struct EvalCmd {  // one evaluation's plane constants: per room n[3][3] (normals of the + walls), dp[3], dm[3], sa[3], sk[3] (side tests), 1.0f, pad
+constexpr int EV_CMD_F = 16;  // floats per room: one 64-byte line
+struct EvalCmd {  // one evaluation's plane constants: per room n[3][3] (normals of the + walls), dp[3], dm[3], pad
   float c[HS_MAX_ROOMS][EV_CMD_F];
 };
 
@@ -150,9 +150,7 @@ __device__ __forceinline__ void load_room_consts(RoomK& R, const float* c16) {
   for (int j = 0; j < 3; ++j) {
     R.n[j][0] = c16[3 * j]; R.n[j][1] = c16[3 * j + 1]; R.n[j][2] = c16[3 * j + 2];
     R.dp[j] = c16[9 + j]; R.dm[j] = c16[12 + j];
-    R.sa[j] = c16[15 + j]; R.sk[j] = c16[18 + j];
   }
-  R.one = c16[21];
 }
 
 // raw room sums -> record component L (= lane); raw value k lives on lane k of the calling warp, lanes >= EV_NRAW hold 0.
@@ -173,6 +171,11 @@ __device__ __forceinline__ double raw_to_record(double raw, int L) {
   const double vc = __shfl_sync(0xffffffffu, raw, ic), vd = __shfl_sync(0xffffffffu, raw, id);
   const double r = ((va - vb) - vc) - vd;
   return neg ? -r : r;
+}
+
+__device__ __forceinline__ void add_group(ChainsP& ch, const RoomK& R, const float4& q0, const float4& q1, const float4& q2) {
+  add_point(ch, R, q0.x, q0.y, q0.z); add_point(ch, R, q0.w, q1.x, q1.y);
+  add_point(ch, R, q1.z, q1.w, q2.x); add_point(ch, R, q2.y, q2.z, q2.w);
 }
 
 template <int NCONS, int STAGES, int GPT, int FLUSH_TILES, bool SESSION>
@@ -223,7 +226,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hp), "=r"(hstop) : "l"(&a.h_ctl->posted) : "memory");
       if (hp != seq) {
         const unsigned long long t_seen = peer_now_ns();
-        while (seq != hp) {  // copy the new commands host -> device ring (24 floats per room)
+        while (seq != hp) {  // copy the new commands host -> device ring (16 floats = one 64-byte line per room)
           if (lane == 0) a.h_times[2 * (seq % EV_QCAP)] = t_seen;
           const float4* src = reinterpret_cast<const float4*>(a.h_cmds[seq % EV_QCAP].c);
           float4* dst = reinterpret_cast<float4*>(a.d_cmds[seq % EV_QCAP].c);
@@ -445,9 +448,9 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       RoomK R;
       if (SESSION) {
         const float* c16 = a.d_cmds[e % EV_QCAP].c[r];
-        float t[22];
+        float t[15];
 #pragma unroll
-        for (int i = 0; i < 22; ++i) t[i] = __ldcg(c16 + i);
+        for (int i = 0; i < 15; ++i) t[i] = __ldcg(c16 + i);
         load_room_consts(R, t);
       } else {
         load_room_consts(R, cmd0.c[r]);
@@ -461,8 +464,8 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         // ragged head / tail points (at most 3 each): the same per-point block, one point per thread
         const int64_t head_end = gl * 4, tail_begin = gh * 4;
         const int64_t nh = head_end - lo, ntail = hi - tail_begin;
-        if (static_cast<int64_t>(threadIdx.x) < nh) { const int64_t i = lo + threadIdx.x; add_point_pred3(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
-        else if (threadIdx.x >= 32 && static_cast<int64_t>(threadIdx.x) - 32 < ntail) { const int64_t i = tail_begin + threadIdx.x - 32; add_point_pred3(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        if (static_cast<int64_t>(threadIdx.x) < nh) { const int64_t i = lo + threadIdx.x; add_point(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        else if (threadIdx.x >= 32 && static_cast<int64_t>(threadIdx.x) - 32 < ntail) { const int64_t i = tail_begin + threadIdx.x - 32; add_point(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
         const int64_t ngroups = gh - gl;
         const int nfull = static_cast<int>(ngroups / TILE_GROUPS);
         const int rem_groups = static_cast<int>(ngroups - static_cast<int64_t>(nfull) * TILE_GROUPS);
@@ -475,12 +478,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
           for (int g = 0; g < GPT; ++g) { q[g][0] = lds_v4(base + g * NCONS * 48); q[g][1] = lds_v4(base + g * NCONS * 48 + 16); q[g][2] = lds_v4(base + g * NCONS * 48 + 32); }
           mbar_arrive_s(empty_s + 8 * stage);  // the values are in registers: hand the slot back before the math
 #pragma unroll
-          for (int g = 0; g < GPT; ++g) {
-            add_point_pred3(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
-            add_point_pred3(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
-            add_point_pred3(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
-            add_point_pred3(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
-          }
+          for (int g = 0; g < GPT; ++g) add_group(ch, R, q[g][0], q[g][1], q[g][2]);
           npts += 4 * GPT;
           if (++stage == STAGES) { stage = 0; parity ^= 1u; }
           if (++since_flush == FLUSH_TILES) { flush_chains(ch, npts, dacc, lane); since_flush = 0; }
@@ -498,10 +496,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
 #pragma unroll
           for (int g = 0; g < GPT; ++g)
             if (g * NCONS + static_cast<int>(threadIdx.x) < rem_groups) {
-              add_point_pred3(ch, R, q[g][0].x, q[g][0].y, q[g][0].z);
-              add_point_pred3(ch, R, q[g][0].w, q[g][1].x, q[g][1].y);
-              add_point_pred3(ch, R, q[g][1].z, q[g][1].w, q[g][2].x);
-              add_point_pred3(ch, R, q[g][2].y, q[g][2].z, q[g][2].w);
+              add_group(ch, R, q[g][0], q[g][1], q[g][2]);
               npts += 4;
             }
           if (++stage == STAGES) { stage = 0; parity ^= 1u; }
@@ -509,7 +504,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         }
       } else {
         const int64_t i = lo + threadIdx.x;
-        if (i < hi) { add_point_pred3(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        if (i < hi) { add_point(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
       }
       flush_chains(ch, npts, dacc, lane);
       // ---- the block's sums of this segment: warp Doubles added in warp order by warp 0 and parked for the reducer; everybody

@@ -744,14 +744,16 @@ def test_eval_random_room_layouts(ctx):
 
 
 def test_eval_side_threshold_is_the_reference_comparison(ctx):
-    """The throughput kernel decides the side of a wall pair with one fused instruction on a host-computed threshold
-    (k_eval.cu side_threshold) instead of comparing the two distances.  Points packed within a few ulps of the mid-plane of the
-    pair that wins the assignment: the per-wall counts must be the reference's (strict `<`, ties keep the + wall), bit for bit."""
+    """Side of a wall pair (Main.hs:1371-1372 under minimumBy: strict `<`, ties keep the + wall): points packed within a few
+    ulps of the mid-plane of the pair that wins the assignment, walls also the wrong way round (negative dimension): the per-wall
+    counts must be the reference's, bit for bit."""
     rng = np.random.default_rng(77)
-    for trial in range(12):
+    for trial in range(15):
         j = trial % 3
         dims = np.array([5.0, 6.0, 7.0])
         dims[j] = rng.uniform(0.5, 1.5)  # axis j is the nearest pair for points around the centre
+        if trial >= 12:
+            dims[j] = -dims[j]  # an optimiser step may cross zero: the + wall then lies on the - side
         center = rng.normal(size=3) * (0.0 if trial < 3 else 2.0)
         quat = np.array([1.0, 0, 0, 0]) if trial < 6 else rng.normal(size=4)
         params = np.concatenate([center, dims, quat])
