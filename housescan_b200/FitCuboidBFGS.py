@@ -94,3 +94,30 @@ def fitCuboidToCloudBFGS(cloud, initial, max_iter=200, gtol=1e-6):
     plane (planes as makePlanesFromCuboid, Main.hs:1852-1874), objective and gradient reduced on the GPU.
     -> (params, f, iterations, evaluations)"""
     return cloud.ctx.fit_cuboid_cloud_bfgs(cloud, initial, max_iter, gtol)
+
+
+def bfgsMinimize(objective, x0, max_iter=200, gtol=1e-6):
+    """The library's BFGS (`hs_bfgs_minimize`) over a Python objective `x -> (f, grad)`: the identical optimiser that
+    fitCuboidToCloudBFGS runs over the GPU objective.  -> (x, f, iterations, evaluations)"""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n = x0.size
+    CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+    def cb(_user, xp, fp, gp):
+        try:
+            f, g = objective(np.ctypeslib.as_array(xp, shape=(n,)).copy())
+            fp[0] = float(f)
+            g = np.asarray(g, dtype=np.float64)
+            for i in range(n):
+                gp[i] = g[i]
+            return 0
+        except Exception:  # noqa: BLE001
+            return 1
+
+    cbk = CB(cb)
+    out = np.zeros(n, np.float64)
+    f, it, ev = C.c_double(), C.c_int32(), C.c_int32()
+    rc = L.load().hs_bfgs_minimize(C.cast(cbk, C.c_void_p), None, L.ptr(x0), n, max_iter, gtol, L.ptr(out), C.byref(f), C.byref(it), C.byref(ev))
+    if rc:
+        raise L.HsError(rc, "hs_bfgs_minimize")
+    return out, f.value, it.value, ev.value

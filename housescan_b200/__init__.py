@@ -12,7 +12,7 @@ from __future__ import annotations
 import os
 
 from ._lib import HS_NE, HS_PS, HS_REC, HsError, SO_PATH, load  # noqa: F401
-from .core import Cloud, Context, EvalSession, peer_group_local, cuboid_grad_from_sums, planes_from_cuboid, proj_to_string, proj_to_xf  # noqa: F401
+from .core import Cloud, Context, EvalSession, peer_group_local, write_ply_begin, write_ply_part_host, cuboid_grad_from_sums, planes_from_cuboid, proj_to_string, proj_to_xf  # noqa: F401
 
 _default_ctx = None
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "hs_eval_session_times": (i32, [vp, i64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hs_eval_session_stop": (i32, [vp]),
     "hs_eval_session_end": (i32, [vp]),
+    "hs_bfgs_minimize": (i32, [vp, vp, vp, i32, i32, f64, vp, C.POINTER(f64), C.POINTER(i32), C.POINTER(i32)]),
     "hs_cuboid_grad_from_sums": (i32, [vp, vp, C.POINTER(f64), vp, vp]),
     "hs_plane_sums": (i32, [vp, vp, vp, i32, vp, i32, vp]),
     "hs_scatter3x3": (i32, [vp, vp, vp, vp]),
@@ -68,6 +69,9 @@ SIGNATURES = {
     "hs_translate": (i32, [vp, vp, vp, vp]),
     "hs_mean_extent": (i32, [vp, vp, vp, C.POINTER(f32)]),
     "hs_write_ply": (i32, [vp, vp, vp, C.c_char_p]),
+    "hs_write_ply_begin": (i32, [C.c_char_p, i64, i32]),
+    "hs_write_ply_part": (i32, [vp, vp, vp, C.c_char_p, i64, i64]),
+    "hs_write_ply_part_host": (i32, [C.c_char_p, vp, vp, i64, i64, i64]),
     "hs_proj_to_string": (i32, [vp, C.c_char_p, i32]),
     "hs_proj_to_xf": (i32, [vp, C.c_char_p, i32]),
     "hs_cc_label": (i32, [vp, vp, vp, i64, u32, vp]),

@@ -289,6 +289,13 @@ class Context:
             raise ValueError("rgb must have one row per point")
         self._chk(self.lib.hs_write_ply(self.h, cloud.h, ptr(rgb_a), path.encode()))
 
+    def write_ply_part(self, cloud: Cloud, path: str, first: int, n_total: int, rgb=None):
+        """this rank's points [first, first + len(cloud)) of a file created by `write_ply_begin` (any rank order)"""
+        rgb_a = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3) if rgb is not None else None
+        if rgb_a is not None and rgb_a.shape[0] != len(cloud):
+            raise ValueError("rgb must have one row per point")
+        self._chk(self.lib.hs_write_ply_part(self.h, cloud.h, ptr(rgb_a), path.encode(), first, n_total))
+
     def write_pcd(self, cloud: Cloud, path: str, rgb=None):
         rgb_a = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3) if rgb is not None else None
         if rgb_a is not None and rgb_a.shape[0] != len(cloud):
@@ -356,6 +363,21 @@ class Context:
 
 
 # ---- host-only helpers (no device needed) -------------------------------------------------------------------
+def write_ply_begin(path: str, n_total: int, has_rgb: bool = False) -> None:
+    """create the .ply with its header at the final size (ONE caller, before any `write_ply_part`)"""
+    rc = L.load().hs_write_ply_begin(path.encode(), n_total, 1 if has_rgb else 0)
+    if rc:
+        raise HsError(rc, f"hs_write_ply_begin: cannot write {path}")
+
+
+def write_ply_part_host(path: str, xyz, first: int, n_total: int, rgb=None) -> None:
+    xyz = as_f32(xyz).reshape(-1, 3)
+    rgb_a = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3) if rgb is not None else None
+    rc = L.load().hs_write_ply_part_host(path.encode(), ptr(xyz), ptr(rgb_a), first, xyz.shape[0], n_total)
+    if rc:
+        raise HsError(rc, f"hs_write_ply_part_host: cannot write {path}")
+
+
 def planes_from_cuboid(params) -> np.ndarray:
     out = np.empty((6, 4), np.float32)
     rc = L.load().hs_planes_from_cuboid(ptr(as_f64(params, (10,))), ptr(out))

@@ -6,6 +6,9 @@
 #include <exception>
 #include <vector>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include "../host/hs_host.hpp"
 #include "hs_internal.cuh"
 #include "k_peer.cuh"
@@ -586,6 +589,55 @@ int32_t hs_write_ply(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb, con
   if (!hs::write_ply(path, host.data(), rgb, cloud->n, &err)) { ctx->err = err; return HS_EIO; }
   return HS_OK;
 }
+// Sharded full-resolution export (Main.hs:1716-1730 transforms a room's cloud, README.md:16 step 4 exports
+// it): every rank transforms its point range on its own GPU and writes its part of ONE file.  hs_write_ply_begin (one caller)
+// creates the file with the header at its final size; after that any number of hs_write_ply_part calls - different ranks,
+// processes, any order - fill in the body.  The device -> host copy runs in two pinned halves so that the copy of one chunk
+// overlaps the write of the previous one.  The file is byte-identical to hs_write_ply's.
+int32_t hs_write_ply_begin(const char* path, int64_t n_total, int32_t has_rgb) {
+  if (!path || n_total < 0) return HS_EINVAL;
+  std::string err;
+  return hs::write_ply_begin(path, n_total, has_rgb != 0, &err) ? HS_OK : HS_EIO;
+}
+int32_t hs_write_ply_part_host(const char* path, const float* xyz, const uint8_t* rgb, int64_t first, int64_t n, int64_t n_total) {
+  if (!path || (!xyz && n > 0) || first < 0 || n < 0 || first + n > n_total) return HS_EINVAL;
+  const int fd = open(path, O_WRONLY);
+  if (fd < 0) return HS_EIO;
+  std::string err;
+  const bool ok = hs::write_ply_part(fd, xyz, rgb, first, n, n_total, &err);
+  return (close(fd) == 0 && ok) ? HS_OK : HS_EIO;
+}
+int32_t hs_write_ply_part(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb, const char* path, int64_t first, int64_t n_total) {
+  HS_LOCK(ctx);
+  if (!cloud || !path || first < 0 || first + cloud->n > n_total) HS_FAIL(ctx, HS_EINVAL, "hs_write_ply_part: need 0 <= first and first + n <= n_total");
+  const int fd = open(path, O_WRONLY);
+  if (fd < 0) HS_FAIL(ctx, HS_EIO, std::string("hs_write_ply_part: cannot open ") + path + " (hs_write_ply_begin first)");
+  const int64_t CH = 1 << 20;  // points per chunk: 12 MB
+  int32_t rc = hs_ensure_pinned(ctx, static_cast<size_t>(2 * CH) * 12);
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (rc == HS_OK && (cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess)) { ctx->err = "cudaEventCreate failed"; rc = HS_ECUDA; }
+  std::string err;
+  float* half[2] = {reinterpret_cast<float*>(ctx->h_pinned), reinterpret_cast<float*>(ctx->h_pinned) + 3 * CH};
+  const int64_t nchunks = (cloud->n + CH - 1) / CH;
+  auto issue = [&](int64_t c) {
+    const int64_t i0 = c * CH, m = std::min(CH, cloud->n - i0);
+    if (cudaMemcpyAsync(half[c & 1], cloud->d + 3 * i0, static_cast<size_t>(m) * 12, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaEventRecord(ev[c & 1], ctx->stream) != cudaSuccess) { ctx->err = "hs_write_ply_part: device -> host copy failed"; return false; }
+    return true;
+  };
+  if (rc == HS_OK && nchunks > 0 && !issue(0)) rc = HS_ECUDA;
+  for (int64_t c = 0; c < nchunks && rc == HS_OK; ++c) {
+    if (c + 1 < nchunks && !issue(c + 1)) { rc = HS_ECUDA; break; }
+    if (cudaEventSynchronize(ev[c & 1]) != cudaSuccess) { ctx->err = "hs_write_ply_part: device -> host copy failed"; rc = HS_ECUDA; break; }
+    const int64_t i0 = c * CH, m = std::min(CH, cloud->n - i0);
+    if (!hs::write_ply_part(fd, half[c & 1], rgb ? rgb + 3 * i0 : nullptr, first + i0, m, n_total, &err)) { ctx->err = err; rc = HS_EIO; }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& e : ev) if (e) cudaEventDestroy(e);
+  if (close(fd) != 0 && rc == HS_OK) { ctx->err = "hs_write_ply_part: close failed"; rc = HS_EIO; }
+  return rc;
+}
+
 static int32_t put_string(const std::string& s, char* buf, int32_t buflen) {
   if (!buf || buflen <= static_cast<int32_t>(s.size())) return HS_EINVAL;
   std::memcpy(buf, s.c_str(), s.size() + 1);
@@ -1027,6 +1079,19 @@ int32_t hs_fit_cuboid_cloud_bfgs(hs_ctx* ctx, const hs_cloud* cloud, const doubl
   }
   if (!r.ok) return last_rc != HS_OK ? last_rc : HS_ECUDA;
   for (int i = 0; i < 10; ++i) params_out[i] = r.x[i];
+  if (f_out) *f_out = r.f;
+  if (iters) *iters = r.iters;
+  if (evals) *evals = r.evals;
+  return HS_OK;
+}
+
+int32_t hs_bfgs_minimize(hs_objective_fn eval, void* user, const double* x0, int32_t n, int32_t max_iter, double gtol, double* x_out, double* f_out,
+                         int32_t* iters, int32_t* evals) {
+  if (!eval || !x0 || !x_out || n < 1 || n > 4096) return HS_EINVAL;
+  auto fn = [&](const double* x, double* f, double* g) { return eval(user, x, f, g) == 0; };
+  hs::BFGSResult r = hs::bfgs(fn, x0, n, max_iter > 0 ? max_iter : 200, gtol > 0 ? gtol : 1e-6);
+  if (!r.ok) return HS_EINVAL;
+  for (int i = 0; i < n; ++i) x_out[i] = r.x[i];
   if (f_out) *f_out = r.f;
   if (iters) *iters = r.iters;
   if (evals) *evals = r.evals;

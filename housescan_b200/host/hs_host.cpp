@@ -5,6 +5,9 @@
 // optimisers, <=25-node solves and formatters that the reference also runs on the host.
 #include "hs_host.hpp"
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -472,30 +475,63 @@ std::string proj_to_xf(const float m[16]) {
 }
 
 // binary little-endian PLY
-bool write_ply(const char* path, const float* xyz, const uint8_t* rgb, int64_t n, std::string* err) {
+std::string ply_header(int64_t n, bool rgb) {
+  std::string h = "ply\nformat binary_little_endian 1.0\ncomment housescan_b200 full-resolution export\nelement vertex " + std::to_string(static_cast<long long>(n)) +
+                  "\nproperty float x\nproperty float y\nproperty float z\n";
+  if (rgb) h += "property uchar red\nproperty uchar green\nproperty uchar blue\n";
+  h += "end_header\n";
+  return h;
+}
+
+// header + a file of the final size: the body is filled in by write_ply_part, in any order, by any number of writers
+bool write_ply_begin(const char* path, int64_t n, bool rgb, std::string* err) {
   FILE* fp = std::fopen(path, "wb");
   if (!fp) { *err = std::string("cannot open ") + path; return false; }
-  std::fprintf(fp, "ply\nformat binary_little_endian 1.0\ncomment housescan_b200 full-resolution export\nelement vertex %lld\n"
-                   "property float x\nproperty float y\nproperty float z\n", static_cast<long long>(n));
-  if (rgb) std::fprintf(fp, "property uchar red\nproperty uchar green\nproperty uchar blue\n");
-  std::fprintf(fp, "end_header\n");
-  bool ok = true;
-  if (!rgb) ok = std::fwrite(xyz, 12, static_cast<size_t>(n), fp) == static_cast<size_t>(n);
-  else {
-    const size_t chunk = 1 << 16;
-    std::vector<uint8_t> buf(chunk * 15);
-    for (int64_t i0 = 0; i0 < n && ok; i0 += chunk) {
-      const size_t m = static_cast<size_t>(std::min<int64_t>(chunk, n - i0));
-      for (size_t i = 0; i < m; ++i) {
-        std::memcpy(&buf[i * 15], xyz + 3 * (i0 + i), 12);
-        std::memcpy(&buf[i * 15 + 12], rgb + 3 * (i0 + i), 3);
-      }
-      ok = std::fwrite(buf.data(), 15, m, fp) == m;
-    }
-  }
+  const std::string h = ply_header(n, rgb);
+  bool ok = std::fwrite(h.data(), 1, h.size(), fp) == h.size();
+  if (std::fflush(fp) != 0) ok = false;
+  if (ok && ftruncate(fileno(fp), static_cast<off_t>(h.size() + static_cast<size_t>(n) * (rgb ? 15 : 12))) != 0) ok = false;
   if (std::fclose(fp) != 0) ok = false;
   if (!ok) *err = std::string("short write to ") + path;
   return ok;
+}
+
+// points [first, first + m) of an n-point file (xyz / rgb point to the FIRST of the m points)
+bool write_ply_part(int fd, const float* xyz, const uint8_t* rgb, int64_t first, int64_t m, int64_t n, std::string* err) {
+  const size_t hdr = ply_header(n, rgb != nullptr).size();
+  auto put = [&](const void* p, size_t bytes, size_t at) {
+    const char* c = static_cast<const char*>(p);
+    while (bytes) {
+      const ssize_t w = pwrite(fd, c, bytes, static_cast<off_t>(at));
+      if (w <= 0) return false;
+      c += w; at += static_cast<size_t>(w); bytes -= static_cast<size_t>(w);
+    }
+    return true;
+  };
+  bool ok = true;
+  if (!rgb) ok = put(xyz, static_cast<size_t>(m) * 12, hdr + static_cast<size_t>(first) * 12);
+  else {
+    const size_t chunk = 1 << 16;
+    std::vector<uint8_t> buf(chunk * 15);
+    for (int64_t i0 = 0; i0 < m && ok; i0 += chunk) {
+      const size_t k = static_cast<size_t>(std::min<int64_t>(chunk, m - i0));
+      for (size_t i = 0; i < k; ++i) {
+        std::memcpy(&buf[i * 15], xyz + 3 * (i0 + i), 12);
+        std::memcpy(&buf[i * 15 + 12], rgb + 3 * (i0 + i), 3);
+      }
+      ok = put(buf.data(), k * 15, hdr + static_cast<size_t>(first + i0) * 15);
+    }
+  }
+  if (!ok) *err = "short write to the .ply body";
+  return ok;
+}
+
+bool write_ply(const char* path, const float* xyz, const uint8_t* rgb, int64_t n, std::string* err) {
+  if (!write_ply_begin(path, n, rgb != nullptr, err)) return false;
+  const int fd = open(path, O_WRONLY);
+  if (fd < 0) { *err = std::string("cannot open ") + path; return false; }
+  const bool ok = write_ply_part(fd, xyz, rgb, 0, n, n, err);
+  return (close(fd) == 0) && ok;
 }
 
 // GroupConnectedComponents regrouping from min-index vertex labels (GroupConnectedComponents.hs:46-54):

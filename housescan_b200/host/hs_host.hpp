@@ -54,6 +54,9 @@ std::string show_float(float x);
 std::string proj_to_string(const float m[16]);
 std::string proj_to_xf(const float m[16]);
 bool write_ply(const char* path, const float* xyz, const uint8_t* rgb, int64_t n, std::string* err);
+std::string ply_header(int64_t n, bool rgb);
+bool write_ply_begin(const char* path, int64_t n, bool rgb, std::string* err);
+bool write_ply_part(int fd, const float* xyz, const uint8_t* rgb, int64_t first, int64_t m, int64_t n, std::string* err);
 void group_edges_by_label(const uint32_t* src, const uint32_t* label, int64_t E, int32_t* comp_out, int64_t* order_out, int32_t* ncomp);
 
 

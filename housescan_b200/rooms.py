@@ -62,6 +62,31 @@ def depth_stream_records_sharded(reduce_fn, frames, poses, rank: int, world: int
     return out
 
 
+def export_room_ply_sharded(transform_fn, write_part_fn, path: str, n_total: int, rank: int, world: int, has_rgb: bool = False, group=None):
+    """Per-room rigid transform + full-resolution .ply export sharded by point range (the room's `roomProj`
+    of Main.hs:1716-1730 applied to the FULL-resolution cloud, README.md:16 step 4, Main.hs:2305-2313 delegates this to external
+    tools).  Rank r holds the points [lo, hi) = shard_range(n_total, r, world) of the room:
+        transform_fn(lo, hi)          -> this rank's transformed shard (on the GPU: Context.transform of its cloud)
+        write_part_fn(shard, lo)      -> writes it at its place in the file (Context.write_ply_part / write_ply_part_host)
+    Rank 0 creates the file with the header at its final size, a barrier publishes it, then every rank writes its own bytes: no
+    collective on the data path, and the file is byte-identical to the single-rank export.  Returns (lo, hi)."""
+    from .core import write_ply_begin
+
+    lo, hi = shard_range(n_total, rank, world)
+    if rank == 0:
+        write_ply_begin(path, n_total, has_rgb)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier(group=group)
+    write_part_fn(transform_fn(lo, hi), lo)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier(group=group)
+    return lo, hi
+
+
 X, Y, Z = 0, 1, 2
 SAME = ("Same",)
 

@@ -166,6 +166,14 @@ HS_API int32_t hs_mean_extent(hs_ctx* ctx, const hs_cloud* cloud, double mean[3]
 /* full-resolution export (README.md:16 step 4; replaces the external plyxform / pcl_transform_point_cloud of
  * Main.hs:2311-2313): binary little-endian PLY, float x y z [+ uchar red green blue]. */
 HS_API int32_t hs_write_ply(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb_or_null, const char* path);
+/* The same file written by several ranks (per-room transform + export sharded by point range;
+ * Main.hs:1716-1730, README.md:16): ONE caller creates the file with its header at the final size (begin), then every rank writes
+ * the points [first, first + n) it holds - any order, any process.  Byte-identical to hs_write_ply of the whole cloud. */
+HS_API int32_t hs_write_ply_begin(const char* path, int64_t n_total, int32_t has_rgb);
+HS_API int32_t hs_write_ply_part_host(const char* path, const float* xyz, const uint8_t* rgb_or_null, int64_t first, int64_t n,
+                                      int64_t n_total); /* the same for points that live in host memory */
+HS_API int32_t hs_write_ply_part(hs_ctx* ctx, const hs_cloud* cloud, const uint8_t* rgb_or_null, const char* path, int64_t first,
+                                 int64_t n_total);
 /* ---- room input formats: the step before the hot path (README.md:13-16) ----------------------- */
 /* planeEqsFromFile (Main.hs:1379-1389): PCL's planes.txt, one `a b c d` per line meaning ax + by + cz + d = 0; the result is
  * mkPlaneEqABCD a b c (-d).  Parsing stops at the first line that does not match (attoparsec parseOnly); no plane at all is
@@ -254,6 +262,12 @@ HS_API int32_t hs_fit_cuboid(const double corners[24], int32_t variant /*0 fitCu
 HS_API int32_t hs_fit_cuboid_cloud_bfgs(hs_ctx* ctx, const hs_cloud* cloud, const double init[10], int32_t max_iter,
                                         double gtol, double params_out[10], double* f_out, int32_t* iters,
                                         int32_t* evals);
+/* The same BFGS (host/hs_host.cpp) over a caller-supplied objective: eval(user, x, &f, g) returns 0 on success.  What a host
+ * program uses to minimise any of the records' objectives with its own chain rule (FitCuboidBFGS.hs:172-252 drives GSL the same
+ * way through hmatrix-gsl's callbacks), and what the parity tests use to run the identical optimiser over the oracle's objective. */
+typedef int32_t (*hs_objective_fn)(void* user, const double* x, double* f, double* grad);
+HS_API int32_t hs_bfgs_minimize(hs_objective_fn eval, void* user, const double* x0, int32_t n, int32_t max_iter, double gtol,
+                                double* x_out, double* f_out, int32_t* iters, int32_t* evals);
 /* TranslationOptimizer.lstSqDistancesI (TranslationOptimizer.hs:48-72) on bijected indices; HS_ESINGULAR => Nothing */
 HS_API int32_t hs_lstsq_distances(const int32_t* i_idx, const int32_t* j_idx, const double* d, int32_t m, int32_t n_nodes,
                                   double* pos_out, double* rmse_out);

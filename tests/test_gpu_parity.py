@@ -578,6 +578,25 @@ def test_bfgs_on_cloud_recovers_cuboid(ctx):
     assert min(np.linalg.norm(qa - qb), np.linalg.norm(qa + qb)) < 2e-3
 
 
+def test_bfgs_fit_matches_the_same_optimiser_over_the_oracle_objective(ctx):
+    """North-star bar: fitted cuboid parameters within 1e-6 relative of the reference's.  The reference side is the identical BFGS
+    (`hs_bfgs_minimize`) driven by the oracle's objective / gradient on the CPU; the product side drives the GPU session."""
+    from housescan_b200 import FitCuboidBFGS as F
+
+    true = np.concatenate([[0.4, -0.3, 3.5], [4.0, 2.5, 3.0], synth.quat_from_axis_angle([0.2, 1, 0.1], 12.0)])
+    xyz, _ = synth.cuboid_room_cloud(120_000, true, sigma=0.003, seed=22)
+    init = true + np.concatenate([[0.05, -0.04, 0.03], [0.08, -0.06, 0.05], 0.02 * np.array([1, -1, 1, -1])])
+    p_g, f_g, it_g, ev_g = ctx.fit_cuboid_cloud_bfgs(ctx.upload(xyz), init, 100, 1e-7)
+
+    def objective(x):
+        f, g, _, _ = O.cuboid_residual_grad(xyz, x)
+        return f, g
+
+    p_o, f_o, it_o, ev_o = F.bfgsMinimize(objective, init, 100, 1e-7)
+    assert abs(f_g - f_o) <= 1e-6 * f_o, (f_g, f_o)
+    assert np.max(np.abs(p_g - p_o) / np.maximum(np.abs(p_o), 1e-2)) < 1e-6, (p_g, p_o, it_g, it_o)
+
+
 # ------------------------------------------------------------------ six planes that are NOT a cuboid's antiparallel pairs
 def test_six_unpaired_planes_take_the_generic_path(ctx, room_small):
     """K == 6 picks the unrolled kernels; the shared-dot-product shortcut applies only when planes 2j / 2j+1 have exactly negated
@@ -768,3 +787,30 @@ def test_eval_side_threshold_is_the_reference_comparison(ctx):
         assert np.array_equal(rec[0, 16:22], ro[16:22]), (trial, rec[0, 16:22], ro[16:22])
         assert rec[0, 16 + 2 * j] > 1000 and rec[0, 17 + 2 * j] > 1000  # both sides populated: the threshold was exercised
         assert abs(rec[0, 0] - ro[0]) <= 1e-6 * ro[0]
+
+
+def test_sharded_transform_export_equals_single_export(ctx, tmp_path):
+    """SURVEY.md 8e row 3 on the GPU: three point-range shards of a room are transformed (`hs_transform`) and written with
+    `hs_write_ply_part` in reverse order into ONE file; byte-identical to `hs_write_ply` of the whole transformed cloud, and the
+    transformed points are the oracle's bit for bit."""
+    import housescan_b200 as hb
+    from housescan_b200.rooms import shard_range
+
+    rng = np.random.default_rng(12)
+    n = 2_500_003  # several pinned chunks per part
+    xyz = rng.normal(size=(n, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, size=(n, 3), dtype=np.uint8)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, :3] = synth.rot_rows_from_quat(synth.quat_from_axis_angle([0.3, 1.0, -0.2], 40.0)).astype(np.float32)
+    m[3, :3] = [1.5, -2.0, 0.25]
+    whole = ctx.transform(ctx.upload(xyz), m)
+    assert np.array_equal(whole.download().view(np.uint32), O.project_cloud(xyz, m).view(np.uint32))
+    for tag, colors in (("plain", None), ("rgb", rgb)):
+        single, parts = str(tmp_path / f"single_{tag}.ply"), str(tmp_path / f"parts_{tag}.ply")
+        ctx.write_ply(whole, single, colors)
+        hb.write_ply_begin(parts, n, colors is not None)
+        for rank in (2, 0, 1):
+            lo, hi = shard_range(n, rank, 3)
+            shard = ctx.transform(ctx.upload(xyz[lo:hi]), m)
+            ctx.write_ply_part(shard, parts, lo, n, None if colors is None else colors[lo:hi])
+        assert open(single, "rb").read() == open(parts, "rb").read()

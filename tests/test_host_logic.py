@@ -337,3 +337,21 @@ def test_auto_align_floor_and_corner_suggestions(built_lib):
     d = np.linalg.norm(sugg[:, None, :] - room.corners[None, :, :], axis=2)
     assert d.min(axis=1).max() < 1e-4  # the suggestions are the room's corners
     assert Room(_OracleEngine(), xyz, np.zeros((0, 4), np.float32)).autoAlignFloor() == "room has no planes"
+
+
+def test_bfgs_minimize_callback_entry_point(built_lib):
+    """`hs_bfgs_minimize`: the library's BFGS over a caller-supplied objective (quadratic with a known minimum; an objective that
+    fails is reported, not swallowed)."""
+    from housescan_b200 import FitCuboidBFGS as F
+    from housescan_b200 import HsError
+
+    A = np.diag([1.0, 4.0, 9.0, 0.5])
+    b = np.array([1.0, 2.0, 3.0, -1.0])
+    x, f, it, ev = F.bfgsMinimize(lambda x: (0.5 * x @ A @ x - b @ x, A @ x - b), np.zeros(4), 200, 1e-10)
+    assert np.allclose(x, np.linalg.solve(A, b), atol=1e-8) and it > 0 and ev >= it
+
+    def bad(x):
+        raise RuntimeError("objective failed")
+
+    with pytest.raises(HsError):
+        F.bfgsMinimize(bad, np.zeros(4))
