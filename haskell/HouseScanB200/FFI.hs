@@ -117,3 +117,16 @@ foreign import ccall unsafe "hs_proj_compose" c_proj_compose :: Ptr CFloat -> Pt
 foreign import ccall unsafe "hs_proj_translate" c_proj_translate :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
 foreign import ccall unsafe "hs_proj_rotate_around" c_proj_rotate_around :: Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> Ptr CFloat -> IO Int32
 foreign import ccall safe "hs_ply_info" c_ply_info :: CString -> Ptr Int64 -> Ptr Int32 -> Ptr Int32 -> IO Int32
+
+-- host-only mirrors used by the FitCuboidBFGS shim (FitCuboidBFGS.hs:51-131, :247-252)
+foreign import ccall unsafe "hs_cuboid_from_params" c_cuboid_from_params :: Ptr CDouble -> Ptr CDouble -> IO Int32
+foreign import ccall unsafe "hs_errfun"             c_errfun             :: Ptr CDouble -> Ptr CDouble -> IO CDouble
+foreign import ccall unsafe "hs_guess_dims"         c_guess_dims         :: Ptr CDouble -> Ptr CDouble -> IO Int32
+foreign import ccall unsafe "hs_cuboid_grad_from_sums"
+  c_cuboid_grad_from_sums :: Ptr CDouble -> Ptr CDouble -> Ptr CDouble -> Ptr CDouble -> Ptr Int64 -> IO Int32
+foreign import ccall unsafe "hs_planes_from_cuboid" c_planes_from_cuboid :: Ptr CDouble -> Ptr CFloat -> IO Int32
+foreign import ccall safe "hs_kth_smallest"         c_kth_smallest       :: Ptr HsCtx -> Ptr HsCloud -> Int32 -> Int64 -> Ptr CFloat -> IO Int32
+-- sharded full-resolution export (SURVEY.md 8e row 3)
+foreign import ccall safe "hs_write_ply_begin"     c_write_ply_begin     :: CString -> Int64 -> Int32 -> IO Int32
+foreign import ccall safe "hs_write_ply_part"      c_write_ply_part      :: Ptr HsCtx -> Ptr HsCloud -> Ptr Word8 -> CString -> Int64 -> Int64 -> IO Int32
+foreign import ccall safe "hs_write_ply_part_host" c_write_ply_part_host :: CString -> Ptr CFloat -> Ptr Word8 -> Int64 -> Int64 -> Int64 -> IO Int32

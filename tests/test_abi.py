@@ -80,3 +80,31 @@ def test_haskell_ffi_binds_only_declared_symbols():
     assert len(bound) >= 30
     declared = set(declared_symbols())
     assert not [b for b in bound if b not in declared]
+
+
+SHIMS = ["FitCuboidBFGS", "TranslationOptimizer", "GroupConnectedComponents", "VectorUtil", "HoniHelper"]
+
+
+def _export_list(src: str):
+    """names between `module X (` and `) where`, comments dropped, in order"""
+    m = re.search(r"^module\s+\w+\s*\((.*?)\)\s*where", src, re.S | re.M)
+    assert m, "no export list"
+    body = re.sub(r"--.*", "", m.group(1))
+    return [t.strip() for t in body.split(",") if t.strip()]
+
+
+@pytest.mark.parametrize("mod", SHIMS)
+def test_haskell_shim_keeps_the_reference_export_list(mod):
+    """haskell/<Module>.hs drops in for housescan/<Module>.hs: its export list starts with the reference's, name for name and in
+    the reference's order; what follows is additive.  Every c_* it calls is bound in HouseScanB200/FFI.hs."""
+    shim = open(os.path.join(ROOT, "haskell", mod + ".hs")).read()
+    ours = _export_list(shim)
+    ref_path = os.path.join("/root/reference/housescan", mod + ".hs")
+    if os.path.exists(ref_path):  # the reference is mounted in the build container only
+        theirs = _export_list(open(ref_path).read())
+        assert ours[: len(theirs)] == theirs, (mod, ours, theirs)
+    ffi = open(os.path.join(ROOT, "haskell", "HouseScanB200", "FFI.hs")).read()
+    bound = set(re.findall(r"\b(c_\w+)\s*::", ffi))
+    dev = open(os.path.join(ROOT, "haskell", "HouseScanB200", "Device.hs")).read()
+    used = set(re.findall(r"\b(c_\w+)\b", shim)) | set(re.findall(r"\b(c_\w+)\b", dev))
+    assert not (used - bound), (mod, sorted(used - bound))
