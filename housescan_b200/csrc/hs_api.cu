@@ -15,6 +15,23 @@
 
 static thread_local std::string g_create_err;
 
+// temporary device buffers of one call: freed on every path out of the scope (cudaFree waits for work that still uses them)
+struct DevTemps {
+  std::vector<void*> ptrs;
+  template <class T>
+  cudaError_t alloc(T** out, size_t bytes) {
+    void* p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = static_cast<T*>(p);
+    return e;
+  }
+  ~DevTemps() { for (void* p : ptrs) cudaFree(p); }
+  DevTemps() = default;
+  DevTemps(const DevTemps&) = delete;
+  DevTemps& operator=(const DevTemps&) = delete;
+};
+
 // Every entry point that touches the device goes through here: one in-flight call per ctx; an open evaluation session owns the
 // stream (anything enqueued behind its resident kernel would wait for hs_eval_session_end); and a peer exchange that timed out
 // in an earlier asynchronous call is reported by the next call as HS_ENCCL (the kernels raise the mapped status word).
@@ -221,10 +238,11 @@ int32_t hs_backproject_ref(hs_ctx* ctx, const uint16_t* depth, int32_t w, int32_
   uint16_t* d_depth = nullptr;
   uint8_t* d_mask = nullptr;
   int32_t rc = HS_OK;
+  DevTemps tmp;
   {
     HS_LOCK(ctx);
-    HS_CUDA_TRY(ctx, cudaMalloc(&d_depth, npx * 2 + 16));
-    if (mask_out) HS_CUDA_TRY(ctx, cudaMalloc(&d_mask, npx + 16));
+    HS_CUDA_TRY(ctx, tmp.alloc(&d_depth, npx * 2 + 16));
+    if (mask_out) HS_CUDA_TRY(ctx, tmp.alloc(&d_mask, npx + 16));
     rc = copy_h2d(ctx, d_depth, depth, npx * 2);
   }
   if (rc == HS_OK && xyz_out) rc = hs_cloud_alloc(ctx, npx, &cl);
@@ -234,7 +252,7 @@ int32_t hs_backproject_ref(hs_ctx* ctx, const uint16_t* depth, int32_t w, int32_
   if (rc == HS_OK && mask_out) { HS_LOCK(ctx); rc = copy_d2h_sync(ctx, mask_out, d_mask, npx); }
   if (n_valid) *n_valid = nv;
   if (cl) hs_cloud_free(ctx, cl);
-  { HS_LOCK(ctx); cudaStreamSynchronize(ctx->stream); cudaFree(d_depth); if (d_mask) cudaFree(d_mask); }
+  { HS_LOCK(ctx); cudaStreamSynchronize(ctx->stream); }
   return rc;
 }
 
@@ -275,16 +293,17 @@ int32_t hs_backproject_reduce6x6(hs_ctx* ctx, const uint16_t* frames, int64_t nf
   const size_t fbytes = static_cast<size_t>(nframes) * w * h * 2;
   uint16_t* d_frames = nullptr;
   double* d_out = nullptr;
+  DevTemps tmp;
   {
     HS_LOCK(ctx);
-    HS_CUDA_TRY(ctx, cudaMalloc(&d_frames, fbytes + 16));
-    HS_CUDA_TRY(ctx, cudaMalloc(&d_out, static_cast<size_t>(nframes) * HS_NE * sizeof(double)));
+    HS_CUDA_TRY(ctx, tmp.alloc(&d_frames, fbytes + 16));
+    HS_CUDA_TRY(ctx, tmp.alloc(&d_out, static_cast<size_t>(nframes) * HS_NE * sizeof(double)));
     if (int32_t rc = copy_h2d(ctx, d_frames, frames, fbytes)) return rc;
   }
   int32_t rc = hs_backproject_reduce6x6_dev(ctx, d_frames, nframes, w, h, intr, poses, planes, K, d_out);
   { HS_LOCK(ctx);
     if (rc == HS_OK) rc = copy_d2h_sync(ctx, out, d_out, static_cast<size_t>(nframes) * HS_NE * sizeof(double));
-    cudaStreamSynchronize(ctx->stream); cudaFree(d_frames); cudaFree(d_out); }
+    cudaStreamSynchronize(ctx->stream); }
   return rc;
 }
 
@@ -304,16 +323,17 @@ int32_t hs_plane_assign(hs_ctx* ctx, const hs_cloud* cloud, const float* planes,
   const int64_t n = cloud->n;
   uint8_t* d_a = nullptr;
   float* d_r = nullptr;
+  DevTemps tmp;
   {
     HS_LOCK(ctx);
-    if (assign_out) HS_CUDA_TRY(ctx, cudaMalloc(&d_a, n + 16));
-    if (resid_out) HS_CUDA_TRY(ctx, cudaMalloc(&d_r, n * 4 + 16));
+    if (assign_out) HS_CUDA_TRY(ctx, tmp.alloc(&d_a, n + 16));
+    if (resid_out) HS_CUDA_TRY(ctx, tmp.alloc(&d_r, n * 4 + 16));
   }
   int32_t rc = hs_plane_assign_dev(ctx, cloud, planes, K, d_a, d_r);
   { HS_LOCK(ctx);
     if (rc == HS_OK && assign_out && n) rc = copy_d2h_sync(ctx, assign_out, d_a, n);
     if (rc == HS_OK && resid_out && n) rc = copy_d2h_sync(ctx, resid_out, d_r, n * 4);
-    cudaStreamSynchronize(ctx->stream); if (d_a) cudaFree(d_a); if (d_r) cudaFree(d_r); }
+    cudaStreamSynchronize(ctx->stream); }
   return rc;
 }
 
@@ -453,11 +473,10 @@ int32_t hs_rooms_cuboid_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* 
   HS_LOCK(ctx);
   if (!rec_out || nrooms < 1) HS_FAIL(ctx, HS_EINVAL, "hs_rooms_cuboid_sums: bad arguments");
   double* d_out = ctx->d_small;
-  double* big = nullptr;
-  if (nrooms > HS_MAX_ROOMS) { HS_CUDA_TRY(ctx, cudaMalloc(&big, sizeof(double) * HS_REC * nrooms)); d_out = big; }
+  DevTemps tmp;  // more rooms than the ctx's resident record buffer holds (HS_MAX_ROOMS): a buffer for this call
+  if (nrooms > HS_MAX_ROOMS) HS_CUDA_TRY(ctx, tmp.alloc(&d_out, sizeof(double) * HS_REC * nrooms));
   int32_t rc = rooms_sums_enqueue(ctx, cloud, room_offsets, nrooms, params, d_out);
   if (rc == HS_OK) rc = copy_d2h_sync(ctx, rec_out, d_out, sizeof(double) * HS_REC * nrooms);
-  if (big) { cudaStreamSynchronize(ctx->stream); cudaFree(big); }
   return rc;
 }
 
@@ -481,11 +500,12 @@ int32_t hs_plane_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_of
   HS_LOCK(ctx);
   if (!cloud || !room_offsets || !planes || !out || nrooms < 1) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: bad arguments");
   if (room_offsets[0] < 0 || room_offsets[nrooms] > cloud->n) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: room offsets outside the cloud");
+  if (K < 1 || K > HS_MAX_PLANES) HS_FAIL(ctx, HS_EINVAL, "hs_plane_sums: need 1 <= K <= 8 planes per room");
   // one launch per room, all enqueued back to back; the K x HS_PS records land side by side and come back in ONE copy
   const size_t total = static_cast<size_t>(nrooms) * K * HS_PS;
   double* d_out = ctx->d_small;
-  double* big = nullptr;
-  if (total > static_cast<size_t>(HS_MAX_ROOMS) * HS_REC) { HS_CUDA_TRY(ctx, cudaMalloc(&big, total * sizeof(double))); d_out = big; }
+  DevTemps tmp;
+  if (total > static_cast<size_t>(HS_MAX_ROOMS) * HS_REC) HS_CUDA_TRY(ctx, tmp.alloc(&d_out, total * sizeof(double)));
   int32_t rc = HS_OK;
   HS_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, total * sizeof(double), ctx->stream));
   for (int r = 0; r < nrooms && rc == HS_OK; ++r) {
@@ -496,7 +516,6 @@ int32_t hs_plane_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_of
     rc = launch_plane_sums(ctx, cloud->d, room_offsets[r], room_offsets[r + 1], t, d_out + static_cast<size_t>(r) * K * HS_PS);
   }
   if (rc == HS_OK) rc = copy_d2h_sync(ctx, out, d_out, total * sizeof(double));
-  if (big) { cudaStreamSynchronize(ctx->stream); cudaFree(big); }
   return rc;
 }
 
@@ -659,12 +678,13 @@ int32_t hs_cc_label(hs_ctx* ctx, const uint32_t* src, const uint32_t* dst, int64
     if (src[e] >= N || dst[e] >= N) { ctx->err = "hs_cc_label: vertex id out of range (vertices must be contiguous, GroupConnectedComponents.hs:38)"; return HS_EINVAL; }
   if (N == 0) return HS_OK;
   uint32_t *d_s = nullptr, *d_d = nullptr, *d_l = nullptr;
+  DevTemps tmp;
   {
     HS_LOCK(ctx);
-    HS_CUDA_TRY(ctx, cudaMalloc(&d_l, static_cast<size_t>(N) * 4));
+    HS_CUDA_TRY(ctx, tmp.alloc(&d_l, static_cast<size_t>(N) * 4));
     if (E > 0) {
-      HS_CUDA_TRY(ctx, cudaMalloc(&d_s, static_cast<size_t>(E) * 4));
-      HS_CUDA_TRY(ctx, cudaMalloc(&d_d, static_cast<size_t>(E) * 4));
+      HS_CUDA_TRY(ctx, tmp.alloc(&d_s, static_cast<size_t>(E) * 4));
+      HS_CUDA_TRY(ctx, tmp.alloc(&d_d, static_cast<size_t>(E) * 4));
       if (int32_t rc = copy_h2d(ctx, d_s, src, static_cast<size_t>(E) * 4)) return rc;
       if (int32_t rc = copy_h2d(ctx, d_d, dst, static_cast<size_t>(E) * 4)) return rc;
     }
@@ -672,7 +692,7 @@ int32_t hs_cc_label(hs_ctx* ctx, const uint32_t* src, const uint32_t* dst, int64
   int32_t rc = hs_cc_label_dev(ctx, d_s, d_d, E, N, d_l);
   { HS_LOCK(ctx);
     if (rc == HS_OK) rc = copy_d2h_sync(ctx, label_out, d_l, static_cast<size_t>(N) * 4);
-    cudaStreamSynchronize(ctx->stream); cudaFree(d_l); if (d_s) cudaFree(d_s); if (d_d) cudaFree(d_d); }
+    cudaStreamSynchronize(ctx->stream); }
   return rc;
 }
 int32_t hs_group_cc(hs_ctx* ctx, const uint32_t* src, const uint32_t* dst, int64_t E, uint32_t N, int32_t* comp_out, int64_t* order_out, int32_t* ncomp_out) {
@@ -690,6 +710,7 @@ static int32_t kth_impl(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int64_
   if (!cloud || !out || axis < 0 || axis > 2) HS_FAIL(ctx, HS_EINVAL, "hs_kth: bad arguments");
   if (k < 1) HS_FAIL(ctx, HS_EINVAL, "kLargestBy: k must be >= 1 if the vector is not empty");   // VectorUtil.hs:13
   if (k > cloud->n) HS_FAIL(ctx, HS_EINVAL, "kLargestBy: k must bet be > length of the vector");  // VectorUtil.hs:14 (sic)
+  if (cloud->n >= (static_cast<int64_t>(1) << 32)) HS_FAIL(ctx, HS_EINVAL, "hs_kth: clouds of 2^32 points or more are not supported (32-bit histogram bins); select per shard with hs_kth_shard_pass");
   float* d_out = reinterpret_cast<float*>(ctx->d_small);
   if (int32_t rc = launch_kth(ctx, cloud->d, cloud->n, axis, k, largest, d_out)) return rc;
   return copy_d2h_sync(ctx, out, d_out, sizeof(float));
@@ -705,11 +726,11 @@ int32_t hs_kth_shard_pass(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, int3
   if (cloud->n >= (1ll << 32)) HS_FAIL(ctx, HS_EINVAL, "hs_kth_shard_pass: at most 2^32 - 1 points per shard");
   if (cloud->n == 0) { std::memset(hist_out, 0, sizeof(uint32_t) * 2048); return HS_OK; }  // an empty shard adds nothing
   uint32_t* d_buf = nullptr;
-  HS_CUDA_TRY(ctx, cudaMalloc(&d_buf, sizeof(uint32_t) * 2048));
+  DevTemps tmp;
+  HS_CUDA_TRY(ctx, tmp.alloc(&d_buf, sizeof(uint32_t) * 2048));
   int32_t rc = launch_kth_shard_pass(ctx, cloud->d, cloud->n, axis, pass, prefix, mask, d_buf);
   if (rc == HS_OK) rc = copy_d2h_sync(ctx, hist_out, d_buf, sizeof(uint32_t) * 2048);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_buf);
   return rc;
 }
 uint32_t hs_kth_key_of_float(float v) { uint32_t b; std::memcpy(&b, &v, 4); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
@@ -720,6 +741,7 @@ static int32_t filter_impl(hs_ctx* ctx, const hs_cloud* cloud, int32_t axis, flo
   if (out->cap < cloud->n || out->d == cloud->d) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: output cloud too small or aliases the input");
   if ((colors != nullptr) != (colors_out != nullptr)) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: colors in/out must both be given");
   if (colors && (colors->n != cloud->n || colors_out->cap < cloud->n)) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: colors must be same size as the cloud");  // Main.hs:114
+  if (cloud->n >= (static_cast<int64_t>(1) << 32)) HS_FAIL(ctx, HS_EINVAL, "hs_filter_le: clouds of 2^32 points or more are not supported (32-bit compaction offsets); filter per shard");
   int64_t* d_n = reinterpret_cast<int64_t*>(ctx->d_small);
   if (int32_t rc = launch_filter_le(ctx, cloud->d, cloud->n, axis, limit, colors ? colors->d : nullptr, out->d, colors_out ? colors_out->d : nullptr, d_n)) return rc;
   int64_t m = 0;

@@ -16,16 +16,19 @@
 
 namespace hs {
 
-// attoparsec `double`: optional sign, at least one decimal digit, optional `.digits`, optional `e[sign]digits`; a trailing '.'
-// or 'e' that is not followed by a number is not consumed.  Returns the number of characters consumed (0 = no parse).
+// attoparsec `double` (Data.Attoparsec.ByteString.Char8 `scientifically`): optional sign, at least one decimal digit, then a '.'
+// is consumed whenever it is there, followed by zero or more digits (`anyWord8 *> takeWhile isDigit`: "1." parses as 1), then an
+// optional `e[sign]digits`; an 'e' that is not followed by a number is not consumed (the alternative backtracks).
+// Returns the number of characters consumed (0 = no parse).
 static size_t parse_double(const char* s, size_t len, double* out) {
   size_t i = 0;
   if (i < len && (s[i] == '-' || s[i] == '+')) ++i;
   const size_t d0 = i;
   while (i < len && s[i] >= '0' && s[i] <= '9') ++i;
   if (i == d0) return 0;
-  if (i + 1 < len && s[i] == '.' && s[i + 1] >= '0' && s[i + 1] <= '9') {
-    ++i;
+  size_t dot = std::string::npos;
+  if (i < len && s[i] == '.') {
+    dot = i++;
     while (i < len && s[i] >= '0' && s[i] <= '9') ++i;
   }
   if (i < len && (s[i] == 'e' || s[i] == 'E')) {
@@ -35,7 +38,8 @@ static size_t parse_double(const char* s, size_t len, double* out) {
     while (j < len && s[j] >= '0' && s[j] <= '9') ++j;
     if (j > e0) i = j;
   }
-  const std::string tok(s, i);
+  std::string tok(s, i);
+  if (dot != std::string::npos && (dot + 1 == tok.size() || tok[dot + 1] < '0' || tok[dot + 1] > '9')) tok.insert(dot + 1, "0");  // "1." / "1.e5" for strtod
   *out = std::strtod(tok.c_str(), nullptr);  // correctly rounded; attoparsec's own conversion may differ in the last Double
   return i;                                  // digit, which realToFrac :: Double -> Float hides (parity unpinned there)
 }
@@ -173,7 +177,10 @@ bool pcd_parse_header(const char* buf, size_t len, PcdHeader* h, std::string* er
   if (nf == 0 || h->size.size() != nf || h->type.size() != nf) { *err = "PCD: FIELDS / SIZE / TYPE do not match"; return false; }
   if (h->count.empty()) h->count.assign(nf, 1);
   if (h->count.size() != nf) { *err = "PCD: COUNT does not match FIELDS"; return false; }
-  if (h->points < 0) h->points = h->width * h->height;
+  if (h->points < 0) {
+    if (h->width < 0 || h->height < 0 || (h->height > 0 && h->width > static_cast<int64_t>(len) / h->height)) { *err = "PCD: WIDTH x HEIGHT exceeds the file size"; return false; }
+    h->points = h->width * h->height;  // cannot overflow: the product is <= the file length
+  }
   if (h->points < 0) { *err = "PCD: no POINTS / WIDTH x HEIGHT"; return false; }
   if (static_cast<uint64_t>(h->points) > len) { *err = "PCD: POINTS exceeds the file size"; return false; }  // every point takes >= 1 byte
   h->field_offset.resize(nf);

@@ -623,7 +623,10 @@ def diagonal_pairs(n):
 # numbers follow attoparsec's documented `double` grammar; parity unpinned by reference fixtures (the reference ships none).
 import re as _re
 
-_ATTO_DOUBLE = _re.compile(rb"[+-]?[0-9]+(?:\.[0-9]+)?(?:[eE][+-]?[0-9]+)?")
+# attoparsec >= 0.11 (`scientifically`: after the integer part a '.' is consumed whenever present, `anyWord8 *> takeWhile isDigit`,
+# so "1." is 1); housescan.cabal:31 only asks for >= 0.10.4.0, whose `floaty` backtracked over a dot without digits - a build
+# today resolves to the newer grammar, which is the one restated here.
+_ATTO_DOUBLE = _re.compile(rb"[+-]?[0-9]+(?:\.[0-9]*)?(?:[eE][+-]?[0-9]+)?")
 _ATTO_SPACE = _re.compile(rb"[ \t\n\v\f\r]*")
 
 
@@ -638,7 +641,10 @@ def plane_eqs_from_text(text):
             if not m:
                 ok = False
                 break
-            vals.append(float(m.group()))
+            tok = m.group()
+            if b"." in tok and not tok.split(b".")[1][:1].isdigit():
+                tok = tok.replace(b".", b".0", 1)  # "1." / "1.e5"
+            vals.append(float(tok))
             j = m.end()
             if c < 3:
                 j = _ATTO_SPACE.match(text, j).end()

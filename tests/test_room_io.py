@@ -22,7 +22,8 @@ PLANE_TEXTS = [
     "1 0 0 2\n 0 1 0 3\n",                                       # next line starts with a blank: stops after one plane
     "1\n0\n0\n5\n0 0 1 7",                                       # skipSpace between a b c d spans newlines
     "1 0 0 2\n\n0 1 0 3\n",                                      # empty line: stops
-    "1. 0 0 2\n",                                                # `1.` is not consumed as a number: no plane at all -> error
+    "1. 0 0 2\n",                                                # attoparsec >= 0.11: the dot is consumed, `1.` is 1 -> one plane
+    "1.e1 0. 0 2.\n3 4 5 6\n",                                   # dot without digits before an exponent / at the end of a line
     ".5 0 0 2\n",                                                # needs a leading digit: error
     "",                                                          # error
     "2 0 0 1e400\n",                                             # overflow to inf
@@ -84,6 +85,14 @@ def ctx():
     c = hb.Context(0)
     yield c
     c.close()
+
+
+def test_pcd_width_height_overflow_is_rejected(built_lib, tmp_path):
+    """WIDTH x HEIGHT that overflows int64 (or merely exceeds the file) is an error, not a 0-point cloud"""
+    bad = tmp_path / "overflow.pcd"
+    bad.write_bytes(b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 4611686018427387904\nHEIGHT 4\nDATA binary\n" + b"\0" * 48)
+    with pytest.raises(hb.HsError):
+        RoomIO.pcdInfo(str(bad))
 
 
 @pytest.mark.gpu
