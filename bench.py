@@ -234,6 +234,12 @@ def main():
     ap.add_argument("--mode", type=int, default=-1, help="evaluation kernel variant (hs_ctx_set_mode key 0)")
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5_stream", "c4_cc", "c2_export"],
+                    help="c3 (default, the headline line): 12-room apartment evaluation; the others are the remaining sharded rows of SURVEY.md 8e (tools/bench_workloads.py)")
+    ap.add_argument("--frames", type=int, default=10_000, help="c5_stream: frames of the replayed stream")
+    ap.add_argument("--storeys", type=int, default=50, help="c4_cc: storeys of 1000 x 1000 vertices")
+    ap.add_argument("--points", type=int, default=8_000_000, help="c2_export: points of the room")
+    ap.add_argument("--out-dir", default="", help="c2_export: directory of the .ply (default: the system temp dir)")
     ap.add_argument("--path", default="session", choices=["session", "launch"],
                     help="session = one resident kernel runs all K evaluations (hs_eval_session_*); launch = one kernel launch per evaluation")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
@@ -247,6 +253,12 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload != "c3":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_workloads
+
+        bench_workloads.WORKLOADS[args.workload](args)
+        return
 
     import torch
     import torch.distributed as dist

@@ -213,7 +213,9 @@ class Room:
     def suggestPoints(self, cutoff_factor=1.2):
         """Main.suggestPoints (Main.hs:1521-1538): corners of every plane triple p < q < s (planeCorner), kept when they lie within
         cutoffFactor x (largest distance of a cloud point from the room mean) of the room mean.  Mean and extent are the GPU
-        reductions of hs_mean_extent.  Returns (kept corners [m, 3], number of triples)."""
+        reductions of hs_mean_extent.  The reference filters `p < q, q < s` on the planes' Ord instance (their ids): `self.planes`
+        is kept in ascending plane-id order (loadRoom / addPlane append with fresh, growing ids), which makes the index triples
+        i < j < k the same enumeration in the same order.  Returns (kept corners [m, 3], number of triples)."""
         mean, maxdist = self.engine.mean_extent(self.cloud)
         m = np.asarray(mean, np.float64).astype(np.float32)
         cutoff = np.float32(np.float32(cutoff_factor) * np.float32(maxdist))

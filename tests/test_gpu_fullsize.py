@@ -151,8 +151,10 @@ def test_c3_apartment_records_100m(ctx, dev):
     assert np.array_equal(r0, rec) and np.array_equal(r2, rec) and not np.array_equal(r1, rec)
 
 
-def test_c4_components_20m(ctx, dev):
-    P, S = 20, 1000
+def test_c4_components_50m(ctx, dev):
+    """BASELINE configs[3] at its full size: 50 M plane-inlier vertices (50 storeys of 1000 x 1000), ~97 M edges; canonical min-index
+    labels bit-exact against the oracle's union-find"""
+    P, S = 50, 1000
     N = P * S * S
     g = torch.Generator(device=dev)
     g.manual_seed(4)
@@ -162,6 +164,7 @@ def test_c4_components_20m(ctx, dev):
     e = e[:, torch.rand(e.shape[1], device=dev, generator=g) >= 0.03]
     src, dst = e[0].to(torch.int32).contiguous(), e[1].to(torch.int32).contiguous()
     E = src.numel()
+    del e, vid
     lab = torch.empty(N, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()  # torch built the edge list on its stream; the library reads it on its own
     ctx._chk(ctx.lib.hs_cc_label_dev(ctx.h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), E, N, C.c_void_p(lab.data_ptr())))
@@ -209,3 +212,32 @@ def test_c5_depth_stream_200_frames(ctx, dev):
     assert torch.equal(r[:8].repeat(nf // 8, 1), r)                       # replayed frames: bit-identical records whoever computed them
     host = ctx.backproject_reduce6x6(base[:2], w, h, planes, intr=intr)   # host-buffer entry point, same records
     assert np.array_equal(host, r[:2].cpu().numpy())
+
+
+def test_c5_depth_stream_10k_frames_fused(ctx, dev):
+    """BASELINE configs[4] at its full size: 10 000 640x480 frames (6.1 GB of depth) through the fused back-projection + 6x6
+    reduction; the frames never exist as point clouds.  Per-frame pixel counts exact, replayed frames give bit-identical records,
+    and the first frames equal the oracle's records."""
+    import housescan_b200 as hb
+    import oracle as O
+    from housescan_b200 import synth
+    from housescan_b200._lib import ptr
+
+    w, h, nf = 640, 480, 10_000
+    base, _ = synth.depth_stream(8, w, h)
+    frames = torch.from_numpy(base.astype(np.int32)).to(dev).to(torch.int16).repeat(nf // 8, 1, 1).contiguous()
+    planes = hb.planes_from_cuboid(synth.C1_PARAMS)
+    intr = np.array(synth.KINFU_INTR, np.float32)
+    rec = torch.empty(nf * hb.HS_NE, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    ctx._chk(ctx.lib.hs_backproject_reduce6x6_dev(ctx.h, C.c_void_p(frames.data_ptr()), nf, w, h, ptr(intr), None, ptr(planes), 6, C.c_void_p(rec.data_ptr())))
+    torch.cuda.synchronize()
+    r = rec.view(nf, hb.HS_NE)
+    counts = torch.cat([(frames[i : i + 1000] != 0).view(-1, w * h).sum(dim=1) for i in range(0, nf, 1000)])
+    assert torch.equal(r[:, 28].long(), counts)
+    assert torch.equal(r[:8].repeat(nf // 8, 1), r)
+    ro = O.backproject_reduce6x6(base, w, h, planes, intr=intr)
+    got = r[:8].cpu().numpy()
+    assert np.array_equal(got[:, 28], ro[:, 28])
+    scale = np.abs(ro).max(axis=1, keepdims=True)
+    assert np.max(np.abs(got - ro) / scale) < 1e-6
