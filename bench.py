@@ -234,11 +234,11 @@ def main():
     ap.add_argument("--mode", type=int, default=-1, help="evaluation kernel variant (hs_ctx_set_mode key 0)")
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c5_stream", "c4_cc", "c2_export"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5_stream", "c4_cc", "c2_export", "a12_ceiling"],
                     help="c3 (default, the headline line): 12-room apartment evaluation; the others are the remaining sharded rows of SURVEY.md 8e (tools/bench_workloads.py)")
     ap.add_argument("--frames", type=int, default=10_000, help="c5_stream: frames of the replayed stream")
     ap.add_argument("--storeys", type=int, default=50, help="c4_cc: storeys of 1000 x 1000 vertices")
-    ap.add_argument("--points", type=int, default=8_000_000, help="c2_export: points of the room")
+    ap.add_argument("--points", type=int, default=8_000_000, help="c2_export / a12_ceiling: points of the room")
     ap.add_argument("--out-dir", default="", help="c2_export: directory of the .ply (default: the system temp dir)")
     ap.add_argument("--path", default="session", choices=["session", "launch"],
                     help="session = one resident kernel runs all K evaluations (hs_eval_session_*); launch = one kernel launch per evaluation")

@@ -385,32 +385,36 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       const double* lrec = a.local_rec + static_cast<size_t>(e % EV_D) * (HS_MAX_ROOMS * HS_REC);
       double* dst = SESSION ? a.out + static_cast<size_t>(e % EV_QCAP) * count : a.out;
       bool ok = true;
-      if (a.px.world > 1) peer_push_warp(a.px, a.epoch0 + e, lrec, count);
-      if (SESSION) {  // in-order commit: results and done counters advance evaluation by evaluation
+      // the exchange of evaluation e depends on the peers only: it runs while earlier evaluations are still being finalised by
+      // other blocks; only the publication below is in order
+      if (a.px.world > 1) {
+        peer_push_warp(a.px, a.epoch0 + e, lrec, count);
+        ok = peer_collect_warp(a.px, a.epoch0 + e, dst, count);
+      } else {
+        for (int i = lane; i < count; i += 32) dst[i] = __ldcg(lrec + i);
+      }
+      if (SESSION) {
+        double* hdst = a.h_results + static_cast<size_t>(e % EV_QCAP) * count;
+        for (int i = lane; i < count; i += 32) hdst[i] = dst[i];  // each lane re-reads what it wrote itself
+        __threadfence_system();
+        __syncwarp();
+        // in-order commit: the done counters advance evaluation by evaluation
         const unsigned long long t0 = peer_now_ns();
         while (ld_acquire_u32(&a.ctl->done_seq) != e) {
           if (peer_now_ns() - t0 > 2 * PEER_TIMEOUT_NS) { ok = false; break; }
           __nanosleep(64);
         }
       }
-      if (a.px.world > 1) ok = peer_collect_warp(a.px, a.epoch0 + e, dst, count) && ok;
-      else for (int i = lane; i < count; i += 32) dst[i] = __ldcg(lrec + i);
       if (!ok && lane == 0) {
         a.ctl->error = 1u;
         if (a.h_status) st_sys_u32(a.h_status, static_cast<uint32_t>(HS_ENCCL));
         if (SESSION) st_sys_u32(&a.h_ctl->error, 1u);
       }
-      if (SESSION) {
-        double* hdst = a.h_results + static_cast<size_t>(e % EV_QCAP) * count;
-        for (int i = lane; i < count; i += 32) hdst[i] = dst[i];
+      if (SESSION && lane == 0) {
+        a.h_times[2 * (e % EV_QCAP) + 1] = peer_now_ns();
         __threadfence_system();
-        __syncwarp();
-        if (lane == 0) {
-          a.h_times[2 * (e % EV_QCAP) + 1] = peer_now_ns();
-          __threadfence_system();
-          st_sys_u32(&a.h_ctl->done, e + 1u);
-          st_release_u32(&a.ctl->done_seq, e + 1u);
-        }
+        st_sys_u32(&a.h_ctl->done, e + 1u);
+        st_release_u32(&a.ctl->done_seq, e + 1u);
       }
     }
     return;

@@ -30,13 +30,22 @@ __device__ __forceinline__ volatile uint32_t* peer_flag(unsigned long long mailb
   return reinterpret_cast<volatile uint32_t*>(reinterpret_cast<double*>(mailbox) + PEER_DATA_DOUBLES) + (static_cast<size_t>(slot) * HS_PEER_MAX + src) * PEER_FLAG_STRIDE;
 }
 
+constexpr int PEER_VPL = (static_cast<int>(PEER_SLOT_DOUBLES) + 31) / 32;  // record values per lane of the exchanging warp (24 for 32 rooms)
+
 // Step 1 (never blocks): this rank's record src[0..count) -> slot [epoch][rank] of every mailbox, then the flags.  One full warp.
+// The record is read ONCE into registers (all loads in flight together), then stored to every peer: posted NVLink stores, nothing
+// waits until the single system-scope fence in front of the flags.
 __device__ __forceinline__ void peer_push_warp(const PeerExchange& px, uint32_t epoch, const double* src, int count) {
   const int lane = static_cast<int>(threadIdx.x & 31);
   const uint32_t slot = epoch % PEER_SLOTS;
+  double v[PEER_VPL];
+#pragma unroll
+  for (int k = 0; k < PEER_VPL; ++k) v[k] = (lane + 32 * k < count) ? __ldcg(src + lane + 32 * k) : 0.0;
   for (int p = 0; p < px.world; ++p) {
     double* dst = peer_data(px.mailbox[p], slot, px.rank);
-    for (int i = lane; i < count; i += 32) dst[i] = __ldcg(src + i);
+#pragma unroll
+    for (int k = 0; k < PEER_VPL; ++k)
+      if (lane + 32 * k < count) dst[lane + 32 * k] = v[k];
   }
   __threadfence_system();
   __syncwarp();
@@ -47,7 +56,8 @@ __device__ __forceinline__ void peer_push_warp(const PeerExchange& px, uint32_t 
 }
 
 // Step 2: wait for every rank's record of this epoch in the local mailbox and add them in rank order into dst[0..count).
-// Returns false (and fills dst with NaN) when a peer did not show up within PEER_TIMEOUT_NS.  One full warp.
+// Returns false (and fills dst with NaN) when a peer did not show up within PEER_TIMEOUT_NS.  One full warp.  The HS_PEER_MAX
+// loads of a value are issued together (the slots of absent ranks are not read), then added in rank order: identical on every rank.
 __device__ __forceinline__ bool peer_collect_warp(const PeerExchange& px, uint32_t epoch, double* dst, int count) {
   const int lane = static_cast<int>(threadIdx.x & 31);
   const uint32_t slot = epoch % PEER_SLOTS;
@@ -62,9 +72,16 @@ __device__ __forceinline__ bool peer_collect_warp(const PeerExchange& px, uint32
     __threadfence_system();
   }
   ok = __all_sync(0xffffffffu, ok);
+  const double* base = peer_data(px.mailbox[px.rank], slot, 0);
   for (int i = lane; i < count; i += 32) {
+    double v[HS_PEER_MAX];
+#pragma unroll
+    for (int r = 0; r < HS_PEER_MAX; ++r)  // the peers wrote these lines over NVLink: read them from L2, never from a stale L1 line
+      v[r] = (r < px.world) ? __ldcv(base + static_cast<size_t>(r) * PEER_SLOT_DOUBLES + i) : 0.0;
     double s = 0.0;
-    for (int r = 0; r < px.world; ++r) s += *reinterpret_cast<const volatile double*>(peer_data(px.mailbox[px.rank], slot, r) + i);  // rank order: identical on every rank
+#pragma unroll
+    for (int r = 0; r < HS_PEER_MAX; ++r)
+      if (r < px.world) s += v[r];  // rank order
     dst[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
   }
   return ok;

@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def _setup(args):
+def _setup(args, backend="nccl"):
     import torch
     import torch.distributed as dist
 
@@ -38,7 +38,7 @@ def _setup(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group(backend, device_id=dev)
     ctx = hb.Context(local)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -268,4 +268,43 @@ def c2_export(args):
             pass
 
 
-WORKLOADS = {"c5_stream": c5_stream, "c4_cc": c4_cc, "c2_export": c2_export}
+# ------------------------------------------------------------------------------------------------------------------ a12
+def a12_ceiling(args):
+    """removeCeiling (Main.hs:2643-2664) over a cloud sharded by point range: the k-th largest y over all ranks (three radix passes,
+    three all-reduces of 2048 counters) + the order-preserving filter of every rank's own points"""
+    torch, dist, hb, ctx, dev, rank, world = _setup(args, backend="cpu:gloo,cuda:nccl")
+    import bench
+    from housescan_b200 import VectorUtil
+    from housescan_b200.rooms import shard_range
+
+    n = args.points
+    lo, hi = shard_range(n, rank, world)
+    n_loc = hi - lo
+    buf, pts = bench.gen_points_torch(torch, dev, bench.room_params(1), [n_loc], seed=70 + rank)
+    cloud = ctx.wrap(buf.data_ptr(), n_loc, keepalive=buf)
+    torch.cuda.synchronize()
+    last = {}
+
+    def step():
+        kept, _, y_limit, first = VectorUtil.removeCeilingSharded(cloud)
+        last["kept"], last["y"], last["first"] = len(kept), float(y_limit), first
+        kept.free()
+
+    ms = _time_steps(torch, dist, world, dev, step, args.warmup, args.steps)
+    per = ms / args.steps
+    kept_total = torch.tensor([float(last["kept"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(kept_total)
+    achieved = (24.0 * n_loc + 24.0 * n_loc) / (per * 1e-3) / 1e9  # k-th: 24 B/point physical; filter: 12 in (x2 passes or 1) + 12 out x 0.8
+    _emit(rank, world, dist, {
+        "metric": "remove_ceiling_points_per_sec", "value": n * args.steps / (ms * 1e-3), "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 keys", "data": "synthetic",
+        "config": {"workload": "removeCeiling: k-th largest y (k = n/5) + order-preserving filter", "points": n, "sharding": f"point-range x{world}",
+                   "collective": "none" if world == 1 else "3 all-reduces of 2048 counters (gloo, host histograms) + 1 all-gather of kept counts", "y_limit": last["y"],
+                   "kept_fraction": float(kept_total.item()) / n},
+        "gpu_launches": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": _peak(), "unit": "GB/s", "frac": achieved / _peak(), "traffic": None, "bytes_per_point": 48.0,
+                     "kernel": "k_sel2_first/next + k_filter_onepass (host round trips between the radix passes included)"}})
+
+
+WORKLOADS = {"c5_stream": c5_stream, "c4_cc": c4_cc, "c2_export": c2_export, "a12_ceiling": a12_ceiling}
