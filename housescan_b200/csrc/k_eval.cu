@@ -6,7 +6,10 @@
 #include <cmath>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <new>
 #include <thread>
 
@@ -20,8 +23,7 @@ constexpr int EVK_NCONS = 384, EVK_STAGES = 3, EVK_GPT = 4, EVK_FLUSH = 16;
 constexpr int EVK_SEG_COST_DEFAULT = 768;  // an extra room segment in a block costs about this many 4-point groups (flush + block sum)
 
 constexpr size_t eval_smem_bytes() {
-  return static_cast<size_t>(EVK_STAGES) * EVK_GPT * EVK_NCONS * 48 + 2 * EVK_STAGES * 8 + static_cast<size_t>(2) * (EVK_NCONS / 32) * EV_NRAW * 8 +
-         static_cast<size_t>(EV_PARK) * EV_NRAW * 8;
+  return static_cast<size_t>(EVK_STAGES) * EVK_GPT * EVK_NCONS * 48 + 2 * EVK_STAGES * 8 + static_cast<size_t>(EV_WS) * (EVK_NCONS / 32) * EV_NRAW * 8;
 }
 
 // standalone exchange for the kernels that do not carry it in their tail (one warp)
@@ -63,6 +65,10 @@ struct hs_eval_session {
   double* d_results = nullptr;
   unsigned long long* h_times = nullptr;
   uint32_t posted = 0;
+  EvalArgs args;          // the resident kernel's arguments
+  unsigned long long* d_trace = nullptr;  // HS_EVAL_TRACE=<file>: per-block stamps of the first evaluations, written to <file> at end
+  int nblocks = 0;
+  bool launched = false;  // the kernel starts with the first post (its commands are in the ring before the kernel looks)
   bool stopped = false;
   bool empty = false;  // no point in any room: records are zero, no kernel runs
 };
@@ -183,13 +189,14 @@ static int32_t eval_prepare(hs_ctx* ctx, int64_t n, const int64_t* off, int nroo
   return HS_OK;
 }
 
-static void fill_cmd(EvalCmd& c, int r, const float pl[24]) {
+static void fill_cmd(EvalCmd& c, int r, const float pl[24], uint32_t seq = 0) {
   for (int j = 0; j < 3; ++j) {
     for (int k = 0; k < 3; ++k) c.c[r][3 * j + k] = pl[8 * j + k];
     c.c[r][9 + j] = pl[8 * j + 3];
     c.c[r][12 + j] = pl[8 * j + 7];
   }
-  c.c[r][15] = 0.f;
+  const uint32_t stamp = seq + 1u;  // the kernel's prefetch buffer is valid for evaluation seq iff it carries this stamp
+  std::memcpy(&c.c[r][15], &stamp, 4);
 }
 
 int32_t launch_peer_allreduce(hs_ctx* ctx, double* d_buf, int count) {
@@ -284,6 +291,27 @@ static int32_t session_spin(hs_eval_session* s, const char* who, Cond cond) {
   }
 }
 
+// The resident kernel is launched by the first post, right after the FIRST command has been written to the ring: the kernel finds
+// work the moment it starts, and the host converts and posts the remaining parameter sets while the device evaluates.
+static int32_t session_launch(hs_eval_session* s) {
+  if (s->launched || s->empty) return HS_OK;
+  hs_ctx* ctx = s->ctx;
+  hs_eval_state* st = ctx->eval;
+  auto kern = k_eval<EVK_NCONS, EVK_STAGES, EVK_GPT, EVK_FLUSH, true>;
+  if (!st->attr_set[1]) {
+    HS_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eval_smem_bytes())));
+    st->attr_set[1] = true;
+  }
+  HS_CUDA_TRY(ctx, cudaMemsetAsync(st->d_ctl, 0, sizeof(EvalCtl), ctx->stream));
+  EvalCmd none;
+  std::memset(&none, 0, sizeof none);
+  kern<<<s->nblocks, EVK_NCONS + 128, eval_smem_bytes(), ctx->stream>>>(s->args, none);
+  ctx->launches++;
+  HS_CUDA_TRY(ctx, cudaGetLastError());
+  s->launched = true;
+  return HS_OK;
+}
+
 extern "C" {
 
 int32_t hs_eval_session_begin(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, int32_t allreduce, hs_eval_session** out) {
@@ -311,7 +339,7 @@ int32_t hs_eval_session_begin(hs_ctx* ctx, const hs_cloud* cloud, const int64_t*
   std::memset(s->h_ctl, 0, 64);
   if (s->empty) std::memset(s->h_results, 0, rec_bytes * EV_QCAP);  // no kernel: every record is zero
   if (!s->empty) {
-    EvalArgs a;
+    EvalArgs& a = s->args;
     std::memset(&a, 0, sizeof a);
     a.xyz = cloud->d; a.plan = st->d_plan; a.ctl = st->d_ctl; a.partials = st->d_partials; a.local_rec = st->d_local_rec; a.out = s->d_results;
     a.d_cmds = st->d_cmds;
@@ -327,17 +355,11 @@ int32_t hs_eval_session_begin(hs_ctx* ctx, const hs_cloud* cloud, const int64_t*
     a.h_status = ctx->d_status;
     a.idle_timeout_ns = 20ull * 1000000000ull;
     if (s->exchange) { a.px = ctx->px; a.epoch0 = ctx->px.epoch + 1; }
-    auto kern = k_eval<EVK_NCONS, EVK_STAGES, EVK_GPT, EVK_FLUSH, true>;
-    if (!st->attr_set[1]) {
-      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eval_smem_bytes()))) != cudaSuccess) return fail(e);
-      st->attr_set[1] = true;
+    s->nblocks = st->h_plan.nblocks;
+    if (const char* tf = std::getenv("HS_EVAL_TRACE")) {  // tracing: where the time of an evaluation goes, block by block
+      const size_t bytes = sizeof(unsigned long long) * EV_TRACE_EVALS * s->nblocks * 4;
+      if (tf[0] && cudaMalloc(&s->d_trace, bytes) == cudaSuccess) { cudaMemsetAsync(s->d_trace, 0, bytes, ctx->stream); a.trace = s->d_trace; }
     }
-    if ((e = cudaMemsetAsync(st->d_ctl, 0, sizeof(EvalCtl), ctx->stream)) != cudaSuccess) return fail(e);
-    EvalCmd none;
-    std::memset(&none, 0, sizeof none);
-    kern<<<st->h_plan.nblocks, EVK_NCONS + 128, eval_smem_bytes(), ctx->stream>>>(a, none);
-    ctx->launches++;
-    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
   }
   ctx->session = s;
   *out = s;
@@ -351,7 +373,7 @@ int32_t hs_eval_session_post(hs_eval_session* s, const double* params, int32_t c
   if (!params || count < 0) { ctx->err = "hs_eval_session_post: bad arguments"; return HS_EINVAL; }
   if (s->stopped) { ctx->err = "hs_eval_session_post: the session has been stopped"; return HS_EINVAL; }
   for (int32_t i = 0; i < count; ++i) {
-    if (!s->empty) {
+    if (!s->empty && s->posted - host_load(&s->h_ctl->done) >= static_cast<uint32_t>(EV_QCAP)) {
       // a ring entry is free again once its evaluation is done
       if (int32_t rc = session_spin(s, "hs_eval_session_post", [&] { return s->posted - host_load(&s->h_ctl->done) < static_cast<uint32_t>(EV_QCAP); })) return rc;
     }
@@ -362,11 +384,13 @@ int32_t hs_eval_session_post(hs_eval_session* s, const double* params, int32_t c
       for (int j = 0; j < 3; ++j)
         for (int k = 0; k < 3; ++k)
           if (!(pl[8 * j + k] == -pl[8 * j + 4 + k])) { ctx->err = "hs_eval_session_post: parameters do not give antiparallel wall pairs (NaN?)"; return HS_EINVAL; }
-      fill_cmd(c, r, pl);
+      fill_cmd(c, r, pl, s->posted);
     }
     ++s->posted;
     if (s->empty) host_store(&s->h_ctl->done, s->posted);  // zero records, already in h_results
     host_store(&s->h_ctl->posted, s->posted);
+    if (!s->launched)  // the first command is in the ring: start the kernel, the rest is posted while it evaluates
+      if (int32_t rc = session_launch(s)) return rc;
   }
   return HS_OK;
 }
@@ -421,6 +445,18 @@ int32_t hs_eval_session_end(hs_eval_session* s) {
   if (e != cudaSuccess) { ctx->err = std::string("hs_eval_session_end: ") + cudaGetErrorString(e); rc = HS_ECUDA; }
   if (rc == HS_OK) rc = session_check(s, "hs_eval_session_end");
   if (rc == HS_OK && !s->empty && host_load(&s->h_ctl->done) != s->posted) { ctx->err = "hs_eval_session_end: the kernel ended before all posted evaluations were done"; rc = HS_ECUDA; }
+  if (s->d_trace) {
+    const size_t nwords = static_cast<size_t>(EV_TRACE_EVALS) * s->nblocks * 4;
+    std::vector<unsigned long long> host(nwords);
+    if (cudaMemcpy(host.data(), s->d_trace, nwords * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess)
+      if (FILE* fp = std::fopen(std::getenv("HS_EVAL_TRACE"), "wb")) {
+        const int32_t hdr[4] = {EV_TRACE_EVALS, s->nblocks, 4, static_cast<int32_t>(s->posted)};
+        std::fwrite(hdr, sizeof hdr, 1, fp);
+        std::fwrite(host.data(), sizeof(unsigned long long), nwords, fp);
+        std::fclose(fp);
+      }
+    cudaFree(s->d_trace);
+  }
   if (s->exchange) ctx->px.epoch += s->posted;  // every rank posted the same evaluations
   if (ctx->h_status) *ctx->h_status = 0;  // reported through this call
   ctx->session = nullptr;

@@ -11,8 +11,11 @@
 //              predicated point block of k_eval_point.cuh into 21 Float chains, and every FLUSH_TILES tiles the warp transposes
 //              its chains with shuffles (lane l ends up with the warp total of chain l: 104 instructions instead of the 22
 //              butterflies of round 1) and lane l adds its total into ONE Double register.  At the end of a room segment the
-//              lanes park their Doubles in shared memory, sync, and go straight on to the next segment / evaluation: they never
-//              touch global memory and never wait for a reduction (at most EV_D evaluations in flight).
+//              lanes leave their Doubles in shared memory, sync, and go straight on to the next segment / evaluation: they never
+//              touch global memory and never wait for a reduction (at most EV_D evaluations in flight).  In the session form
+//              what the next evaluation needs (control words, plane constants) was fetched with cp.async while this one streamed,
+//              and the go decision rides on the segment's own barrier: no bubble between evaluations.  A segment's ragged head /
+//              tail points (room offsets are arbitrary) are staged with cp.async too and evaluated after the tiles.
 //   reducer    adds the warps' Doubles in warp order into the block's partial record of (evaluation, room), publishes it and
 //              takes the room's ticket; the block that delivers the LAST partial of a room adds the room's partials in block
 //              order (deterministic) and converts the raw sums into the HS_REC record.  Never waits for anything remote.
@@ -35,8 +38,11 @@ constexpr int EV_MAXB = 256;   // blocks of a plan (>= SM count)
 constexpr int EV_D = 4;        // evaluations in flight per GPU: partial-record ring, tickets (PEER_SLOTS >= 2 * EV_D)
 constexpr int EV_NRAW = 22;    // raw sums per (block, room): f, T[3], M[3], B[9], C1, C2, Cm[3], N
 constexpr int EV_QCAP = 256;   // command / result ring entries of a session
-constexpr int EV_PARK = 16;    // ring of parked block sums (segments the reducer may lag behind the consumers)
+constexpr int EV_PARK = 16;    // entries of the consumers -> reducer queue
+constexpr int EV_WS = 4;       // segments the reducer may lag behind the consumers (buffers of warp sums)
 constexpr int EV_FQ = 8;       // finaliser queue entries (>= EV_D)
+constexpr int EV_TRACE_EVALS = 32;  // evaluations covered by a session trace
+constexpr int EV_PF = 4;       // segments of a block whose constants are prefetched for the next evaluation (more: loaded at use)
 static_assert(PEER_SLOTS >= 2 * EV_D, "mailbox slots must cover two windows of in-flight evaluations");
 
 struct EvalPlan {  // device memory; fixed for a (cloud, room offsets, grid) triple
@@ -49,7 +55,7 @@ struct EvalPlan {  // device memory; fixed for a (cloud, room offsets, grid) tri
 };
 
 constexpr int EV_CMD_F = 16;  // floats per room: one 64-byte line
-struct EvalCmd {  // one evaluation's plane constants: per room n[3][3] (normals of the + walls), dp[3], dm[3], pad
+struct EvalCmd {  // one evaluation's plane constants: per room n[3][3] (normals of the + walls), dp[3], dm[3], [15] = bits of (sequence number + 1)
   float c[HS_MAX_ROOMS][EV_CMD_F];
 };
 
@@ -81,6 +87,7 @@ struct EvalArgs {
   EvalHostCtl* h_ctl;           // session
   double* h_results;            // session: host-mapped result ring [EV_QCAP][nrooms * HS_REC]
   unsigned long long* h_times;  // session: host-mapped [EV_QCAP][2] %globaltimer stamps: command seen by the device, records committed
+  unsigned long long* trace;    // session tracing (HS_EVAL_TRACE=<file>): [EV_TRACE_EVALS][nblocks][4] %globaltimer stamps, else nullptr
   uint32_t* h_status;           // mapped word of the ctx: set to HS_ENCCL when a peer timed out
   unsigned long long idle_timeout_ns;
   uint32_t epoch0;              // peer epoch of evaluation 0 (epochs are > 0)
@@ -96,6 +103,10 @@ __device__ __forceinline__ float4 ld_sys_v4(const float4* p) {
   float4 v;
   asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
 template <int NCONS>
@@ -189,11 +200,17 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(STAGES) * TILE_BYTES);
   uint64_t* empty = full + STAGES;
-  double* wsum = reinterpret_cast<double*>(empty + STAGES);  // [2][NW][EV_NRAW]: the warps' Doubles of the segment just finished
-  double* parked = wsum + 2 * NW * EV_NRAW;                  // [EV_PARK][EV_NRAW]: block sums waiting for the reducer
+  double* wsum = reinterpret_cast<double*>(empty + STAGES);  // [EV_WS][NW][EV_NRAW]: the warps' Doubles of the last EV_WS segments, summed by the reducer
   __shared__ int64_t s_lo[HS_MAX_ROOMS], s_hi[HS_MAX_ROOMS];  // point range of each room segment of this block
   __shared__ uint32_t s_rq[EV_PARK], s_fq[EV_FQ];            // consumers -> reducer (e << 8 | room), reducer -> finaliser (e)
   __shared__ volatile uint32_t s_rq_tail, s_rq_head, s_fq_tail, s_exit, s_exit2, s_consumed_lo, s_consumed_hi, s_go;
+  __shared__ volatile uint32_t s_go_fast[2];  // [parity of the evaluation]: decided before the previous evaluation's final barrier
+  // session: what the NEXT evaluation needs, fetched with cp.async while the current one streams (no bubble between evaluations):
+  // a snapshot of the control words {posted, stop, done_seq, error} and the plane constants of the block's first EV_PF segments
+  __shared__ float s_rag[6][3];  // a segment's ragged head (<= 3) and tail (<= 3) points, staged with cp.async while the tiles stream
+  __shared__ __align__(16) uint32_t s_ctl_snap[4];
+  __shared__ volatile uint32_t s_pf_ok[2];  // [parity of the evaluation]: its constants were prefetched from a command that had been published before
+  __shared__ __align__(16) float s_cmd_pf[2][EV_PF][EV_CMD_F];
 
   const EvalPlan* __restrict__ plan = a.plan;
   const int b = static_cast<int>(blockIdx.x);
@@ -205,7 +222,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCONS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    s_rq_tail = 0; s_rq_head = 0; s_fq_tail = 0; s_exit = 0; s_exit2 = 0; s_consumed_lo = 0; s_consumed_hi = 0; s_go = 0;
+    s_rq_tail = 0; s_rq_head = 0; s_fq_tail = 0; s_exit = 0; s_exit2 = 0; s_consumed_lo = 0; s_consumed_hi = 0; s_go = 0; s_go_fast[0] = 0; s_go_fast[1] = 0; s_pf_ok[0] = 0; s_pf_ok[1] = 0;
   }
   if (static_cast<int>(threadIdx.x) < nseg) {
     const int64_t p0 = plan->blk_g0[b] * 4, p1 = min(plan->blk_g0[b + 1] * 4, plan->n);
@@ -225,17 +242,26 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       uint32_t hp, hstop;  // {posted, stop} sit side by side: ONE read over PCIe per poll
       asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hp), "=r"(hstop) : "l"(&a.h_ctl->posted) : "memory");
       if (hp != seq) {
+        // copy the new commands host -> device ring (one 64-byte line per room) and publish them one by one: the consumers start on
+        // the first while the rest still crosses PCIe.  All loads of a command are in flight together (<= 4 per lane for 32 rooms).
         const unsigned long long t_seen = peer_now_ns();
-        while (seq != hp) {  // copy the new commands host -> device ring (16 floats = one 64-byte line per room)
+        while (seq != hp) {
           if (lane == 0) a.h_times[2 * (seq % EV_QCAP)] = t_seen;
           const float4* src = reinterpret_cast<const float4*>(a.h_cmds[seq % EV_QCAP].c);
           float4* dst = reinterpret_cast<float4*>(a.d_cmds[seq % EV_QCAP].c);
-          for (int i = lane; i < nrooms * (EV_CMD_F / 4); i += 32) dst[i] = ld_sys_v4(src + i);
+          const int nv = nrooms * (EV_CMD_F / 4);
+          float4 v[HS_MAX_ROOMS * (EV_CMD_F / 4) / 32];
+#pragma unroll
+          for (int k = 0; k < HS_MAX_ROOMS * (EV_CMD_F / 4) / 32; ++k)
+            if (lane + 32 * k < nv) v[k] = ld_sys_v4(src + lane + 32 * k);
+#pragma unroll
+          for (int k = 0; k < HS_MAX_ROOMS * (EV_CMD_F / 4) / 32; ++k)
+            if (lane + 32 * k < nv) dst[lane + 32 * k] = v[k];
           ++seq;
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) st_release_u32(&a.ctl->posted, seq);
         }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release_u32(&a.ctl->posted, seq);
         t_last = peer_now_ns();
         spins = 0;
         continue;
@@ -311,13 +337,16 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       // ---- publish the block's partial record of (evaluation, room)
       const int blo = plan->room_blo[r], nb = plan->room_nb[r];
       double* part = a.partials + ((static_cast<size_t>(slot) * nrooms + r) * nblocks) * EV_NRAW;
-      if (lane < EV_NRAW) {
-        part[static_cast<size_t>(b - blo) * EV_NRAW + lane] = parked[(head % EV_PARK) * EV_NRAW + lane];
+      if (lane < EV_NRAW) {  // the warps' Doubles added in warp order (deterministic)
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sum += wsum[((head % EV_WS) * NW + w) * EV_NRAW + lane];
+        part[static_cast<size_t>(b - blo) * EV_NRAW + lane] = sum;
         __threadfence();
       }
       __syncwarp();
       ++head;
-      if (lane == 0) s_rq_head = head;  // the parked sums of this segment may be overwritten
+      if (lane == 0) s_rq_head = head;  // this segment's warp sums may be overwritten
       uint32_t last = 0;
       if (lane == 0) {
         const uint32_t t = atomicAdd(&a.ctl->room_ticket[slot][r], 1u);
@@ -423,17 +452,21 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
   // =================================================================================================== consumers
   uint64_t tt = 0;  // tiles consumed so far
   uint32_t stage = 0, parity = 0;
+  int last_si = -1;  // last segment of the block that holds points (the evaluation's final barrier happens there)
+  for (int si = 0; si < nseg; ++si)
+    if (s_lo[si] < s_hi[si]) last_si = si;
   uint32_t qtail = 0;  // segments handed to the reducer so far
-  uint32_t wpar = 0;
   const uint32_t tiles_s = smem_u32(tiles) + threadIdx.x * 48, empty_s = smem_u32(empty);
   for (uint32_t e = 0; SESSION || e == 0; ++e) {
-    if (SESSION) {
+    if (SESSION && !(e > 0 && s_go_fast[e & 1])) {
       // wait for command e (or the end of the session); never run more than EV_D evaluations ahead of the finalised ones.
-      // One thread decides for the block: a split decision would leave warps behind at the named barrier.
+      // One thread decides for the block: a split decision would leave warps behind at the named barrier.  (Fast path: thread 0
+      // took the decision from the control snapshot before the previous evaluation's final barrier, see below - no second barrier.)
       if (threadIdx.x == 0) {
-        uint32_t go = 0;
-        for (;;) {
+        uint32_t go = 0, known_posted = 0;
+        while (!go) {
           const uint32_t posted = ld_acquire_u32(&a.ctl->posted), done = ld_acquire_u32(&a.ctl->done_seq);
+          known_posted = posted;
           if (static_cast<int32_t>(posted - e) > 0) {
             if (e - done < static_cast<uint32_t>(EV_D)) { go = 1; break; }
           } else if (ld_acquire_u32(&a.ctl->stop) && static_cast<int32_t>(ld_acquire_u32(&a.ctl->posted) - e) <= 0) break;
@@ -441,21 +474,43 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
           __nanosleep(40);
         }
         s_go = go;
+        // command e + 1 may be prefetched only if it is known to be published already (the dispatcher writes a command's lines
+        // unordered and publishes `posted` after a fence: an unpublished command can be half written)
+        s_pf_ok[(e + 1) & 1] = static_cast<int32_t>(known_posted - (e + 1)) > 0 ? 1u : 0u;
       }
       consumers_sync<NCONS>();
       if (!s_go) break;
     }
+    if (SESSION) {
+      // prefetch for evaluation e + 1 (asynchronous, lands long before this evaluation's first segment ends)
+      if (threadIdx.x == 0) cp_async16(smem_u32(s_ctl_snap), a.ctl);
+      else if (s_pf_ok[(e + 1) & 1] && static_cast<int>(threadIdx.x) - 32 >= 0 && static_cast<int>(threadIdx.x) - 32 < 4 * min(nseg, EV_PF)) {
+        const int q = static_cast<int>(threadIdx.x) - 32, sj = q >> 2, part = q & 3;
+        cp_async16(smem_u32(&s_cmd_pf[(e + 1) & 1][sj][4 * part]), a.d_cmds[(e + 1) % EV_QCAP].c[rfirst + sj] + 4 * part);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    bool pf_waited = !SESSION;
+    const bool tracing = SESSION && a.trace != nullptr && e < static_cast<uint32_t>(EV_TRACE_EVALS) && threadIdx.x == 64;
+    unsigned long long* tr = tracing ? a.trace + (static_cast<size_t>(e) * nblocks + b) * 4 : nullptr;
+    if (tracing) tr[0] = peer_now_ns();
     for (int si = 0; si < nseg; ++si) {
       const int r = rfirst + si;
       const int64_t lo = s_lo[si], hi = s_hi[si];
       if (lo >= hi) continue;  // a room without points between two rooms of this block: no segment, no partial, no ticket (room_nb counts none)
       RoomK R;
       if (SESSION) {
-        const float* c16 = a.d_cmds[e % EV_QCAP].c[r];
-        float t[15];
+        // constants of (evaluation e, room r): from the prefetch buffer when it holds exactly this command (stamp), else from L2
+        const float* pf = s_cmd_pf[e & 1][si < EV_PF ? si : 0];
+        if (si < EV_PF && e > 0 && s_pf_ok[e & 1] && __float_as_uint(pf[15]) == e + 1u) {
+          load_room_consts(R, pf);
+        } else {
+          const float* c16 = a.d_cmds[e % EV_QCAP].c[r];
+          float t[15];
 #pragma unroll
-        for (int i = 0; i < 15; ++i) t[i] = __ldcg(c16 + i);
-        load_room_consts(R, t);
+          for (int i = 0; i < 15; ++i) t[i] = __ldcg(c16 + i);
+          load_room_consts(R, t);
+        }
       } else {
         load_room_consts(R, cmd0.c[r]);
       }
@@ -463,19 +518,30 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       ch.clear();
       int npts = 0;
       double dacc = 0.0;
+      bool has_rag = false;
+      int ragslot = 0;
       const int64_t gl = (lo + 3) >> 2, gh = hi >> 2;
       if (gl <= gh) {
         // ragged head / tail points (at most 3 each): the same per-point block, one point per thread
         const int64_t head_end = gl * 4, tail_begin = gh * 4;
         const int64_t nh = head_end - lo, ntail = hi - tail_begin;
-        if (static_cast<int64_t>(threadIdx.x) < nh) { const int64_t i = lo + threadIdx.x; add_point(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
-        else if (threadIdx.x >= 32 && static_cast<int64_t>(threadIdx.x) - 32 < ntail) { const int64_t i = tail_begin + threadIdx.x - 32; add_point(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
+        // staged into shared memory asynchronously, evaluated after the tiles: no warp waits for a global load at the segment's start
+        const bool rag_head = static_cast<int64_t>(threadIdx.x) < nh, rag_tail = threadIdx.x >= 32 && static_cast<int64_t>(threadIdx.x) - 32 < ntail;
+        has_rag = rag_head || rag_tail;
+        ragslot = rag_head ? static_cast<int>(threadIdx.x) : 3 + static_cast<int>(threadIdx.x) - 32;
+        if (has_rag) {
+          const int64_t i = rag_head ? lo + threadIdx.x : tail_begin + threadIdx.x - 32;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_rag[ragslot][c])), "l"(a.xyz + 3 * i + c) : "memory");
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         const int64_t ngroups = gh - gl;
         const int nfull = static_cast<int>(ngroups / TILE_GROUPS);
         const int rem_groups = static_cast<int>(ngroups - static_cast<int64_t>(nfull) * TILE_GROUPS);
         int since_flush = 0;
         for (int t = 0; t < nfull; ++t) {
           mbar_wait(full + stage, parity);
+          if (tracing && t == 0 && si == 0) tr[1] = peer_now_ns();
           const uint32_t base = tiles_s + stage * TILE_BYTES;
           float4 q[GPT][3];
 #pragma unroll
@@ -510,30 +576,36 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         const int64_t i = lo + threadIdx.x;
         if (i < hi) { add_point(ch, R, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]); ++npts; }
       }
+      if (tracing && si == last_si) tr[2] = peer_now_ns();
+      if (has_rag) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        add_point(ch, R, s_rag[ragslot][0], s_rag[ragslot][1], s_rag[ragslot][2]);
+        ++npts;
+      }
       flush_chains(ch, npts, dacc, lane);
-      // ---- the block's sums of this segment: warp Doubles added in warp order by warp 0 and parked for the reducer; everybody
-      // else moves on at once (wsum is double-buffered: warp 0 joins the next segment's barrier only after it has read this one)
-      if (lane < EV_NRAW) wsum[(wpar * NW + warp) * EV_NRAW + lane] = dacc;
+      // ---- the block's sums of this segment: every warp leaves its Doubles in buffer qtail % EV_WS and moves on at once; the
+      // reducer warp adds them in warp order.  The buffer is free once the reducer has taken segment qtail - EV_WS.
+      if (qtail >= static_cast<uint32_t>(EV_WS))
+        while (static_cast<int32_t>(s_rq_head - (qtail - (EV_WS - 1))) < 0) __nanosleep(32);  // only with many tiny rooms per block
+      if (lane < EV_NRAW) wsum[((qtail % EV_WS) * NW + warp) * EV_NRAW + lane] = dacc;
+      if (!pf_waited) { asm volatile("cp.async.wait_all;" ::: "memory"); pf_waited = true; }  // own copies done; the barrier publishes them
+      if (SESSION && si == last_si && threadIdx.x == 0) {
+        // decision for evaluation e + 1 from the snapshot this thread fetched at the start of e: posted, not throttled, no error
+        // => everybody goes straight on after this barrier.  Anything else takes the polling path at the top of the loop, AFTER
+        // this evaluation's sums have been handed over (a one-by-one caller posts e + 1 only when it has seen e's records).
+        const uint32_t ps = s_ctl_snap[0], ds = s_ctl_snap[2];
+        const bool fast = static_cast<int32_t>(ps - (e + 1)) > 0 && (e + 1) - ds < static_cast<uint32_t>(EV_D) && s_ctl_snap[3] == 0u;
+        s_go_fast[(e + 1) & 1] = fast ? 1u : 0u;  // (a raised stop flag does not matter while posted commands are left)
+        if (fast) s_pf_ok[(e + 2) & 1] = static_cast<int32_t>(ps - (e + 2)) > 0 ? 1u : 0u;
+      }
       consumers_sync<NCONS>();
-      if (warp == 0) {
-        if (lane == 0)
-          while (qtail - s_rq_head >= static_cast<uint32_t>(EV_PARK)) __nanosleep(32);  // reducer EV_PARK segments behind: only with > 4 tiny rooms per block
-        __syncwarp();
-        if (lane < EV_NRAW) {
-          double sum = 0.0;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) sum += wsum[(wpar * NW + w) * EV_NRAW + lane];
-          parked[(qtail % EV_PARK) * EV_NRAW + lane] = sum;
-        }
-        __syncwarp();
-        if (lane == 0) {
-          s_rq[qtail % EV_PARK] = (e << 8) | static_cast<uint32_t>(r);
-          __threadfence_block();
-          s_rq_tail = qtail + 1;
-        }
+      if (tracing && si == last_si) tr[3] = peer_now_ns();
+      if (threadIdx.x == 0) {
+        s_rq[qtail % EV_PARK] = (e << 8) | static_cast<uint32_t>(r);
+        __threadfence_block();
+        s_rq_tail = qtail + 1;
       }
       ++qtail;
-      wpar ^= 1u;
     }
   }
   // ---- leaving: tell the producer how far the ring was consumed and let producer / reducer / finaliser drain
