@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--out-dir", default="", help="c2_export: directory of the .ply (default: the system temp dir)")
     ap.add_argument("--path", default="session", choices=["session", "launch"],
                     help="session = one resident kernel runs all K evaluations (hs_eval_session_*); launch = one kernel launch per evaluation")
+    ap.add_argument("--defer-launch", action="store_true",
+                    help="session path: start the resident kernel at stop() with every command in place (for profilers that block in the launch call, e.g. ncu)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: p2p = records summed over NVLink peer memory inside the reduction kernel (product path); nccl = kernel + dist.all_reduce")
     args = ap.parse_args()
@@ -280,6 +282,8 @@ def main():
         ctx.set_mode(0, args.mode)
     if args.blocks_per_sm > 0:
         ctx.set_mode(1, args.blocks_per_sm)
+    if args.defer_launch:
+        ctx.set_mode(4, 1)
     # a dedicated non-default stream shared by torch (events, NCCL ordering) and the library (kernels, copies)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)

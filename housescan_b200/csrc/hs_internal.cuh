@@ -62,6 +62,8 @@ struct hs_ctx {
 
 enum { HS_MODE_EVAL_KERNEL = 0, HS_MODE_BLOCKS_PER_SM = 1,
        HS_MODE_EVAL_SEG_COST = 2,  // evaluation kernel: cost of an extra room segment in 4-point groups for the weighted partition (0 = default)
+       HS_MODE_SESSION_LAUNCH = 4, // evaluation sessions: 0 = the resident kernel starts with the first posted command (default); 1 = it starts when the host
+                                   // first needs the device (wait / stop / full ring): for tools that serialise kernel launches (ncu blocks in the launch call)
        HS_MODE_PS_KERNEL = 7,   // per-plane sums: 0 = ring form (bulk-async tiles, warp-level flushes), 1 = all-Double form, 2 = direct-load Float chains
        HS_MODE_SEL_KERNEL = 8,  // k-th: 0 = 11/11/10-bit passes over compacted keys, 1 = four 8-bit passes over the cloud
        HS_MODE_FILTER_KERNEL = 12,  // order-preserving filter: 0 = count pass + scatter pass, 1 = single pass (decoupled look-back)

@@ -20,7 +20,7 @@ namespace hsk {
 
 // product configuration: 12 consumer warps, 3 ring stages of 72 KB, 16 points per thread per tile, Float chains of 256 points
 constexpr int EVK_NCONS = 384, EVK_STAGES = 3, EVK_GPT = 4, EVK_FLUSH = 16;
-constexpr int EVK_SEG_COST_DEFAULT = 768;  // an extra room segment in a block costs about this many 4-point groups (flush + block sum)
+constexpr int EVK_SEG_COST_DEFAULT = 1536;  // an extra room segment in a block costs about this many 4-point groups (flush + block sum)
 
 constexpr size_t eval_smem_bytes() {
   return static_cast<size_t>(EVK_STAGES) * EVK_GPT * EVK_NCONS * 48 + 2 * EVK_STAGES * 8 + static_cast<size_t>(EV_WS) * (EVK_NCONS / 32) * EV_NRAW * 8;
@@ -80,11 +80,19 @@ static int64_t plan_walk(int64_t G, int nb, int64_t target, int seg_cost, const 
   int64_t g = 0;
   for (int b = 0; b < nb; ++b) {
     if (g0_out) g0_out[b] = g;
+    // a block streams `target` groups minus seg_cost for every room boundary strictly inside its range.  If shortening the range
+    // would push a boundary out of it, the block ends AT that boundary instead (the room starts the next block: no second segment).
     int64_t end = std::min(G, g + target);
-    for (int it = 0; it < 2; ++it) {  // boundaries strictly inside (4g, 4 end) cost seg_cost groups each
+    for (int it = 0; it <= nbounds; ++it) {
       int k = 0;
       for (int i = 0; i < nbounds; ++i) k += (bounds[i] > 4 * g && bounds[i] < 4 * end);
-      end = std::max(std::min(G, g + 1), std::min(G, g + target - static_cast<int64_t>(k) * seg_cost));
+      const int64_t want = std::max(std::min(G, g + 1), std::min(G, g + target - static_cast<int64_t>(k) * seg_cost));
+      if (want >= end) break;
+      int64_t first_dropped = -1;
+      for (int i = 0; i < nbounds; ++i)
+        if (bounds[i] > 4 * want && bounds[i] < 4 * end && (first_dropped < 0 || bounds[i] < first_dropped)) first_dropped = bounds[i];
+      if (first_dropped < 0) { end = want; break; }
+      end = std::max(std::max(want, first_dropped / 4), g + 1);
     }
     g = end;
   }
@@ -104,6 +112,7 @@ static void build_plan(EvalPlan& P, int64_t n, const int64_t* off, int nrooms, i
   int64_t bounds[HS_MAX_ROOMS];
   int nbounds = 0;
   for (int r = 0; r < nrooms; ++r) {
+    if (off[r + 1] <= off[r]) P.empty_mask |= 1u << r;
     if (off[r + 1] > off[r]) {
       ++P.nrooms_nonempty;
       if (off[r] > off[0] && off[r] > 0) bounds[nbounds++] = off[r];  // start of a non-empty room that is not the first point
@@ -374,7 +383,8 @@ int32_t hs_eval_session_post(hs_eval_session* s, const double* params, int32_t c
   if (s->stopped) { ctx->err = "hs_eval_session_post: the session has been stopped"; return HS_EINVAL; }
   for (int32_t i = 0; i < count; ++i) {
     if (!s->empty && s->posted - host_load(&s->h_ctl->done) >= static_cast<uint32_t>(EV_QCAP)) {
-      // a ring entry is free again once its evaluation is done
+      // a ring entry is free again once its evaluation is done (the kernel must be running for that)
+      if (int32_t rc = session_launch(s)) return rc;
       if (int32_t rc = session_spin(s, "hs_eval_session_post", [&] { return s->posted - host_load(&s->h_ctl->done) < static_cast<uint32_t>(EV_QCAP); })) return rc;
     }
     EvalCmd& c = s->h_cmds[s->posted % EV_QCAP];
@@ -389,7 +399,7 @@ int32_t hs_eval_session_post(hs_eval_session* s, const double* params, int32_t c
     ++s->posted;
     if (s->empty) host_store(&s->h_ctl->done, s->posted);  // zero records, already in h_results
     host_store(&s->h_ctl->posted, s->posted);
-    if (!s->launched)  // the first command is in the ring: start the kernel, the rest is posted while it evaluates
+    if (!s->launched && ctx->modes[HS_MODE_SESSION_LAUNCH] == 0)  // the first command is in the ring: start the kernel, the rest is posted while it evaluates
       if (int32_t rc = session_launch(s)) return rc;
   }
   return HS_OK;
@@ -403,6 +413,7 @@ int32_t hs_eval_session_wait(hs_eval_session* s, int64_t seq, double* rec_out) {
   HS_SLOCK(ctx);
   if (seq < 0 || seq >= static_cast<int64_t>(s->posted)) { ctx->err = "hs_eval_session_wait: evaluation has not been posted"; return HS_EINVAL; }
   if (static_cast<int64_t>(s->posted) - seq > EV_QCAP) { ctx->err = "hs_eval_session_wait: record no longer in the result ring (256 evaluations)"; return HS_EINVAL; }
+  if (int32_t rc = session_launch(s)) return rc;  // deferred-launch mode: the kernel starts when the host first needs a result
   if (int32_t rc = session_spin(s, "hs_eval_session_wait", [&] { return static_cast<int64_t>(host_load(&s->h_ctl->done)) > seq; })) return rc;
   if (int32_t rc = session_check(s, "hs_eval_session_wait")) return rc;
   if (rec_out) std::memcpy(rec_out, s->h_results + static_cast<size_t>(seq % EV_QCAP) * s->nrooms * HS_REC, sizeof(double) * s->nrooms * HS_REC);
@@ -421,6 +432,8 @@ int32_t hs_eval_session_stop(hs_eval_session* s) {
   HS_SLOCK(ctx);
   s->stopped = true;
   host_store(&s->h_ctl->stop, 1u);
+  if (s->posted > 0)  // deferred-launch mode: the kernel starts now, with every command and the stop flag in place
+    if (int32_t rc = session_launch(s)) return rc;
   return HS_OK;
 }
 
@@ -440,7 +453,7 @@ int32_t hs_eval_session_end(hs_eval_session* s) {
   HS_SLOCK(ctx);
   s->stopped = true;
   host_store(&s->h_ctl->stop, 1u);
-  int32_t rc = HS_OK;
+  int32_t rc = s->posted > 0 ? session_launch(s) : HS_OK;
   const cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { ctx->err = std::string("hs_eval_session_end: ") + cudaGetErrorString(e); rc = HS_ECUDA; }
   if (rc == HS_OK) rc = session_check(s, "hs_eval_session_end");

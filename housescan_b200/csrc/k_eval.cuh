@@ -35,18 +35,19 @@
 namespace hsk {
 
 constexpr int EV_MAXB = 256;   // blocks of a plan (>= SM count)
-constexpr int EV_D = 4;        // evaluations in flight per GPU: partial-record ring, tickets (PEER_SLOTS >= 2 * EV_D)
+constexpr int EV_D = 8;        // evaluations in flight per GPU: partial-record ring, tickets (PEER_SLOTS >= 2 * EV_D)
 constexpr int EV_NRAW = 22;    // raw sums per (block, room): f, T[3], M[3], B[9], C1, C2, Cm[3], N
 constexpr int EV_QCAP = 256;   // command / result ring entries of a session
 constexpr int EV_PARK = 16;    // entries of the consumers -> reducer queue
 constexpr int EV_WS = 4;       // segments the reducer may lag behind the consumers (buffers of warp sums)
-constexpr int EV_FQ = 8;       // finaliser queue entries (>= EV_D)
+constexpr int EV_FQ = 16;      // finaliser queue entries (>= EV_D)
 constexpr int EV_TRACE_EVALS = 32;  // evaluations covered by a session trace
 constexpr int EV_PF = 4;       // segments of a block whose constants are prefetched for the next evaluation (more: loaded at use)
 static_assert(PEER_SLOTS >= 2 * EV_D, "mailbox slots must cover two windows of in-flight evaluations");
 
 struct EvalPlan {  // device memory; fixed for a (cloud, room offsets, grid) triple
-  int32_t nblocks, nrooms, nrooms_nonempty, pad;
+  int32_t nblocks, nrooms, nrooms_nonempty;
+  uint32_t empty_mask;  // bit r: room r holds no point (its record is zero)
   int64_t n;
   int64_t off[HS_MAX_ROOMS + 1];
   int64_t blk_g0[EV_MAXB + 1];  // block b owns the 4-point groups [blk_g0[b], blk_g0[b+1])
@@ -322,6 +323,10 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
   // =================================================================================================== reducer
   if (warp == W_REDUCER) {
     uint32_t head = 0, ftail = 0;
+    // the plan entries this warp needs, read once: lane i keeps (first block, block count) of room rfirst + i
+    const int nonempty = plan->nrooms_nonempty;
+    const uint32_t empty_mask = plan->empty_mask;
+    const int my_blo = (lane < nseg) ? plan->room_blo[rfirst + lane] : 0, my_nb = (lane < nseg) ? plan->room_nb[rfirst + lane] : 0;
     for (;;) {
       bool leave = false;
       while (s_rq_tail == head) {
@@ -335,7 +340,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       const int r = static_cast<int>(item & 255u);
       const uint32_t slot = e % EV_D;
       // ---- publish the block's partial record of (evaluation, room)
-      const int blo = plan->room_blo[r], nb = plan->room_nb[r];
+      const int blo = __shfl_sync(0xffffffffu, my_blo, r - rfirst), nb = __shfl_sync(0xffffffffu, my_nb, r - rfirst);
       double* part = a.partials + ((static_cast<size_t>(slot) * nrooms + r) * nblocks) * EV_NRAW;
       if (lane < EV_NRAW) {  // the warps' Doubles added in warp order (deterministic)
         double sum = 0.0;
@@ -375,14 +380,14 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       last = 0;
       if (lane == 0) {
         const uint32_t t = atomicAdd(&a.ctl->rooms_done[slot], 1u);
-        last = (t == static_cast<uint32_t>(plan->nrooms_nonempty) - 1u);
+        last = (t == static_cast<uint32_t>(nonempty) - 1u);
         if (last) { a.ctl->rooms_done[slot] = 0u; __threadfence(); }
       }
       last = __shfl_sync(0xffffffffu, last, 0);
       if (!last) continue;
       // ---- last room of the evaluation
-      for (int rr = 0; rr < nrooms; ++rr)  // rooms without points: zero records
-        if (plan->off[rr + 1] == plan->off[rr] && lane < HS_REC) lrec[rr * HS_REC + lane] = 0.0;
+      for (uint32_t m = empty_mask; m; m &= m - 1u)  // rooms without points: zero records
+        if (lane < HS_REC) lrec[(__ffs(m) - 1) * HS_REC + lane] = 0.0;
       if (direct) continue;  // the end of the kernel publishes a.out
       __threadfence();
       __syncwarp();
@@ -424,10 +429,8 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       }
       if (SESSION) {
         double* hdst = a.h_results + static_cast<size_t>(e % EV_QCAP) * count;
-        for (int i = lane; i < count; i += 32) hdst[i] = dst[i];  // each lane re-reads what it wrote itself
-        __threadfence_system();
-        __syncwarp();
-        // in-order commit: the done counters advance evaluation by evaluation
+        for (int i = lane; i < count; i += 32) hdst[i] = dst[i];  // each lane re-reads what it wrote itself; posted PCIe writes
+        // in-order commit: the done counters advance evaluation by evaluation (the writes above travel meanwhile)
         const unsigned long long t0 = peer_now_ns();
         while (ld_acquire_u32(&a.ctl->done_seq) != e) {
           if (peer_now_ns() - t0 > 2 * PEER_TIMEOUT_NS) { ok = false; break; }
@@ -439,11 +442,14 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         if (a.h_status) st_sys_u32(a.h_status, static_cast<uint32_t>(HS_ENCCL));
         if (SESSION) st_sys_u32(&a.h_ctl->error, 1u);
       }
-      if (SESSION && lane == 0) {
-        a.h_times[2 * (e % EV_QCAP) + 1] = peer_now_ns();
-        __threadfence_system();
-        st_sys_u32(&a.h_ctl->done, e + 1u);
-        st_release_u32(&a.ctl->done_seq, e + 1u);
+      if (SESSION) {
+        if (lane == 0) a.h_times[2 * (e % EV_QCAP) + 1] = peer_now_ns();
+        __threadfence_system();  // every lane's record stores (device ring, host ring) before the counters
+        __syncwarp();
+        if (lane == 0) {
+          st_sys_u32(&a.h_ctl->done, e + 1u);
+          st_release_u32(&a.ctl->done_seq, e + 1u);
+        }
       }
     }
     return;

@@ -15,7 +15,7 @@
 
 namespace hsk {
 
-constexpr int PEER_SLOTS = 8;
+constexpr int PEER_SLOTS = 16;
 constexpr size_t PEER_SLOT_DOUBLES = static_cast<size_t>(HS_MAX_ROOMS) * HS_REC;
 constexpr size_t PEER_DATA_DOUBLES = static_cast<size_t>(PEER_SLOTS) * HS_PEER_MAX * PEER_SLOT_DOUBLES;  // [slot][source rank][record]
 constexpr size_t PEER_FLAG_STRIDE = 32;                                                                  // uint32 units: one 128-byte line per flag
