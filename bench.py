@@ -396,6 +396,13 @@ def main():
     ev1.record()
     barrier()
     launches = ctx.launch_count - l0
+    timeline = None
+    if sess is not None:  # the session's own device-clock stamps of the timed evaluations (per rank; the clocks of different GPUs are not comparable)
+        sess.wait(sess.posted - 1, want_record=False)
+        tm = np.array([sess.times(i) for i in range(args.steps)], dtype=np.int64)
+        gaps = np.diff(tm[:, 1]) / 1e3 if args.steps > 1 else np.zeros(1)
+        timeline = {"first_seen_to_first_commit_us": float(tm[0, 1] - tm[0, 0]) / 1e3, "commit_gap_median_us": float(np.median(gaps)), "commit_gap_max_us": float(np.max(gaps)),
+                    "first_seen_to_last_commit_us": float(tm[-1, 1] - tm[0, 0]) / 1e3}
     last_rec = finish(sess, want_last=True)
     ms = ev0.elapsed_time(ev1)
     k_ms_timed = ms / args.steps  # this rank's own time per step (before the max over ranks)
@@ -403,6 +410,12 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if timeline is not None:
+        timeline["events_minus_device_span_us"] = k_ms_timed * args.steps * 1e3 - timeline["first_seen_to_last_commit_us"]
+        if world > 1:  # every rank's view, gathered: min / max over ranks
+            allt = [None] * world
+            dist.all_gather_object(allt, timeline)
+            timeline = {k: {"min": min(t[k] for t in allt), "max": max(t[k] for t in allt)} for k in timeline}
     value = n_total * args.steps / (ms * 1e-3)
     if last_rec is None:
         last_rec = rec.cpu().numpy().reshape(N_ROOMS, hb.HS_REC).copy()
@@ -534,7 +547,7 @@ def main():
                        "points_per_gpu": int(n_local), "sharding": f"point-range x{world}",
                        "collective": ("none" if world == 1 else ("records summed over NVLink peer memory inside the reduction kernel (12x24 f64, CUDA IPC mailboxes)" if use_p2p
                                       else "nccl all_reduce of 12x24 f64 per step")),
-                       "collective_vs_nccl_max_rel": collective_check},
+                       "collective_vs_nccl_max_rel": collective_check, "session_timeline": timeline},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 12), "d2h_bytes_per_step": int(N_ROOMS * hb.HS_REC * 8),
                     "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps, "h2d_gbs_per_gpu": n_local * 12 / (e_ms / e2e_steps * 1e-3) / 1e9,
                     "path": "hs_cloud_write (pinned host -> HBM) + one evaluation launch (+ exchange) + record D2H, every step"},

@@ -300,8 +300,8 @@ static int32_t session_spin(hs_eval_session* s, const char* who, Cond cond) {
   }
 }
 
-// The resident kernel is launched by the first post, right after the FIRST command has been written to the ring: the kernel finds
-// work the moment it starts, and the host converts and posts the remaining parameter sets while the device evaluates.
+// The resident kernel is launched by the first post (or, in deferred mode, when the host first needs the device).  Its control block
+// is zero at that point: zeroed at creation, after every plan change and by every hs_eval_session_end.
 static int32_t session_launch(hs_eval_session* s) {
   if (s->launched || s->empty) return HS_OK;
   hs_ctx* ctx = s->ctx;
@@ -311,7 +311,6 @@ static int32_t session_launch(hs_eval_session* s) {
     HS_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eval_smem_bytes())));
     st->attr_set[1] = true;
   }
-  HS_CUDA_TRY(ctx, cudaMemsetAsync(st->d_ctl, 0, sizeof(EvalCtl), ctx->stream));
   EvalCmd none;
   std::memset(&none, 0, sizeof none);
   kern<<<s->nblocks, EVK_NCONS + 128, eval_smem_bytes(), ctx->stream>>>(s->args, none);
@@ -381,6 +380,10 @@ int32_t hs_eval_session_post(hs_eval_session* s, const double* params, int32_t c
   HS_SLOCK(ctx);
   if (!params || count < 0) { ctx->err = "hs_eval_session_post: bad arguments"; return HS_EINVAL; }
   if (s->stopped) { ctx->err = "hs_eval_session_post: the session has been stopped"; return HS_EINVAL; }
+  // the resident kernel starts before the first parameter set is converted: its start-up (~10 us) hides the conversion, and its
+  // dispatcher finds the command on one of its first polls
+  if (count > 0 && !s->launched && ctx->modes[HS_MODE_SESSION_LAUNCH] == 0)
+    if (int32_t rc = session_launch(s)) return rc;
   for (int32_t i = 0; i < count; ++i) {
     if (!s->empty && s->posted - host_load(&s->h_ctl->done) >= static_cast<uint32_t>(EV_QCAP)) {
       // a ring entry is free again once its evaluation is done (the kernel must be running for that)
@@ -399,8 +402,6 @@ int32_t hs_eval_session_post(hs_eval_session* s, const double* params, int32_t c
     ++s->posted;
     if (s->empty) host_store(&s->h_ctl->done, s->posted);  // zero records, already in h_results
     host_store(&s->h_ctl->posted, s->posted);
-    if (!s->launched && ctx->modes[HS_MODE_SESSION_LAUNCH] == 0)  // the first command is in the ring: start the kernel, the rest is posted while it evaluates
-      if (int32_t rc = session_launch(s)) return rc;
   }
   return HS_OK;
 }
@@ -470,6 +471,7 @@ int32_t hs_eval_session_end(hs_eval_session* s) {
       }
     cudaFree(s->d_trace);
   }
+  if (s->launched) cudaMemsetAsync(ctx->eval->d_ctl, 0, sizeof(EvalCtl), ctx->stream);  // counters back to zero for the next session / launch
   if (s->exchange) ctx->px.epoch += s->posted;  // every rank posted the same evaluations
   if (ctx->h_status) *ctx->h_status = 0;  // reported through this call
   ctx->session = nullptr;

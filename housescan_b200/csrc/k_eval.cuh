@@ -438,9 +438,8 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         }
       }
       if (!ok && lane == 0) {
-        a.ctl->error = 1u;
         if (a.h_status) st_sys_u32(a.h_status, static_cast<uint32_t>(HS_ENCCL));
-        if (SESSION) st_sys_u32(&a.h_ctl->error, 1u);
+        if (SESSION) { a.ctl->error = 1u; st_sys_u32(&a.h_ctl->error, 1u); }  // (the one-launch form leaves the control block untouched)
       }
       if (SESSION) {
         if (lane == 0) a.h_times[2 * (e % EV_QCAP) + 1] = peer_now_ns();
