@@ -329,9 +329,9 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
     const int my_blo = (lane < nseg) ? plan->room_blo[rfirst + lane] : 0, my_nb = (lane < nseg) ? plan->room_nb[rfirst + lane] : 0;
     for (;;) {
       bool leave = false;
-      while (s_rq_tail == head) {
+      while (s_rq_tail == head) {  // long naps: every poll takes issue slots from the consumer warps of this scheduler
         if (s_exit && s_rq_tail == head) { leave = true; break; }
-        __nanosleep(32);
+        __nanosleep(200);
       }
       if (leave) break;
       __threadfence_block();
@@ -409,7 +409,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       bool leave = false;
       while (s_fq_tail == head) {
         if (s_exit2 && s_fq_tail == head) { leave = true; break; }
-        __nanosleep(64);
+        __nanosleep(400);
       }
       if (leave) break;
       __threadfence_block();
@@ -434,7 +434,7 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
         const unsigned long long t0 = peer_now_ns();
         while (ld_acquire_u32(&a.ctl->done_seq) != e) {
           if (peer_now_ns() - t0 > 2 * PEER_TIMEOUT_NS) { ok = false; break; }
-          __nanosleep(64);
+          __nanosleep(250);
         }
       }
       if (!ok && lane == 0) {

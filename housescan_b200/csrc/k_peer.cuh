@@ -47,12 +47,9 @@ __device__ __forceinline__ void peer_push_warp(const PeerExchange& px, uint32_t 
     for (int k = 0; k < PEER_VPL; ++k)
       if (lane + 32 * k < count) dst[lane + 32 * k] = v[k];
   }
-  __threadfence_system();
-  __syncwarp();
-  if (lane < px.world) {  // lane p tells rank p that this rank's record has landed
-    __threadfence_system();
-    *peer_flag(px.mailbox[lane], slot, px.rank) = epoch;
-  }
+  __threadfence_system();  // every lane's record stores are performed system-wide ...
+  __syncwarp();            // ... before any lane raises a flag
+  if (lane < px.world) *peer_flag(px.mailbox[lane], slot, px.rank) = epoch;  // lane p tells rank p that this rank's record has landed
 }
 
 // Step 2: wait for every rank's record of this epoch in the local mailbox and add them in rank order into dst[0..count).
@@ -65,24 +62,29 @@ __device__ __forceinline__ bool peer_collect_warp(const PeerExchange& px, uint32
   if (lane < px.world) {
     volatile uint32_t* f = peer_flag(px.mailbox[px.rank], slot, lane);
     const unsigned long long t0 = peer_now_ns();
-    while (static_cast<int32_t>(*f - epoch) < 0) {
+    while (static_cast<int32_t>(*f - epoch) < 0) {  // long naps: this warp shares its scheduler with warps that stream the cloud
       if (peer_now_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
-      __nanosleep(40);
+      __nanosleep(250);
     }
     __threadfence_system();
   }
   ok = __all_sync(0xffffffffu, ok);
   const double* base = peer_data(px.mailbox[px.rank], slot, 0);
-  for (int i = lane; i < count; i += 32) {
-    double v[HS_PEER_MAX];
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  for (int i = lane; i < count; i += 64) {  // two values per round: 2 x HS_PEER_MAX loads in flight
+    double v[2][HS_PEER_MAX];
+    const bool second = i + 32 < count;
 #pragma unroll
-    for (int r = 0; r < HS_PEER_MAX; ++r)  // the peers wrote these lines over NVLink: read them from L2, never from a stale L1 line
-      v[r] = (r < px.world) ? __ldcv(base + static_cast<size_t>(r) * PEER_SLOT_DOUBLES + i) : 0.0;
-    double s = 0.0;
+    for (int r = 0; r < HS_PEER_MAX; ++r) {  // the peers wrote these lines over NVLink: read them from L2, never from a stale L1 line
+      v[0][r] = (r < px.world) ? __ldcv(base + static_cast<size_t>(r) * PEER_SLOT_DOUBLES + i) : 0.0;
+      v[1][r] = (r < px.world && second) ? __ldcv(base + static_cast<size_t>(r) * PEER_SLOT_DOUBLES + i + 32) : 0.0;
+    }
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int r = 0; r < HS_PEER_MAX; ++r)
-      if (r < px.world) s += v[r];  // rank order
-    dst[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
+      if (r < px.world) { s0 += v[0][r]; s1 += v[1][r]; }  // rank order
+    dst[i] = ok ? s0 : nan;
+    if (second) dst[i + 32] = ok ? s1 : nan;
   }
   return ok;
 }

@@ -15,6 +15,6 @@ PY
 }
 run 8
 run 1
-run 4
+
 run 8
 grep -v "OMP_NUM\|^\*\*\*\|^$" gpurun_out/r2p_bench.err | tail -5
