@@ -424,6 +424,8 @@ def main():
     # ---- the same K steps again after half a second of continuous load (the clock sampler needs samples under load, and this box's
     # sustained state differs from its burst state: the kernel is issue-bound and follows the SM clock under the power cap)
     n_heat = int(min(20000, max(100, round(500.0 / max(ms / args.steps, 1e-3)))))  # same value on every rank (ms is the max over ranks)
+    if args.defer_launch:
+        n_heat = min(n_heat, 200)  # a deferred launch must find every command in the 256-entry ring
     barrier()
     finish(run_steps(n_heat))
     sess = open_steps()

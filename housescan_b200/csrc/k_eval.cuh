@@ -391,9 +391,6 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       if (direct) continue;  // the end of the kernel publishes a.out
       __threadfence();
       __syncwarp();
-      // this rank's records go out to the peers NOW, from the warp that completed them: a push never waits behind the finaliser's
-      // wait for other ranks (a rank that is late with evaluation e must not also be late with e + 1)
-      if (a.px.world > 1) peer_push_warp(a.px, a.epoch0 + e, lrec, nrooms * HS_REC);
       if (lane == 0) {
         s_fq[ftail % EV_FQ] = e;
         __threadfence_block();
@@ -425,7 +422,10 @@ k_eval(const __grid_constant__ EvalArgs a, const __grid_constant__ EvalCmd cmd0)
       // the exchange of evaluation e depends on the peers only: it runs while earlier evaluations are still being finalised by
       // other blocks; only the publication below is in order
       if (a.px.world > 1) {
-        ok = peer_collect_warp(a.px, a.epoch0 + e, dst, count);  // (pushed by the reducer that completed the evaluation)
+        // (pushing from the reducer warp instead - so that a push never queues behind a collect - was measured at 8 GPUs: 39 us per
+        // evaluation against 33, profiles/r02f_bench_n8_reducer_push_rejected.json: the reducer is the busier warp of the block)
+        peer_push_warp(a.px, a.epoch0 + e, lrec, count);
+        ok = peer_collect_warp(a.px, a.epoch0 + e, dst, count);
       } else {
         for (int i = lane; i < count; i += 32) dst[i] = __ldcg(lrec + i);
       }
