@@ -130,3 +130,6 @@ foreign import ccall safe "hs_kth_smallest"         c_kth_smallest       :: Ptr 
 foreign import ccall safe "hs_write_ply_begin"     c_write_ply_begin     :: CString -> Int64 -> Int32 -> IO Int32
 foreign import ccall safe "hs_write_ply_part"      c_write_ply_part      :: Ptr HsCtx -> Ptr HsCloud -> Ptr Word8 -> CString -> Int64 -> Int64 -> IO Int32
 foreign import ccall safe "hs_write_ply_part_host" c_write_ply_part_host :: CString -> Ptr CFloat -> Ptr Word8 -> Int64 -> Int64 -> Int64 -> IO Int32
+-- the evaluation kernel's static partition of a cloud layout (host only; diagnostics)
+foreign import ccall unsafe "hs_eval_plan"
+  c_eval_plan :: Int64 -> Ptr Int64 -> Int32 -> Int32 -> Int32 -> Ptr Int32 -> Ptr Int64 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> IO Int32

@@ -322,6 +322,30 @@ static int32_t session_launch(hs_eval_session* s) {
 
 extern "C" {
 
+// The evaluation kernel's static partition, host only (no device, no ctx): what `hs_rooms_cuboid_sums*` and the sessions would use
+// for this cloud layout on a GPU with `sm_count` SMs.  For tests and for callers that want to see how a layout is cut.
+int32_t hs_eval_plan(int64_t n, const int64_t* room_offsets, int32_t nrooms, int32_t sm_count, int32_t seg_cost, int32_t* nblocks_out,
+                     int64_t* block_first_group_out /* nblocks + 1 */, int32_t* block_room_first_out, int32_t* block_room_last_out,
+                     int32_t* room_first_block_out, int32_t* room_nblocks_out) {
+  if (n < 0 || !room_offsets || nrooms < 1 || nrooms > HS_MAX_ROOMS || sm_count < 1 || !nblocks_out) return HS_EINVAL;
+  for (int r = 0; r < nrooms; ++r)
+    if (room_offsets[r] > room_offsets[r + 1]) return HS_EINVAL;
+  if (room_offsets[0] < 0 || room_offsets[nrooms] > n) return HS_EINVAL;
+  EvalPlan P;
+  build_plan(P, n, room_offsets, nrooms, sm_count, seg_cost > 0 ? seg_cost : (seg_cost < 0 ? 0 : EVK_SEG_COST_DEFAULT));
+  *nblocks_out = P.nblocks;
+  for (int b = 0; b <= P.nblocks && block_first_group_out; ++b) block_first_group_out[b] = P.blk_g0[b];
+  for (int b = 0; b < P.nblocks; ++b) {
+    if (block_room_first_out) block_room_first_out[b] = P.blk_rfirst[b];
+    if (block_room_last_out) block_room_last_out[b] = P.blk_rlast[b];
+  }
+  for (int r = 0; r < nrooms; ++r) {
+    if (room_first_block_out) room_first_block_out[r] = P.room_blo[r];
+    if (room_nblocks_out) room_nblocks_out[r] = P.room_nb[r];
+  }
+  return HS_OK;
+}
+
 int32_t hs_eval_session_begin(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_offsets, int32_t nrooms, int32_t allreduce, hs_eval_session** out) {
   HS_SLOCK(ctx);
   if (!out || !cloud || !room_offsets || nrooms < 1 || nrooms > HS_MAX_ROOMS) { ctx->err = "hs_eval_session_begin: bad arguments (1 <= nrooms <= 32)"; return HS_EINVAL; }

@@ -140,6 +140,13 @@ HS_API int32_t hs_eval_session_times(const hs_eval_session* s, int64_t seq, uint
 HS_API void* hs_eval_session_device_results(const hs_eval_session* s); /* device ring [256][nrooms x HS_REC] doubles */
 HS_API int32_t hs_eval_session_stop(hs_eval_session* s);
 HS_API int32_t hs_eval_session_end(hs_eval_session* s);
+/* The evaluation kernel's static partition of a cloud layout, host only: blocks own contiguous ranges of 4-point groups
+ * [first_group[b], first_group[b+1]); a block pays seg_cost groups (0 = default, < 0 = none) for every room boundary inside its
+ * range, or ends at the boundary.  block_room_first/last = the rooms with points in the block (last < first: none);
+ * room_first_block / room_nblocks = the blocks that deliver a partial record for the room.  Any output but nblocks may be NULL. */
+HS_API int32_t hs_eval_plan(int64_t n, const int64_t* room_offsets, int32_t nrooms, int32_t sm_count, int32_t seg_cost,
+                            int32_t* nblocks_out, int64_t* block_first_group_out, int32_t* block_room_first_out,
+                            int32_t* block_room_last_out, int32_t* room_first_block_out, int32_t* room_nblocks_out);
 /* host chain rule: (params, summed record) -> f, grad, counts */
 HS_API int32_t hs_cuboid_grad_from_sums(const double params[10], const double rec[HS_REC], double* f, double grad[10],
                                         int64_t counts[6]);

@@ -355,3 +355,63 @@ def test_bfgs_minimize_callback_entry_point(built_lib):
 
     with pytest.raises(HsError):
         F.bfgsMinimize(bad, np.zeros(4))
+
+
+def _eval_plan(n, offs, sm_count=148, seg_cost=0):
+    import ctypes as C
+
+    from housescan_b200 import _lib as L
+
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    nr = offs.size - 1
+    nb = C.c_int32()
+    g0 = np.zeros(257, np.int64)
+    rf, rl = np.zeros(256, np.int32), np.zeros(256, np.int32)
+    blo, nbr = np.zeros(nr, np.int32), np.zeros(nr, np.int32)
+    rc = L.load().hs_eval_plan(n, L.ptr(offs), nr, sm_count, seg_cost, C.byref(nb), L.ptr(g0), L.ptr(rf), L.ptr(rl), L.ptr(blo), L.ptr(nbr))
+    assert rc == 0
+    return nb.value, g0[: nb.value + 1], rf[: nb.value], rl[: nb.value], blo, nbr
+
+
+def test_eval_plan_partition_invariants(built_lib):
+    """The evaluation kernel's static partition (`hs_eval_plan`, host only).  Every 4-point group belongs to exactly one block, block
+    ranges are contiguous and ordered, a room's ticket count equals the number of blocks that hold points of it (rooms without
+    points take none - the bug the random-layout GPU test found), and a block that keeps a room boundary inside its range streams
+    fewer groups than a block without one."""
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        nrooms = int(rng.integers(1, 13))
+        scale = int(rng.choice([20, 3_000, 400_000, 9_000_000]))
+        sizes = rng.integers(0, scale, size=nrooms)
+        sizes[rng.random(nrooms) < 0.2] = 0
+        lead, trail = int(rng.integers(0, 9)), int(rng.integers(0, 9))
+        offs = np.concatenate([[0], np.cumsum(sizes)]) + lead
+        n = int(offs[-1]) + trail
+        if n == 0:
+            continue
+        nb, g0, rf, rl, blo, nbr = _eval_plan(n, offs, sm_count=int(rng.choice([1, 7, 148])))
+        G = (n + 3) // 4
+        assert g0[0] == 0 and g0[-1] == G and np.all(np.diff(g0) >= 0), (trial, g0)
+        holds = np.zeros((nb, nrooms), bool)
+        for b in range(nb):
+            p0, p1 = 4 * g0[b], min(4 * g0[b + 1], n)
+            for r in range(nrooms):
+                holds[b, r] = offs[r] < p1 and offs[r + 1] > p0 and offs[r + 1] > offs[r] and p1 > p0
+            rooms = np.flatnonzero(holds[b])
+            if rooms.size:
+                assert rf[b] == rooms[0] and rl[b] == rooms[-1], (trial, b)
+            else:
+                assert rl[b] < rf[b]
+        for r in range(nrooms):
+            blocks = np.flatnonzero(holds[:, r])
+            assert nbr[r] == blocks.size, (trial, r, nbr[r], blocks)
+            if blocks.size:
+                assert blo[r] == blocks[0] and np.array_equal(blocks, np.arange(blocks[0], blocks[0] + blocks.size))  # contiguous
+    # the apartment of the bench on one of eight GPUs: blocks with a boundary inside stream ~1536 groups fewer, nobody more than the target
+    per = 8_333_334
+    offs = np.clip(np.arange(13) * per, 0, 12_500_004)
+    nb, g0, rf, rl, blo, nbr = _eval_plan(12_500_004, offs)
+    sizes = np.diff(g0)
+    two = rl > rf
+    assert nb == 148 and two.sum() == 1
+    assert sizes[two][0] <= sizes[~two].max() - 1000 and sizes.max() - np.median(sizes) <= 16
