@@ -133,3 +133,6 @@ foreign import ccall safe "hs_write_ply_part_host" c_write_ply_part_host :: CStr
 -- the evaluation kernel's static partition of a cloud layout (host only; diagnostics)
 foreign import ccall unsafe "hs_eval_plan"
   c_eval_plan :: Int64 -> Ptr Int64 -> Int32 -> Int32 -> Int32 -> Ptr Int32 -> Ptr Int64 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> IO Int32
+-- the reference's optimiser (NMSimplex2) over a device-resident cloud, driven through an evaluation session
+foreign import ccall safe "hs_fit_cuboid_cloud_nm"
+  c_fit_cuboid_cloud_nm :: Ptr HsCtx -> Ptr HsCloud -> Ptr CDouble -> Ptr CDouble -> CDouble -> Int32 -> Ptr CDouble -> Ptr CDouble -> Ptr Int32 -> Ptr Int32 -> IO Int32

@@ -121,3 +121,33 @@ def bfgsMinimize(objective, x0, max_iter=200, gtol=1e-6):
     if rc:
         raise L.HsError(rc, "hs_bfgs_minimize")
     return out, f.value, it.value, ev.value
+
+
+def nmMinimize(objective, x0, step, eps=1e-8, maxit=2000):
+    """The library's Nelder-Mead (`hs_nm_minimize`: GSL nmsimplex2's rules as `minimize NMSimplex2 eps maxit x0 f step` drives them,
+    FitCuboidBFGS.hs:184,201,233) over a Python objective `x -> f`.  -> (x, f, iterations, evaluations)"""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    step = np.ascontiguousarray(step, dtype=np.float64)
+    n = x0.size
+    CB = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double))
+
+    def cb(_user, xp):
+        try:
+            return float(objective(np.ctypeslib.as_array(xp, shape=(n,)).copy()))
+        except Exception:  # noqa: BLE001
+            return float("nan")
+
+    cbk = CB(cb)
+    out = np.zeros(n, np.float64)
+    f, it, ev = C.c_double(), C.c_int32(), C.c_int32()
+    rc = L.load().hs_nm_minimize(C.cast(cbk, C.c_void_p), None, L.ptr(x0), L.ptr(step), n, eps, maxit, L.ptr(out), C.byref(f), C.byref(it), C.byref(ev))
+    if rc:
+        raise L.HsError(rc, "hs_nm_minimize")
+    return out, f.value, it.value, ev.value
+
+
+def fitCuboidToCloudNM(cloud, initial, step, eps=1e-8, maxit=2000):
+    """The reference's optimiser over the whole room cloud: NMSimplex2 on f(params) = sum of squared distances to the nearest wall,
+    every evaluation one pass of the resident session kernel (initial simplex and shrink steps posted as batches).
+    -> (params, f, iterations, evaluations)"""
+    return cloud.ctx.fit_cuboid_cloud_nm(cloud, initial, step, eps, maxit)

@@ -60,6 +60,8 @@ SIGNATURES = {
     "hs_eval_session_stop": (i32, [vp]),
     "hs_eval_session_end": (i32, [vp]),
     "hs_eval_plan": (i32, [i64, vp, i32, i32, i32, C.POINTER(i32), vp, vp, vp, vp, vp]),
+    "hs_nm_minimize": (i32, [vp, vp, vp, vp, i32, f64, i32, vp, C.POINTER(f64), C.POINTER(i32), C.POINTER(i32)]),
+    "hs_fit_cuboid_cloud_nm": (i32, [vp, vp, vp, vp, f64, i32, vp, C.POINTER(f64), C.POINTER(i32), C.POINTER(i32)]),
     "hs_bfgs_minimize": (i32, [vp, vp, vp, i32, i32, f64, vp, C.POINTER(f64), C.POINTER(i32), C.POINTER(i32)]),
     "hs_cuboid_grad_from_sums": (i32, [vp, vp, C.POINTER(f64), vp, vp]),
     "hs_plane_sums": (i32, [vp, vp, vp, i32, vp, i32, vp]),

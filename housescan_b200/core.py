@@ -362,6 +362,17 @@ class Context:
         return out, f.value, it.value, ev.value
 
 
+    def fit_cuboid_cloud_nm(self, cloud: Cloud, init, step, eps=1e-8, maxit=2000):
+        """the reference's optimiser (NMSimplex2, FitCuboidBFGS.hs:184,201,233) over the cloud objective, through a session"""
+        p0, st = as_f64(init, (10,)), as_f64(step, (10,))
+        out = np.empty(10, np.float64)
+        f = C.c_double()
+        it = C.c_int32()
+        ev = C.c_int32()
+        self._chk(self.lib.hs_fit_cuboid_cloud_nm(self.h, cloud.h, ptr(p0), ptr(st), eps, maxit, ptr(out), C.byref(f), C.byref(it), C.byref(ev)))
+        return out, f.value, it.value, ev.value
+
+
 # ---- host-only helpers (no device needed) -------------------------------------------------------------------
 def write_ply_begin(path: str, n_total: int, has_rgb: bool = False) -> None:
     """create the .ply with its header at the final size (ONE caller, before any `write_ply_part`)"""

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <limits>
 #include <unistd.h>
 
 #include "../host/hs_host.hpp"
@@ -1117,6 +1118,62 @@ int32_t hs_bfgs_minimize(hs_objective_fn eval, void* user, const double* x0, int
   if (f_out) *f_out = r.f;
   if (iters) *iters = r.iters;
   if (evals) *evals = r.evals;
+  return HS_OK;
+}
+
+int32_t hs_nm_minimize(hs_value_fn value, void* user, const double* x0, const double* step, int32_t n, double eps, int32_t maxit, double* x_out,
+                       double* f_out, int32_t* iters, int32_t* evals) {
+  if (!value || !x0 || !step || !x_out || n < 1 || n > 4096) return HS_EINVAL;
+  auto f = [&](const std::vector<double>& x) { return value(user, x.data()); };
+  int ev = 0;
+  hs::NMResult r = hs::nm_simplex2(f, std::vector<double>(x0, x0 + n), std::vector<double>(step, step + n), eps > 0 ? eps : 1e-8,
+                                   maxit > 0 ? maxit : 2000, false, nullptr, &ev);
+  for (int i = 0; i < n; ++i) x_out[i] = r.x[i];
+  if (f_out) *f_out = r.fval;
+  if (iters) *iters = r.iters;
+  if (evals) *evals = ev;
+  return HS_OK;
+}
+
+int32_t hs_fit_cuboid_cloud_nm(hs_ctx* ctx, const hs_cloud* cloud, const double init[10], const double step[10], double eps, int32_t maxit,
+                               double params_out[10], double* f_out, int32_t* iters, int32_t* evals) {
+  if (!ctx) return HS_EINVAL;
+  if (!cloud || !init || !step || !params_out) { ctx->err = "hs_fit_cuboid_cloud_nm: bad arguments"; return HS_EINVAL; }
+  hs_eval_session* sess = nullptr;
+  const int64_t off[2] = {0, cloud->n};
+  if (int32_t rc = hs_eval_session_begin(ctx, cloud, off, 1, 0, &sess)) return rc;
+  int32_t last_rc = HS_OK;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  auto f = [&](const std::vector<double>& x) {
+    double rec[HS_REC];
+    if (last_rc == HS_OK) last_rc = hs_eval_session_eval(sess, x.data(), rec);
+    return last_rc == HS_OK ? rec[0] : nan;
+  };
+  int64_t posted = 0;
+  hs::NMBatch batch = [&](const std::vector<std::vector<double>>& xs, std::vector<double>& ys) {
+    std::vector<double> flat;
+    for (auto& x : xs) flat.insert(flat.end(), x.begin(), x.end());
+    if (last_rc == HS_OK) last_rc = hs_eval_session_post(sess, flat.data(), static_cast<int32_t>(xs.size()));
+    for (size_t q = 0; q < xs.size(); ++q) {
+      double rec[HS_REC];
+      if (last_rc == HS_OK) last_rc = hs_eval_session_wait(sess, posted + static_cast<int64_t>(q), rec);
+      ys[q] = last_rc == HS_OK ? rec[0] : nan;
+    }
+    posted += static_cast<int64_t>(xs.size());
+  };
+  // evaluations posted one by one go through f -> hs_eval_session_eval, which posts and waits: keep `posted` in step
+  auto f_counted = [&](const std::vector<double>& x) { const double v = f(x); ++posted; return v; };
+  int ev = 0;
+  hs::NMResult r = hs::nm_simplex2(f_counted, std::vector<double>(init, init + 10), std::vector<double>(step, step + 10), eps > 0 ? eps : 1e-8,
+                                   maxit > 0 ? maxit : 2000, false, &batch, &ev);
+  const std::string msg = ctx->err;
+  const int32_t rc_end = hs_eval_session_end(sess);
+  if (last_rc != HS_OK) { ctx->err = msg; return last_rc; }
+  if (rc_end != HS_OK) return rc_end;
+  for (int i = 0; i < 10; ++i) params_out[i] = r.x[i];
+  if (f_out) *f_out = r.fval;
+  if (iters) *iters = r.iters;
+  if (evals) *evals = ev;
   return HS_OK;
 }
 

@@ -154,13 +154,16 @@ static void point_mean8(const double pts[24], double c[3]) {  // FitCuboidBFGS.h
 // (FitCuboidBFGS.hs:184,201,233): reflect (-1), expand (-2), contract (0.5), else shrink about the best corner;
 // size = rms distance of the corners to their centre, maintained incrementally; stop when size < eps or maxit.
 // ------------------------------------------------------------------------------------------------
-NMResult nm_simplex2(const std::function<double(const std::vector<double>&)>& f, const std::vector<double>& x0,
-                     const std::vector<double>& step, double eps, int maxit, bool keep_path) {
+NMResult nm_simplex2(const std::function<double(const std::vector<double>&)>& f_in, const std::vector<double>& x0,
+                     const std::vector<double>& step, double eps, int maxit, bool keep_path, const NMBatch* batch, int* evals_out) {
   const int n = static_cast<int>(x0.size()), P = n + 1;
+  int evals = 0;
+  auto f = [&](const std::vector<double>& x) { ++evals; return f_in(x); };
   std::vector<std::vector<double>> X(P, x0);
   std::vector<double> y(P), center(n, 0.0);
-  y[0] = f(x0);
-  for (int i = 0; i < n; ++i) { X[i + 1][i] += step[i]; y[i + 1] = f(X[i + 1]); }
+  for (int i = 0; i < n; ++i) X[i + 1][i] += step[i];
+  if (batch) { (*batch)(X, y); evals += P; }  // the n + 1 corners are independent
+  else for (int i = 0; i < P; ++i) y[i] = f(X[i]);
   auto recompute = [&]() {
     std::fill(center.begin(), center.end(), 0.0);
     for (auto& x : X) for (int k = 0; k < n; ++k) center[k] += x[k];
@@ -211,11 +214,20 @@ NMResult nm_simplex2(const std::function<double(const std::vector<double>&)>& f,
       double val2 = corner_move(0.5, hi, xc2);
       if (std::isfinite(val2) && val2 <= y[hi]) update_point(hi, xc2, val2);
       else {
+        std::vector<std::vector<double>> moved;
+        std::vector<int> which;
         for (int i = 0; i < P; ++i)
           if (i != lo) {
             for (int k = 0; k < n; ++k) X[i][k] = 0.5 * (X[i][k] + X[lo][k]);
-            y[i] = f(X[i]);
+            if (batch) { moved.push_back(X[i]); which.push_back(i); }
+            else y[i] = f(X[i]);
           }
+        if (batch) {  // the n shrunken corners are independent
+          std::vector<double> vals(moved.size());
+          (*batch)(moved, vals);
+          evals += static_cast<int>(moved.size());
+          for (size_t q = 0; q < which.size(); ++q) y[which[q]] = vals[q];
+        }
         S2 = recompute();
       }
     } else {
@@ -234,6 +246,7 @@ NMResult nm_simplex2(const std::function<double(const std::vector<double>&)>& f,
   res.x = X[lo];
   res.fval = y[lo];
   res.iters = it;
+  if (evals_out) *evals_out = evals;
   return res;
 }
 

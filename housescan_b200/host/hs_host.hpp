@@ -23,8 +23,12 @@ struct NMResult {
   int iters = 0;
   std::vector<double> path;  // rows of [iter, f, size, x...]
 };
+// `batch` (optional): evaluates several independent points at once (the initial simplex, a shrink step) - same values, same order
+// as calling f on each; an evaluation session runs such a batch back to back on the device.  evals_out counts objective values.
+using NMBatch = std::function<void(const std::vector<std::vector<double>>&, std::vector<double>&)>;
 NMResult nm_simplex2(const std::function<double(const std::vector<double>&)>& f, const std::vector<double>& x0,
-                     const std::vector<double>& step, double eps, int maxit, bool keep_path);
+                     const std::vector<double>& step, double eps, int maxit, bool keep_path, const NMBatch* batch = nullptr,
+                     int* evals_out = nullptr);
 
 struct FitResult {
   std::vector<double> params;

@@ -275,6 +275,16 @@ HS_API int32_t hs_fit_cuboid_cloud_bfgs(hs_ctx* ctx, const hs_cloud* cloud, cons
 typedef int32_t (*hs_objective_fn)(void* user, const double* x, double* f, double* grad);
 HS_API int32_t hs_bfgs_minimize(hs_objective_fn eval, void* user, const double* x0, int32_t n, int32_t max_iter, double gtol,
                                 double* x_out, double* f_out, int32_t* iters, int32_t* evals);
+/* The reference's own optimiser over a caller-supplied objective: Nelder-Mead with GSL nmsimplex2's update rules as hmatrix's
+ * `minimize NMSimplex2 eps maxit x0 f step` drives it (FitCuboidBFGS.hs:184,201,233).  value(user, x) returns the objective. */
+typedef double (*hs_value_fn)(void* user, const double* x);
+HS_API int32_t hs_nm_minimize(hs_value_fn value, void* user, const double* x0, const double* step, int32_t n, double eps,
+                              int32_t maxit, double* x_out, double* f_out, int32_t* iters, int32_t* evals);
+/* ... and over a device-resident room cloud: f(params) = sum of squared distances to the nearest wall (the objective of
+ * hs_cuboid_residual_grad), evaluated by ONE resident kernel (an evaluation session); the independent evaluations of the initial
+ * simplex and of every shrink step are posted together and run back to back.  step[10] = initial simplex sizes. */
+HS_API int32_t hs_fit_cuboid_cloud_nm(hs_ctx* ctx, const hs_cloud* cloud, const double init[10], const double step[10], double eps,
+                                      int32_t maxit, double params_out[10], double* f_out, int32_t* iters, int32_t* evals);
 /* TranslationOptimizer.lstSqDistancesI (TranslationOptimizer.hs:48-72) on bijected indices; HS_ESINGULAR => Nothing */
 HS_API int32_t hs_lstsq_distances(const int32_t* i_idx, const int32_t* j_idx, const double* d, int32_t m, int32_t n_nodes,
                                   double* pos_out, double* rmse_out);

@@ -597,6 +597,24 @@ def test_bfgs_fit_matches_the_same_optimiser_over_the_oracle_objective(ctx):
     assert np.max(np.abs(p_g - p_o) / np.maximum(np.abs(p_o), 1e-2)) < 1e-6, (p_g, p_o, it_g, it_o)
 
 
+def test_nm_fit_over_the_cloud_matches_the_same_simplex_over_the_oracle_objective(ctx):
+    """The reference's optimiser (NMSimplex2) over the cloud objective through a session (`hs_fit_cuboid_cloud_nm`: initial simplex
+    and shrink steps posted as batches) against the identical simplex (`hs_nm_minimize`) over the oracle's f on the CPU."""
+    from housescan_b200 import FitCuboidBFGS as F
+
+    true = np.concatenate([[0.4, -0.3, 3.5], [4.0, 2.5, 3.0], synth.quat_from_axis_angle([0.2, 1, 0.1], 12.0)])
+    xyz, _ = synth.cuboid_room_cloud(60_000, true, sigma=0.003, seed=23)
+    init = true + np.concatenate([[0.05, -0.04, 0.03], [0.08, -0.06, 0.05], 0.02 * np.array([1, -1, 1, -1])])
+    step = np.array([0.01, 0.01, 0.01, 0.1, 0.1, 0.1, 0.02, 0.02, 0.02, 0.02])
+    p_g, f_g, it_g, ev_g = ctx.fit_cuboid_cloud_nm(ctx.upload(xyz), init, step, 1e-7, 400)
+    p_o, f_o, it_o, ev_o = F.nmMinimize(lambda x: O.cuboid_residual_grad(xyz, x)[0], init, step, 1e-7, 400)
+    f0 = O.cuboid_residual_grad(xyz, init)[0]
+    assert f_g < 0.2 * f0 and abs(f_g - f_o) <= 1e-3 * f_o, (f_g, f_o, f0, it_g, it_o)
+    assert ev_g >= it_g + 11  # the initial simplex alone is 11 evaluations
+    f_check = O.cuboid_residual_grad(xyz, p_g)[0]  # the GPU's end state under the oracle's objective
+    assert abs(f_check - f_g) <= 1e-6 * f_g
+
+
 # ------------------------------------------------------------------ six planes that are NOT a cuboid's antiparallel pairs
 def test_six_unpaired_planes_take_the_generic_path(ctx, room_small):
     """K == 6 picks the unrolled kernels; the shared-dot-product shortcut applies only when planes 2j / 2j+1 have exactly negated

@@ -415,3 +415,24 @@ def test_eval_plan_partition_invariants(built_lib):
     two = rl > rf
     assert nb == 148 and two.sum() == 1
     assert sizes[two][0] <= sizes[~two].max() - 1000 and sizes.max() - np.median(sizes) <= 16
+
+
+def test_nm_minimize_callback_entry_point_matches_the_oracle_simplex(built_lib, oracle_lib):
+    """`hs_nm_minimize` = the library's NMSimplex2 over a caller-supplied objective: the same end state as the oracle's restatement
+    of GSL's nmsimplex2 on the reference's own fitting objective (errfun over 8 corners, FitCuboidBFGS.hs:51-66) and on Rosenbrock;
+    iteration counts equal (same rules, same comparisons)."""
+    import oracle as O
+    from housescan_b200 import FitCuboidBFGS as F
+
+    box = O.cuboid_from_params(np.array([0.3, -0.2, 1.0, 2.0, 1.0, 3.0, 0.9, 0.1, -0.2, 0.3]))
+    x0 = np.array([0.0, 0.0, 0.0, 1.5, 1.5, 1.5, 0.1, 0.1, 0.1, 0.1])
+    step = np.array([0.01, 0.01, 0.01, 0.15, 0.15, 0.15, 0.1, 0.1, 0.1, 0.1])
+    obj = lambda p: O.errfun(box, p)
+    x_o, path = O.nm_simplex2(obj, x0, step, 1e-8, 600)
+    x_g, f_g, it_g, ev_g = F.nmMinimize(obj, x0, step, 1e-8, 600)
+    assert it_g == int(path[-1][0]) and ev_g > it_g
+    assert np.allclose(x_g, x_o, rtol=0, atol=1e-9) and abs(f_g - obj(x_o)) <= 1e-12 + 1e-9 * abs(f_g)
+    rosen = lambda x: (1 - x[0]) ** 2 + 100 * (x[1] - x[0] ** 2) ** 2
+    x_o, path = O.nm_simplex2(rosen, np.array([-1.2, 1.0]), np.array([0.5, 0.5]), 1e-10, 2000)
+    x_g, f_g, it_g, _ = F.nmMinimize(rosen, [-1.2, 1.0], [0.5, 0.5], 1e-10, 2000)
+    assert it_g == int(path[-1][0]) and np.allclose(x_g, x_o, atol=1e-9) and np.allclose(x_g, [1.0, 1.0], atol=1e-6)
