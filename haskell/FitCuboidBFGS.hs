@@ -17,6 +17,7 @@ module FitCuboidBFGS
   -- additive: the objective and the fit over a device-resident room cloud
   , cuboidResidualGrad
   , fitCuboidToCloudBFGS
+  , fitCuboidToCloudNM
   , withCloudObjective
   ) where
 
@@ -104,3 +105,13 @@ fitCuboidToCloudBFGS :: Ctx -> DeviceCloud -> [Double] -> IO ([Double], Int, Dou
 fitCuboidToCloudBFGS ctx dc initial = withDoubles initial $ \pin -> allocaArray 10 $ \pout -> alloca $ \pf -> alloca $ \pit -> do
   check ctx =<< withCtxPtr ctx (\c -> withCloudPtr dc $ \pc -> c_fit_cuboid_cloud_bfgs c pc pin 200 1e-6 pout pf pit nullPtr)
   (,,) <$> peekDoubles 10 pout <*> (fromIntegral <$> peek pit) <*> (realToFrac <$> (peek pf :: IO CDouble))
+
+-- | the reference's own optimiser over the whole room cloud: `minimize NMSimplex2 eps maxit` on the device objective; the library
+-- posts the 11 corners of the initial simplex (and the 10 of every shrink step) to the session as one batch.
+-- (params, iterations, f)
+fitCuboidToCloudNM :: Ctx -> DeviceCloud -> [Double] -> [Double] -> Double -> Int -> IO ([Double], Int, Double)
+fitCuboidToCloudNM ctx dc initial sizes eps maxIt =
+  withDoubles initial $ \pin -> withDoubles sizes $ \pst -> allocaArray 10 $ \pout -> alloca $ \pf -> alloca $ \pit -> do
+    check ctx =<< withCtxPtr ctx (\c -> withCloudPtr dc $ \pc ->
+      c_fit_cuboid_cloud_nm c pc pin pst (realToFrac eps) (fromIntegral maxIt) pout pf pit nullPtr)
+    (,,) <$> peekDoubles 10 pout <*> (fromIntegral <$> peek pit) <*> (realToFrac <$> (peek pf :: IO CDouble))
