@@ -132,6 +132,8 @@ int32_t hs_ctx_destroy(hs_ctx* ctx) {
   if (ctx->d_mailbox) cudaFree(ctx->d_mailbox);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  for (auto& e : ctx->ps_ev) if (e) cudaEventDestroy(e);
+  for (auto& st : ctx->ps_aux) if (st) cudaStreamDestroy(st);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return HS_OK;
@@ -509,12 +511,44 @@ int32_t hs_plane_sums(hs_ctx* ctx, const hs_cloud* cloud, const int64_t* room_of
   if (total > static_cast<size_t>(HS_MAX_ROOMS) * HS_REC) HS_CUDA_TRY(ctx, tmp.alloc(&d_out, total * sizeof(double)));
   int32_t rc = HS_OK;
   HS_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, total * sizeof(double), ctx->stream));
+  // one launch per room (the planes ride in the kernel's constant bank), but three lanes: the ctx stream and two helper streams,
+  // each with its own partial-record region and ticket, rooms round-robin - the tail of a launch (last blocks, last-block sums)
+  // overlaps the next room's start instead of idling the GPU
+  const int lanes = nrooms >= 3 ? 3 : 1;
+  const size_t region = ((static_cast<size_t>(ctx->sm_count) * 2 + 8) * K * HS_PS * sizeof(double) + 255) & ~static_cast<size_t>(255);
+  cudaStream_t lane_stream[3] = {ctx->stream, nullptr, nullptr};
+  if (lanes > 1) {
+    if (!ctx->ps_aux[0]) {
+      for (int i = 0; i < 2; ++i) HS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->ps_aux[i], cudaStreamNonBlocking));
+      for (int i = 0; i < 3; ++i) HS_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ps_ev[i], cudaEventDisableTiming));
+    }
+    if (int32_t rc2 = hs_ensure_scratch(ctx, 3 * region)) return rc2;  // before any lane is in flight: growing would free what a lane uses
+    lane_stream[1] = ctx->ps_aux[0];
+    lane_stream[2] = ctx->ps_aux[1];
+    HS_CUDA_TRY(ctx, cudaEventRecord(ctx->ps_ev[0], ctx->stream));  // the helpers start behind the memset (and whatever precedes it)
+    HS_CUDA_TRY(ctx, cudaStreamWaitEvent(lane_stream[1], ctx->ps_ev[0], 0));
+    HS_CUDA_TRY(ctx, cudaStreamWaitEvent(lane_stream[2], ctx->ps_ev[0], 0));
+  }
+  const cudaStream_t main_stream = ctx->stream;
   for (int r = 0; r < nrooms && rc == HS_OK; ++r) {
     if (room_offsets[r] > room_offsets[r + 1]) { ctx->err = "hs_plane_sums: room offsets must be non-decreasing"; rc = HS_EINVAL; break; }
     PlaneTable t;
     if ((rc = fill_plane_table(ctx, planes + static_cast<size_t>(r) * K * 4, K, HS_MAX_PLANES, t, "hs_plane_sums")) != HS_OK) break;
     if (room_offsets[r] == room_offsets[r + 1]) continue;  // stays zero
+    const int lane = lanes > 1 ? r % 3 : 0;
+    ctx->stream = lane_stream[lane];
+    ctx->ps_scratch_off = lanes > 1 ? lane * region : 0;
+    ctx->ps_ticket_off = lanes > 1 ? 40 + lane : 0;
     rc = launch_plane_sums(ctx, cloud->d, room_offsets[r], room_offsets[r + 1], t, d_out + static_cast<size_t>(r) * K * HS_PS);
+  }
+  ctx->stream = main_stream;
+  ctx->ps_scratch_off = 0;
+  ctx->ps_ticket_off = 0;
+  if (lanes > 1) {  // join: the ctx stream continues behind both helpers (also on an error path: nothing may still run when we return)
+    for (int i = 1; i < 3; ++i) {
+      cudaEventRecord(ctx->ps_ev[i], lane_stream[i]);
+      cudaStreamWaitEvent(main_stream, ctx->ps_ev[i], 0);
+    }
   }
   if (rc == HS_OK) rc = copy_d2h_sync(ctx, out, d_out, total * sizeof(double));
   return rc;

@@ -55,6 +55,12 @@ struct hs_ctx {
   bool peer_local = false;           // mailboxes of a same-process group: addressed directly, nothing to close
   uint32_t* h_status = nullptr;      // mapped pinned word the kernels raise (HS_ENCCL on a peer timeout); d_status is its device alias
   uint32_t* d_status = nullptr;
+  // per-plane sums of several rooms: the rooms' launches go round-robin over three lanes (the ctx stream + two helpers) with their own
+  // partial-record regions and tickets, so that the tail of one room's launch overlaps the start of the next room's
+  cudaStream_t ps_aux[2] = {nullptr, nullptr};
+  cudaEvent_t ps_ev[3] = {nullptr, nullptr, nullptr};
+  size_t ps_scratch_off = 0;         // byte offset of the current lane's partial-record region inside d_scratch
+  int ps_ticket_off = 0;             // word offset of the current lane's ticket inside d_ticket (0 = the shared one)
   hs_eval_state* eval = nullptr;     // evaluation kernel state (lazily created)
   hs_eval_session* session = nullptr;  // open evaluation session: it owns the stream until it ends
   std::mutex mu;

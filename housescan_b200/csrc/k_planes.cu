@@ -277,8 +277,53 @@ k_plane_sums(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __grid
 // FMA is exact, only the short partial sums are rounded to Float), and are then added into per-thread Doubles that live in shared
 // memory, so the registers hold the 10 K chains and four points in flight instead of 9 K Doubles.  Points are read as 4-point
 // groups (3 x LDG.128); the ragged head and tail of the range (room offsets are arbitrary) are taken one point per thread.
+// One axis of a cuboid room's wall pair (K == 6, antiparallel pairs).  The axis wins if its nearer wall is the first minimum of the
+// six |distances| (strict <, ties keep the lower wall index: the scan order of nearest_plane); inside the pair the - wall wins only
+// if it is strictly nearer.  The two walls' predicates come straight from the comparisons (no index, no six setp.eq), every wall
+// accumulates its own signed residual (no select), and an axis is one PTX block of 30 operands.
+//   axis 0: not (a1 < a0) and not (a2 < min(a0, a1));   axis 1: (a1 < a0) and not (a2 < min(a0, a1));   axis 2: a2 < min(a0, a1)
+#define HS_PS_PAIR_BODY(E_SETUP)                                                                                                   \
+  asm("{\n .reg .pred E2, E, Wp, Wm;\n .reg .f32 a01;\n"                                                                          \
+      " min.f32 a01, %27, %28;\n setp.lt.f32 E2, %29, a01;\n" E_SETUP                                                              \
+      " setp.lt.and.f32 Wm, %26, %25, E;\n setp.geu.and.f32 Wp, %26, %25, E;\n"                                                    \
+      "@Wp add.rn.f32 %0, %0, 0f3F800000;\n @Wp add.rn.f32 %1, %1, %23;\n @Wp fma.rn.f32 %2, %23, %23, %2;\n"                     \
+      "@Wp add.rn.f32 %3, %3, %20;\n @Wp add.rn.f32 %4, %4, %21;\n @Wp add.rn.f32 %5, %5, %22;\n"                                 \
+      "@Wp fma.rn.f32 %6, %23, %20, %6;\n @Wp fma.rn.f32 %7, %23, %21, %7;\n @Wp fma.rn.f32 %8, %23, %22, %8;\n"                  \
+      "@Wp max.f32 %9, %9, %25;\n"                                                                                                 \
+      "@Wm add.rn.f32 %10, %10, 0f3F800000;\n @Wm add.rn.f32 %11, %11, %24;\n @Wm fma.rn.f32 %12, %24, %24, %12;\n"               \
+      "@Wm add.rn.f32 %13, %13, %20;\n @Wm add.rn.f32 %14, %14, %21;\n @Wm add.rn.f32 %15, %15, %22;\n"                           \
+      "@Wm fma.rn.f32 %16, %24, %20, %16;\n @Wm fma.rn.f32 %17, %24, %21, %17;\n @Wm fma.rn.f32 %18, %24, %22, %18;\n"            \
+      "@Wm max.f32 %19, %19, %26;\n}\n"                                                                                            \
+      : "+f"(ap[0]), "+f"(ap[1]), "+f"(ap[2]), "+f"(ap[3]), "+f"(ap[4]), "+f"(ap[5]), "+f"(ap[6]), "+f"(ap[7]), "+f"(ap[8]), "+f"(mxp),  \
+        "+f"(am[0]), "+f"(am[1]), "+f"(am[2]), "+f"(am[3]), "+f"(am[4]), "+f"(am[5]), "+f"(am[6]), "+f"(am[7]), "+f"(am[8]), "+f"(mxm)   \
+      : "f"(x), "f"(y), "f"(z), "f"(sp), "f"(rm), "f"(asp), "f"(arm), "f"(a0), "f"(a1), "f"(a2))
+template <int AXIS>
+__device__ __forceinline__ void ps_add_pair(float (&ap)[9], float& mxp, float (&am)[9], float& mxm, float x, float y, float z, float sp, float rm,
+                                            float asp, float arm, float a0, float a1, float a2) {
+  if (AXIS == 0) HS_PS_PAIR_BODY(" setp.geu.and.f32 E, %28, %27, !E2;\n");
+  else if (AXIS == 1) HS_PS_PAIR_BODY(" setp.lt.and.f32 E, %28, %27, !E2;\n");
+  else HS_PS_PAIR_BODY(" setp.lt.f32 E, %29, a01;\n");
+}
+#undef HS_PS_PAIR_BODY
+
 template <int K, bool PAIRED>
 __device__ __forceinline__ void ps_add(float (&a)[K][9], float (&mx)[K], const PlaneTable& tbl, const float4* __restrict__ spl, float x, float y, float z) {
+  if constexpr (K == 6 && PAIRED) {
+    float sp[3], rm[3], asp[3], arm[3], aj[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {  // the very operations of nearest_plane's paired form: same bits, same winner
+      const float tj = __fadd_rn(__fadd_rn(__fmul_rn(tbl.pl[2 * j][0], x), __fmul_rn(tbl.pl[2 * j][1], y)), __fmul_rn(tbl.pl[2 * j][2], z));
+      sp[j] = __fsub_rn(tj, tbl.pl[2 * j][3]);
+      rm[j] = __fsub_rn(-tj, tbl.pl[2 * j + 1][3]);
+      asp[j] = fabsf(sp[j]);
+      arm[j] = fabsf(rm[j]);
+      aj[j] = fminf(asp[j], arm[j]);
+    }
+    ps_add_pair<0>(a[0], mx[0], a[1], mx[1], x, y, z, sp[0], rm[0], asp[0], arm[0], aj[0], aj[1], aj[2]);
+    ps_add_pair<1>(a[2], mx[2], a[3], mx[3], x, y, z, sp[1], rm[1], asp[1], arm[1], aj[0], aj[1], aj[2]);
+    ps_add_pair<2>(a[4], mx[4], a[5], mx[5], x, y, z, sp[2], rm[2], asp[2], arm[2], aj[0], aj[1], aj[2]);
+    return;
+  }
   float ab;
   const int kb = nearest_plane<K, PAIRED>(tbl, x, y, z, ab);
   const float4 nn = spl[kb];
@@ -393,7 +438,7 @@ k_plane_sums_f32(const float* __restrict__ xyz, int64_t i0, int64_t i1, const __
 // ------------------------------------------------------------------------------------------------------------------
 #define PSR_D 4                 // ring slots per warp
 #define PSR_TILE_BYTES 1536u    // 32 groups x 48 B
-#define PSR_FLUSH_TILES 16      // 64 points per lane between flushes
+#define PSR_FLUSH_TILES 64      // 256 points per lane between flushes (the chain length of the evaluation kernel)
 
 template <int K, bool PAIRED>
 __global__ void __launch_bounds__(HS_TPB, 2)
@@ -564,20 +609,21 @@ int32_t launch_plane_assign(hs_ctx* ctx, const float* xyz, int64_t n, const Plan
 template <int K>
 static int32_t launch_plane_sums_k(hs_ctx* ctx, const float* xyz, int64_t i0, int64_t i1, const PlaneTable& tbl, double* d_out) {
   const int nb = pick_blocks(ctx, i1 - i0, 4 * HS_TPB, 2);
-  if (int32_t rc = hs_ensure_scratch(ctx, static_cast<size_t>(nb) * K * HS_PS * sizeof(double))) return rc;
+  if (int32_t rc = hs_ensure_scratch(ctx, ctx->ps_scratch_off + static_cast<size_t>(nb) * K * HS_PS * sizeof(double))) return rc;
+  unsigned int* ticket = ctx->d_ticket + ctx->ps_ticket_off;  // lane of hs_plane_sums (0: the shared ticket)
   if constexpr (K <= 6) {
     if (ctx->modes[HS_MODE_PS_KERNEL] == 0 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {  // ring form
       constexpr int NW = HS_TPB / 32;
       const int dsm = NW * PSR_D * static_cast<int>(PSR_TILE_BYTES) + NW * PSR_D * 8 + NW * K * 9 * 8 + NW * 64 * 4 + NW * 8 * 4;
       const int64_t ngroups = (i1 >> 2) - ((i0 + 3) >> 2);
       const int64_t gpb = ngroups > 0 ? (ngroups + nb - 1) / nb : 1;
-      double* part = reinterpret_cast<double*>(ctx->d_scratch);
+      double* part = reinterpret_cast<double*>(ctx->d_scratch + ctx->ps_scratch_off);
       if (K == 6 && tbl.paired) {
         HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_ring<K, (K == 6)>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
-        k_plane_sums_ring<K, (K == 6)><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, gpb, part, ctx->d_ticket, d_out);
+        k_plane_sums_ring<K, (K == 6)><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, gpb, part, ticket, d_out);
       } else {
         HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_ring<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
-        k_plane_sums_ring<K, false><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, gpb, part, ctx->d_ticket, d_out);
+        k_plane_sums_ring<K, false><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, gpb, part, ticket, d_out);
       }
       ctx->launches++;
       HS_CUDA_TRY(ctx, cudaGetLastError());
@@ -585,20 +631,20 @@ static int32_t launch_plane_sums_k(hs_ctx* ctx, const float* xyz, int64_t i0, in
     }
     if (ctx->modes[HS_MODE_PS_KERNEL] != 1 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
       const int dsm = K * 9 * HS_TPB * static_cast<int>(sizeof(double));
-      double* part = reinterpret_cast<double*>(ctx->d_scratch);
+      double* part = reinterpret_cast<double*>(ctx->d_scratch + ctx->ps_scratch_off);
       if (K == 6 && tbl.paired) {
         HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_f32<K, (K == 6)>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
-        k_plane_sums_f32<K, (K == 6)><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, part, ctx->d_ticket, d_out);
+        k_plane_sums_f32<K, (K == 6)><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, part, ticket, d_out);
       } else {
         HS_CUDA_TRY(ctx, cudaFuncSetAttribute(k_plane_sums_f32<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm));
-        k_plane_sums_f32<K, false><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, part, ctx->d_ticket, d_out);
+        k_plane_sums_f32<K, false><<<nb, HS_TPB, dsm, ctx->stream>>>(xyz, i0, i1, tbl, part, ticket, d_out);
       }
       ctx->launches++;
       HS_CUDA_TRY(ctx, cudaGetLastError());
       return HS_OK;
     }
   }
-  k_plane_sums<K><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, i0, i1, tbl, reinterpret_cast<double*>(ctx->d_scratch), ctx->d_ticket, d_out);
+  k_plane_sums<K><<<nb, HS_TPB, 0, ctx->stream>>>(xyz, i0, i1, tbl, reinterpret_cast<double*>(ctx->d_scratch + ctx->ps_scratch_off), ticket, d_out);
   ctx->launches++;
   HS_CUDA_TRY(ctx, cudaGetLastError());
   return HS_OK;
